@@ -1,0 +1,26 @@
+// C-ABI entry points for the convolution layer primitive (see include/caesar_b200.h).
+#include "../../include/caesar_b200.h"
+#include "conv.cuh"
+#include "common.h"
+
+namespace cy { int conv_block_n(int cout); }
+
+extern "C" int cy_conv_block_n(int cout) { return cy::conv_block_n(cout); }
+
+extern "C" int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ctot, int in_coff, int cin,
+                              const void* w, const float* bias, int cout, int cout_pad, int ksize, int stride,
+                              void* out, int out_ctot, int out_coff, int out_f32, const void* res, int res_ctot,
+                              int res_coff, int act, uintptr_t stream) {
+    cy::ConvDesc d;
+    d.in = (const __nv_bfloat16*)in; d.in_ctot = in_ctot; d.in_coff = in_coff; d.cin = cin;
+    d.B = B; d.Hin = Hin; d.Win = Win; d.ksize = ksize; d.stride = stride;
+    d.w = (const __nv_bfloat16*)w; d.cout_pad = cout_pad; d.bias = bias; d.cout = cout;
+    d.out = out; d.out_ctot = out_ctot; d.out_coff = out_coff; d.out_f32 = out_f32;
+    d.res = (const __nv_bfloat16*)res; d.res_ctot = res_ctot; d.res_coff = res_coff; d.act = act;
+    cy::ConvPlan plan;
+    char err[256];
+    if (cy::conv_make_plan(d, &plan, err, sizeof(err)) != 0) return cy::set_error(CY_ERR_INVALID, "%s", err);
+    int r = cy::conv_launch(plan, (cudaStream_t)stream);
+    if (r != 0) return cy::set_error(CY_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)r));
+    return CY_OK;
+}

@@ -1,0 +1,58 @@
+"""tcgen05 implicit-GEMM conv vs a torch fp32 reference of the same op (bf16-rounded operands)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(B, H, W, cin, cout, k, s, act, res, out_f32, in_extra=0, out_extra=0, seed=0):
+    from caesar_yolo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = torch.device("cuda:0")
+    in_ctot = cin + in_extra
+    in_coff = in_extra
+    x_full = (torch.randn(B, H, W, in_ctot, generator=g) * 1.0).to(torch.bfloat16).to(dev)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(cout, generator=g) * 0.1
+    Ho, Wo = H // s, W // s
+    out_ctot = (cout + 7) // 8 * 8 + out_extra
+    out_coff = out_extra
+    out = torch.full((B, Ho, Wo, out_ctot), 7.0, dtype=torch.float32 if out_f32 else torch.bfloat16, device=dev)
+    r = None
+    if res:
+        r = torch.randn(B, Ho, Wo, cout, generator=g).to(torch.bfloat16).to(dev)
+    wp, bp = ops.pack_conv_weight(w, b, dev)
+    ops.conv2d_nhwc(x_full, in_coff, cin, wp, bp, cout, k, s, out, out_coff, act=act, res=r, res_coff=0)
+    torch.cuda.synchronize()
+    # reference
+    xr = x_full[..., in_coff:in_coff + cin].float().permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(xr, w.float().to(dev), b.to(dev), stride=s, padding=k // 2)
+    if act:
+        y = torch.nn.functional.silu(y)
+    if res:
+        y = y + r.float().permute(0, 3, 1, 2)
+    y = y.permute(0, 2, 3, 1)
+    got = out[..., out_coff:out_coff + cout].float()
+    err = (got - y).abs().max().item()
+    tol = 2e-3 if out_f32 else 3e-2
+    assert err < tol * max(1.0, y.abs().max().item()), (err, y.abs().max().item())
+    if out_extra:
+        assert (out[..., :out_coff] == 7.0).all()  # untouched neighbouring slice
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=2, H=16, W=16, cin=64, cout=64, k=1, s=1, act=True, res=False, out_f32=False),
+    dict(B=2, H=16, W=16, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False),
+    dict(B=3, H=20, W=20, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=2, H=40, W=40, cin=64, cout=128, k=3, s=2, act=True, res=False, out_f32=False),
+    dict(B=1, H=80, W=40, cin=256, cout=256, k=3, s=1, act=True, res=False, out_f32=False, in_extra=64, out_extra=128),
+    dict(B=5, H=20, W=10, cin=320, cout=512, k=1, s=1, act=True, res=False, out_f32=False),
+    dict(B=2, H=20, W=20, cin=64, cout=64, k=1, s=1, act=False, res=False, out_f32=True, out_extra=16),
+    dict(B=2, H=20, W=20, cin=256, cout=5, k=1, s=1, act=False, res=False, out_f32=True, out_extra=64),
+    dict(B=2, H=32, W=32, cin=16, cout=16, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=2, H=32, W=32, cin=32, cout=32, k=3, s=2, act=True, res=False, out_f32=False),
+    dict(B=1, H=160, W=160, cin=64, cout=64, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=4, H=20, W=20, cin=512, cout=512, k=3, s=1, act=True, res=False, out_f32=False),
+])
+def test_conv_matches_torch(case):
+    _run_case(**case)
