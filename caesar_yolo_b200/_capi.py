@@ -20,13 +20,50 @@ def _load():
 
 
 lib = _load()
-lib.cy_last_error.restype = ctypes.c_char_p
 
 c_int = ctypes.c_int
 c_float = ctypes.c_float
+c_double = ctypes.c_double
 c_void_p = ctypes.c_void_p
 c_i64 = ctypes.c_int64
 c_uptr = ctypes.c_size_t
+
+
+class PPConfig(ctypes.Structure):
+    """cy_pp_config (include/caesar_b200.h)."""
+    _fields_ = [
+        ("subtract_bkg", ctypes.c_int32), ("sigma_bkg", c_double), ("use_box_mask_in_bkg", ctypes.c_int32),
+        ("bkg_box_mask_fract", c_double), ("bkg_chid", ctypes.c_int32),
+        ("clip_shift_data", ctypes.c_int32), ("sigma_clip", c_double), ("clip_chid", ctypes.c_int32),
+        ("clip_data", ctypes.c_int32), ("sigma_clip_low", c_double), ("sigma_clip_up", c_double),
+        ("nchannels", ctypes.c_int32),
+        ("zscale_stretch", ctypes.c_int32), ("zscale_contrasts", c_double * 3),
+        ("chan3_preproc", ctypes.c_int32), ("sigma_clip_baseline", c_double),
+        ("normalize_minmax", ctypes.c_int32), ("norm_min", c_double), ("norm_max", c_double),
+        ("enabled", ctypes.c_int32),
+    ]
+
+
+class Letterbox(ctypes.Structure):
+    """cy_letterbox."""
+    _fields_ = [("gain", c_float), ("pad_x", c_float), ("pad_y", c_float), ("w0", ctypes.c_int32),
+                ("h0", ctypes.c_int32)]
+
+
+# every exported symbol of include/caesar_b200.h (tests check that the library exports all of them)
+SYMBOLS = [
+    "cy_last_error", "cy_version", "cy_device_check", "cy_memcpy_d2d", "cy_generate_tiles", "cy_tile_neighbors",
+    "cy_letterbox_shape", "cy_preprocess_scratch_bytes", "cy_preprocess", "cy_conv_block_n", "cy_conv2d_nhwc",
+    "cy_model_create", "cy_model_set_tensor", "cy_model_finalize", "cy_model_forward", "cy_model_info",
+    "cy_model_profile", "cy_model_destroy", "cy_num_anchors", "cy_decode_pred", "cy_postprocess_scratch_bytes",
+    "cy_postprocess", "cy_nms_scratch_bytes", "cy_nms_batched", "cy_merge_tile", "cy_make_records",
+    "cy_compact_scratch_bytes", "cy_compact_records", "cy_merge_global",
+]
+
+lib.cy_last_error.restype = ctypes.c_char_p
+for _n in ("cy_preprocess_scratch_bytes", "cy_postprocess_scratch_bytes", "cy_nms_scratch_bytes",
+           "cy_compact_scratch_bytes"):
+    getattr(lib, _n).restype = ctypes.c_size_t
 
 
 def check(rc):
@@ -45,3 +82,8 @@ def ptr(t):
 def cur_stream():
     import torch
     return c_uptr(torch.cuda.current_stream().cuda_stream)
+
+
+def cuda_memcpy_d2d(dst, src, nbytes):
+    """Device->device copy on torch's current stream (used to read model-owned head buffers in tests)."""
+    check(lib.cy_memcpy_d2d(c_void_p(dst), c_void_p(src), ctypes.c_size_t(nbytes), cur_stream()))

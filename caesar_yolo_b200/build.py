@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         if any(rcs):
             raise RuntimeError("nvcc failed")
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

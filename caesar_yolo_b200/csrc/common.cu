@@ -23,3 +23,7 @@ extern "C" int cy_device_check(void) {
     if (prop.major != 10) return cy::set_error(CY_ERR_CUDA, "device is sm_%d%d, need sm_100", prop.major, prop.minor);
     return CY_OK;
 }
+extern "C" int cy_memcpy_d2d(void* dst, const void* src, size_t nbytes, uintptr_t stream) {
+    CY_CUDA_CHECK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CY_OK;
+}

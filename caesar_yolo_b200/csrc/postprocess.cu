@@ -1,0 +1,561 @@
+// Detect-head decode, confidence filter, score sort, greedy NMS, box rescale and the per-tile IoU merge.
+// Warp/CTA-level kernels, one CTA per tile; everything is batched over tiles.
+//
+// Replaces (reference call sites): ultralytics Detect._inference + ops.non_max_suppression +
+// torchvision.ops.nms + ops.scale_boxes inside `model(...)` (caesar_yolo/evaluation.py:181-193; SURVEY App.
+// A.6) and Analyzer.process_detections (caesar_yolo/evaluation.py:252-346) with utils.get_iou
+// (caesar_yolo/utils.py:54-107) and Graph (caesar_yolo/graph.py:2-41).
+#include "postprocess.h"
+#include "common.h"
+#include <math.h>
+
+namespace cy {
+
+// ------------------------------------------------------------------------------------------ helpers
+
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Block-wide bitonic sort, descending, n a power of two; keys may live in shared or global memory.
+__device__ void block_bitonic_sort_desc(unsigned long long* keys, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const unsigned long long a = keys[i], b = keys[p];
+                const bool desc = ((i & k) == 0);
+                if (desc ? (a < b) : (a > b)) {
+                    keys[i] = b;
+                    keys[p] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// torchvision nms_kernel_impl arithmetic (fp32, no contraction): suppress iff inter/(ai+aj-inter) > thr (double)
+__device__ __forceinline__ bool nms_suppresses(const float4 a, float aa, const float4 b, float ab, double thr) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
+    const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+    return (double)ovr > thr;
+}
+__device__ __forceinline__ float box_area(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+static constexpr int kNmsThreads = 512;  // == chunk size
+static constexpr int kNmsWords = kNmsThreads / 32;
+
+// Greedy NMS over K boxes already in descending score order.  boxes: global [K] float4.
+// keep_pos: global scratch [>= min(K, max_keep)] receives positions (in sorted order) of kept boxes.
+// Returns number kept (valid in all threads).  Uses static shared memory.
+__device__ int nms_sorted_block(const float4* __restrict__ boxes, int K, double thr, int max_keep, int* keep_pos) {
+    __shared__ uint32_t s_mask[kNmsThreads][kNmsWords];
+    __shared__ float4 s_kb[256];
+    __shared__ float s_ka[256];
+    __shared__ uint32_t s_alive[kNmsWords];
+    __shared__ int s_nkeep;
+    __shared__ float4 s_cb[kNmsThreads];
+    __shared__ float s_ca[kNmsThreads];
+    const int t = threadIdx.x;
+    if (t == 0) s_nkeep = 0;
+    __syncthreads();
+    for (int base = 0; base < K; base += kNmsThreads) {
+        const int nk0 = s_nkeep;
+        if (nk0 >= max_keep) break;
+        const int idx = base + t;
+        const bool have = idx < K;
+        float4 bx = make_float4(0, 0, 0, 0);
+        if (have) bx = boxes[idx];
+        const float ar = box_area(bx);
+        s_cb[t] = bx;
+        s_ca[t] = ar;
+        // phase A: test against boxes kept in earlier chunks
+        bool alive = have;
+        for (int kb = 0; kb < nk0; kb += 256) {
+            const int nb = min(256, nk0 - kb);
+            __syncthreads();
+            if (t < nb) {
+                const float4 q = boxes[keep_pos[kb + t]];
+                s_kb[t] = q;
+                s_ka[t] = box_area(q);
+            }
+            __syncthreads();
+            if (alive) {
+                for (int i = 0; i < nb; ++i)
+                    if (nms_suppresses(s_kb[i], s_ka[i], bx, ar, thr)) {
+                        alive = false;
+                        break;
+                    }
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+        if ((t & 31) == 0) s_alive[t >> 5] = bal;
+        __syncthreads();
+        // phase B: intra-chunk suppression mask, row t = boxes j>t in this chunk that t would suppress
+        {
+            uint32_t* row = s_mask[t];
+            for (int wd = 0; wd < kNmsWords; ++wd) {
+                uint32_t bits = 0;
+                if (alive && wd >= (t >> 5)) {
+                    uint32_t cand = s_alive[wd];
+                    if (wd == (t >> 5)) cand &= (t & 31) == 31 ? 0u : (0xffffffffu << ((t & 31) + 1));
+                    while (cand) {
+                        const int b = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        const int j = wd * 32 + b;
+                        if (nms_suppresses(bx, ar, s_cb[j], s_ca[j], thr)) bits |= 1u << b;
+                    }
+                }
+                row[wd] = bits;
+            }
+        }
+        __syncthreads();
+        // phase C: sequential resolve by warp 0; lane w owns word w of the removed set
+        if (t < 32) {
+            uint32_t remv = 0;
+            uint32_t al = t < kNmsWords ? s_alive[t] : 0u;
+            int nk = nk0;
+            for (int wd = 0; wd < kNmsWords && nk < max_keep; ++wd) {
+                // word wd of (alive & ~remv) evolves as we keep boxes inside it
+                while (nk < max_keep) {
+                    const uint32_t avail = __shfl_sync(0xffffffffu, al & ~remv, wd);
+                    if (!avail) break;
+                    const int b = __ffs(avail) - 1;
+                    const int i = wd * 32 + b;
+                    if (t == 0) keep_pos[nk] = base + i;
+                    ++nk;
+                    if (t < kNmsWords) remv |= s_mask[i][t];
+                    if (t == wd) remv |= 1u << b;  // consume i itself
+                }
+            }
+            if (t == 0) s_nkeep = nk;
+        }
+        __syncthreads();
+    }
+    return s_nkeep;
+}
+
+// ------------------------------------------------------------------------------------------ decode
+
+struct HeadLevels {
+    const float* p[3];
+    int h[3], w[3];
+    int a0[3];  // first anchor index of each level
+    int A;
+};
+
+// Full decode (parity entry): pred [B, 4+nc, A] exactly like ultralytics Detect._inference.
+__global__ void decode_pred_kernel(HeadLevels L, int B, int nc, float* __restrict__ pred) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * L.A) return;
+    const int a = (int)(idx % L.A);
+    const int b = (int)(idx / L.A);
+    const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
+    const int la = a - L.a0[l];
+    const float stride = l == 0 ? 8.f : (l == 1 ? 16.f : 32.f);
+    const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC;
+    const float ax = (float)(la % L.w[l]) + 0.5f, ay = (float)(la / L.w[l]) + 0.5f;
+    float d[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float v[16], mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            v[k] = rec[s * 16 + k];
+            mx = fmaxf(mx, v[k]);
+        }
+        float sum = 0.f, acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float e = expf(v[k] - mx);
+            sum += e;
+            acc += e * (float)k;
+        }
+        d[s] = acc / sum;
+    }
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    float* o = pred + (long long)b * (4 + nc) * L.A + a;
+    o[0 * (long long)L.A] = (x1 + x2) / 2.f * stride;
+    o[1 * (long long)L.A] = (y1 + y2) / 2.f * stride;
+    o[2 * (long long)L.A] = (x2 - x1) * stride;
+    o[3 * (long long)L.A] = (y2 - y1) * stride;
+    for (int c = 0; c < nc; ++c) o[(4 + c) * (long long)L.A] = 1.f / (1.f + expf(-rec[64 + c]));
+}
+
+// Stage 1 of the fused path: per anchor best class score; candidates (score > conf) are appended to the tile's key
+// list (order fixed later by the sort; key = score | inverted anchor index | class).
+__global__ void score_key_kernel(HeadLevels L, int B, int nc, float conf, unsigned long long* __restrict__ keys,
+                                 int key_stride, int* __restrict__ cand_count) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * L.A) return;
+    const int a = (int)(idx % L.A);
+    const int b = (int)(idx / L.A);
+    const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
+    const int la = a - L.a0[l];
+    const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC + 64;
+    float best = -1.f;
+    int bc = 0;
+    for (int c = 0; c < nc; ++c) {
+        const float s = 1.f / (1.f + expf(-rec[c]));
+        if (s > best) {  // torch max(): first index on ties
+            best = s;
+            bc = c;
+        }
+    }
+    if (best > conf) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) |
+                                       ((unsigned long long)(0xFFFFFu - (uint32_t)a) << 8) | (unsigned long long)bc;
+        const int slot = atomicAdd(&cand_count[b], 1);
+        keys[(long long)b * key_stride + slot] = key;
+    }
+}
+
+// Stage 2: one CTA per tile. Sort keys (score desc, anchor asc), decode boxes of the candidates, NMS with class
+// offsets, rescale to tile pixels, emit dets[max_det][6].
+__global__ void __launch_bounds__(kNmsThreads) nms_tiles_kernel(HeadLevels L, int B, unsigned long long* keys,
+                                                                int key_stride, const int* __restrict__ cand_count,
+                                                                float4* boxes_scratch,
+                                                                int* keep_scratch, double iou_thr, int max_det,
+                                                                int max_nms, float max_wh, const LetterboxInfo* lb,
+                                                                float* __restrict__ dets, int* __restrict__ ndets) {
+    const int b = blockIdx.x;
+    unsigned long long* k = keys + (long long)b * key_stride;
+    const int ncand = cand_count[b];
+    int npow2 = 2;
+    while (npow2 < ncand) npow2 <<= 1;
+    for (int i = ncand + threadIdx.x; i < npow2; i += blockDim.x) k[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(k, npow2);
+    int K = min(ncand, max_nms);
+    float4* bx = boxes_scratch + (long long)b * key_stride;
+    // decode candidate boxes (xyxy in letterboxed image pixels, + class offset as ultralytics does)
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const unsigned long long key = k[i];
+        const int a = (int)(0xFFFFFu - (uint32_t)((key >> 8) & 0xFFFFFu));
+        const int cls = (int)(key & 0xFFu);
+        const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
+        const int la = a - L.a0[l];
+        const float stride = l == 0 ? 8.f : (l == 1 ? 16.f : 32.f);
+        const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC;
+        const float ax = (float)(la % L.w[l]) + 0.5f, ay = (float)(la / L.w[l]) + 0.5f;
+        float d[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            float v[16], mx = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                v[q] = rec[s * 16 + q];
+                mx = fmaxf(mx, v[q]);
+            }
+            float sum = 0.f, acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float e = expf(v[q] - mx);
+                sum += e;
+                acc += e * (float)q;
+            }
+            d[s] = acc / sum;
+        }
+        const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
+        const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
+        const float w = __fmul_rn(__fsub_rn(x2, x1), stride), h = __fmul_rn(__fsub_rn(y2, y1), stride);
+        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+        const float off = __fmul_rn((float)cls, max_wh);
+        bx[i] = make_float4(__fadd_rn(__fsub_rn(cx, hw), off), __fadd_rn(__fsub_rn(cy, hh), off),
+                            __fadd_rn(__fadd_rn(cx, hw), off), __fadd_rn(__fadd_rn(cy, hh), off));
+    }
+    __syncthreads();
+    int* kp = keep_scratch + (long long)b * max_det;
+    const int nk = nms_sorted_block(bx, K, iou_thr, max_det, kp);
+    // output: undo class offset by re-deriving? No: ultralytics returns x[i] = un-offset boxes.  We recompute them
+    // from the offset ones would lose bits, so decode again from the head record for the kept few.
+    const LetterboxInfo li = lb[b];
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+        const unsigned long long key = k[kp[i]];
+        const int a = (int)(0xFFFFFu - (uint32_t)((key >> 8) & 0xFFFFFu));
+        const int cls = (int)(key & 0xFFu);
+        const float score = __uint_as_float((uint32_t)(key >> 32));
+        const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
+        const int la = a - L.a0[l];
+        const float stride = l == 0 ? 8.f : (l == 1 ? 16.f : 32.f);
+        const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC;
+        const float ax = (float)(la % L.w[l]) + 0.5f, ay = (float)(la / L.w[l]) + 0.5f;
+        float d[4];
+        for (int s = 0; s < 4; ++s) {
+            float v[16], mx = -INFINITY;
+            for (int q = 0; q < 16; ++q) {
+                v[q] = rec[s * 16 + q];
+                mx = fmaxf(mx, v[q]);
+            }
+            float sum = 0.f, acc = 0.f;
+            for (int q = 0; q < 16; ++q) {
+                const float e = expf(v[q] - mx);
+                sum += e;
+                acc += e * (float)q;
+            }
+            d[s] = acc / sum;
+        }
+        const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
+        const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
+        const float w = __fmul_rn(__fsub_rn(x2, x1), stride), h = __fmul_rn(__fsub_rn(y2, y1), stride);
+        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+        // scale_boxes: subtract pad, divide by gain, clip to the original tile
+        float bx1 = __fdiv_rn(__fsub_rn(__fsub_rn(cx, hw), li.pad_x), li.gain);
+        float by1 = __fdiv_rn(__fsub_rn(__fsub_rn(cy, hh), li.pad_y), li.gain);
+        float bx2 = __fdiv_rn(__fsub_rn(__fadd_rn(cx, hw), li.pad_x), li.gain);
+        float by2 = __fdiv_rn(__fsub_rn(__fadd_rn(cy, hh), li.pad_y), li.gain);
+        bx1 = fminf(fmaxf(bx1, 0.f), (float)li.w0);
+        bx2 = fminf(fmaxf(bx2, 0.f), (float)li.w0);
+        by1 = fminf(fmaxf(by1, 0.f), (float)li.h0);
+        by2 = fminf(fmaxf(by2, 0.f), (float)li.h0);
+        float* o = dets + ((long long)b * max_det + i) * 6;
+        o[0] = bx1; o[1] = by1; o[2] = bx2; o[3] = by2; o[4] = score; o[5] = (float)cls;
+    }
+    if (threadIdx.x == 0) ndets[b] = nk;
+}
+
+// Standalone batched NMS == torchvision.ops.nms per segment (parity entry cy_nms / cy_nms_batched).
+__global__ void __launch_bounds__(kNmsThreads) nms_generic_kernel(const float* __restrict__ boxes,
+                                                                  const float* __restrict__ scores,
+                                                                  const int* __restrict__ counts, int stride_n,
+                                                                  int npow2, unsigned long long* keys,
+                                                                  float4* boxes_sorted, int* keep_pos, double thr,
+                                                                  int max_keep, long long* __restrict__ keep,
+                                                                  int* __restrict__ nkeep) {
+    const int b = blockIdx.x;
+    const int N = counts ? counts[b] : stride_n;
+    unsigned long long* k = keys + (long long)b * npow2;
+    const float* bsrc = boxes + (long long)b * stride_n * 4;
+    const float* ssrc = scores + (long long)b * stride_n;
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x)
+        k[i] = i < N ? (((unsigned long long)float_orderable(ssrc[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i))
+                     : 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(k, npow2);
+    float4* bs = boxes_sorted + (long long)b * stride_n;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int src = (int)(0xFFFFFFFFu - (uint32_t)(k[i] & 0xFFFFFFFFull));
+        bs[i] = make_float4(bsrc[src * 4 + 0], bsrc[src * 4 + 1], bsrc[src * 4 + 2], bsrc[src * 4 + 3]);
+    }
+    __syncthreads();
+    int* kp = keep_pos + (long long)b * stride_n;
+    const int nk = nms_sorted_block(bs, N, thr, max_keep, kp);
+    for (int i = threadIdx.x; i < nk; i += blockDim.x)
+        keep[(long long)b * stride_n + i] = (long long)(0xFFFFFFFFu - (uint32_t)(k[kp[i]] & 0xFFFFFFFFull));
+    if (threadIdx.x == 0) nkeep[b] = nk;
+}
+
+// ------------------------------------------------------------------------------------------ per-tile merge
+
+// utils.get_iou in fp32 (numpy>=2 scalar semantics).  Caller guarantees non-degenerate boxes.
+__device__ __forceinline__ float ref_get_iou(const float4 a, const float4 b) {
+    const float xl = fmaxf(a.x, b.x), yt = fmaxf(a.y, b.y), xr = fminf(a.z, b.z), yb = fminf(a.w, b.w);
+    if (xr < xl || yb < yt) return 0.f;
+    const float inter = __fmul_rn(__fsub_rn(xr, xl), __fsub_rn(yb, yt));
+    const float a1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float a2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(a1, a2), inter));
+}
+
+static constexpr int kMergeMaxN = 320;               // >= max_det (300)
+static constexpr int kMergeWords = kMergeMaxN / 32;  // 10
+
+// One CTA (128 threads) per tile.  dets [B, det_stride, 6]; keeps detections with !(score < thr_score), links
+// pairs with iou >= hard or (same class and iou >= soft), connected components by recursive-DFS order, winner =
+// first member in DFS preorder with strictly greatest score (score_best starts at 0).
+__global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict__ dets, const int* __restrict__ ndets,
+                                                         int det_stride, float thr_score, float thr_soft,
+                                                         float thr_hard, int* __restrict__ keep_idx,
+                                                         int* __restrict__ nkeep, int* __restrict__ status) {
+    __shared__ float4 s_box[kMergeMaxN];
+    __shared__ float s_score[kMergeMaxN];
+    __shared__ int s_cls[kMergeMaxN];
+    __shared__ int s_src[kMergeMaxN];
+    __shared__ uint32_t s_adj[kMergeMaxN][kMergeWords];
+    __shared__ int s_N, s_bad;
+    const int b = blockIdx.x;
+    const int n_in = min(ndets[b], kMergeMaxN);
+    const float* D = dets + (long long)b * det_stride * 6;
+    if (threadIdx.x == 0) {
+        // score filter keeps order (evaluation.py:276-287); sequential compaction of <=300 entries
+        int n = 0, bad = 0;
+        for (int i = 0; i < n_in; ++i) {
+            const float sc = D[i * 6 + 4];
+            if (sc < thr_score) continue;
+            const float4 bx = make_float4(D[i * 6 + 0], D[i * 6 + 1], D[i * 6 + 2], D[i * 6 + 3]);
+            if (!(bx.x < bx.z) || !(bx.y < bx.w)) bad = 1;  // get_iou would assert (utils.py:78-81)
+            s_box[n] = bx;
+            s_score[n] = sc;
+            s_cls[n] = (int)D[i * 6 + 5];
+            s_src[n] = i;
+            ++n;
+        }
+        s_N = n;
+        s_bad = (bad && n >= 2) ? 1 : 0;
+    }
+    for (int i = threadIdx.x; i < kMergeMaxN * kMergeWords; i += blockDim.x) (&s_adj[0][0])[i] = 0u;
+    __syncthreads();
+    const int N = s_N;
+    int* ko = keep_idx + (long long)b * det_stride;
+    if (s_bad) {
+        if (threadIdx.x == 0) {
+            nkeep[b] = 0;
+            status[b] = -2;
+        }
+        return;
+    }
+    // adjacency: thread handles rows i = tid, tid+128, ...
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const float4 bi = s_box[i];
+        const int ci = s_cls[i];
+        for (int j = i + 1; j < N; ++j) {
+            const float iou = ref_get_iou(bi, s_box[j]);
+            if (iou >= thr_hard || (ci == s_cls[j] && iou >= thr_soft)) {
+                atomicOr(&s_adj[i][j >> 5], 1u << (j & 31));
+                atomicOr(&s_adj[j][i >> 5], 1u << (i & 31));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // iterative emulation of the recursive DFS (graph.py:9-23): adjacency ascending
+        uint32_t visited[kMergeWords];
+        for (int w = 0; w < kMergeWords; ++w) visited[w] = 0u;
+        short stack[kMergeMaxN];
+        int nk = 0;
+        for (int v = 0; v < N; ++v) {
+            if (visited[v >> 5] >> (v & 31) & 1u) continue;
+            float sbest = 0.f;
+            int best = -1;
+            int sp = 0;
+            stack[sp++] = (short)v;
+            visited[v >> 5] |= 1u << (v & 31);
+            if (s_score[v] > sbest) {
+                sbest = s_score[v];
+                best = v;
+            }
+            while (sp > 0) {
+                const int u = stack[sp - 1];
+                // next unvisited neighbour of u in ascending order
+                int nxt = -1;
+                for (int w = 0; w < kMergeWords; ++w) {
+                    const uint32_t m = s_adj[u][w] & ~visited[w];
+                    if (m) {
+                        nxt = w * 32 + __ffs(m) - 1;
+                        break;
+                    }
+                }
+                if (nxt < 0) {
+                    --sp;
+                    continue;
+                }
+                visited[nxt >> 5] |= 1u << (nxt & 31);
+                if (s_score[nxt] > sbest) {  // preorder visit
+                    sbest = s_score[nxt];
+                    best = nxt;
+                }
+                stack[sp++] = (short)nxt;
+            }
+            // best == -1 only when every score in the component is <= 0; the reference then indexes [-1]
+            ko[nk++] = best >= 0 ? s_src[best] : s_src[N - 1];
+        }
+        nkeep[b] = nk;
+        status[b] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host launchers
+
+static HeadLevels make_levels(const float* h0, const float* h1, const float* h2, int Sh, int Sw) {
+    HeadLevels L;
+    L.p[0] = h0; L.p[1] = h1; L.p[2] = h2;
+    int a = 0;
+    for (int l = 0; l < 3; ++l) {
+        const int s = 8 << l;
+        L.h[l] = Sh / s;
+        L.w[l] = Sw / s;
+        L.a0[l] = a;
+        a += L.h[l] * L.w[l];
+    }
+    L.A = a;
+    return L;
+}
+
+int num_anchors(int Sh, int Sw) {
+    return (Sh / 8) * (Sw / 8) + (Sh / 16) * (Sw / 16) + (Sh / 32) * (Sw / 32);
+}
+
+int decode_pred(const float* h0, const float* h1, const float* h2, int B, int Sh, int Sw, int nc, float* pred,
+                cudaStream_t st) {
+    HeadLevels L = make_levels(h0, h1, h2, Sh, Sw);
+    const long long total = (long long)B * L.A;
+    decode_pred_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, B, nc, pred);
+    return (int)cudaGetLastError();
+}
+
+static int next_pow2(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+size_t postprocess_scratch_bytes(int B, int Sh, int Sw, int max_det) {
+    const int np2 = next_pow2(num_anchors(Sh, Sw));
+    return (size_t)B * np2 * (sizeof(unsigned long long) + sizeof(float4)) + (size_t)B * max_det * sizeof(int) +
+           (size_t)B * sizeof(int) + 256;
+}
+
+int postprocess(const float* h0, const float* h1, const float* h2, int B, int Sh, int Sw, int nc, float conf,
+                float iou, int max_det, const LetterboxInfo* lb, float* dets, int* ndets, void* scratch,
+                cudaStream_t st) {
+    HeadLevels L = make_levels(h0, h1, h2, Sh, Sw);
+    if (L.A >= (1 << 20)) return -1;
+    const int np2 = next_pow2(L.A);
+    unsigned long long* keys = (unsigned long long*)scratch;
+    float4* boxes = (float4*)(keys + (size_t)B * np2);
+    int* keep = (int*)(boxes + (size_t)B * np2);
+    int* cand = keep + (size_t)B * max_det;
+    const long long total = (long long)B * L.A;
+    cudaMemsetAsync(cand, 0, (size_t)B * sizeof(int), st);
+    score_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, B, nc, conf, keys, np2, cand);
+    nms_tiles_kernel<<<B, kNmsThreads, 0, st>>>(L, B, keys, np2, cand, boxes, keep, (double)iou, max_det, 30000,
+                                                7680.f, lb, dets, ndets);
+    return (int)cudaGetLastError();
+}
+
+size_t nms_scratch_bytes(int B, int N) {
+    const int np2 = next_pow2(N < 2 ? 2 : N);
+    return (size_t)B * np2 * sizeof(unsigned long long) + (size_t)B * N * (sizeof(float4) + sizeof(int)) + 256;
+}
+
+int nms_batched(const float* boxes, const float* scores, const int* counts, int B, int N, double thr, int max_keep,
+                long long* keep, int* nkeep, void* scratch, cudaStream_t st) {
+    const int np2 = next_pow2(N < 2 ? 2 : N);
+    unsigned long long* keys = (unsigned long long*)scratch;
+    float4* bs = (float4*)(keys + (size_t)B * np2);
+    int* kp = (int*)(bs + (size_t)B * N);
+    nms_generic_kernel<<<B, kNmsThreads, 0, st>>>(boxes, scores, counts, N, np2, keys, bs, kp, thr,
+                                                  max_keep > 0 ? max_keep : N, keep, nkeep);
+    return (int)cudaGetLastError();
+}
+
+int merge_tiles(const float* dets, const int* ndets, int B, int det_stride, float thr_score, float thr_soft,
+                float thr_hard, int* keep_idx, int* nkeep, int* status, cudaStream_t st) {
+    if (det_stride > kMergeMaxN) return -1;
+    merge_tile_kernel<<<B, 128, 0, st>>>(dets, ndets, det_stride, thr_score, thr_soft, thr_hard, keep_idx, nkeep,
+                                         status);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cy

@@ -9,6 +9,7 @@
  */
 #ifndef CAESAR_B200_H
 #define CAESAR_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -20,20 +21,138 @@ extern "C" {
 #define CY_ERR_NOMEM (-3)
 #define CY_ERR_STATE (-4)
 
+/* ------------------------------------------------------------------------------------------------ types */
+
+/* One tile of utils.generate_tiles (caesar_yolo/utils.py:622-697): xmax/ymax are EXCLUSIVE. */
+typedef struct { int32_t xmin, xmax, ymin, ymax; } cy_tile;
+
+/* Per-tile detection after Analyzer.make_json_results (caesar_yolo/evaluation.py:418-469): integer-truncated
+ * coordinates + tile origin (stored as float like the reference), flags bit0 = edge.  32 bytes: this is the
+ * fixed record exchanged between GPUs (replaces the pickled dicts of inference.py:936-984). */
+typedef struct { float x1, y1, x2, y2, score; int32_t cls, tile_id, flags; } cy_det_record;
+
+/* Final catalog entry (SFinder.merge_edge_sources, caesar_yolo/inference.py:731-931).
+ * flags bit0 = edge, bit1 = merged; tile_id = -1 for merged sources. */
+typedef struct { float x1, y1, x2, y2, score; int32_t cls, flags, tile_id; } cy_source;
+
+/* ultralytics LetterBox / scale_boxes geometry of one tile. */
+typedef struct { float gain, pad_x, pad_y; int32_t w0, h0; } cy_letterbox;
+
+/* Preprocessing stage list = scripts/run.py:272-293 (fixed order), parameters = run.py:80-107 options. */
+typedef struct {
+    int32_t subtract_bkg;        double sigma_bkg;  int32_t use_box_mask_in_bkg;  double bkg_box_mask_fract;
+    int32_t bkg_chid;
+    int32_t clip_shift_data;     double sigma_clip; int32_t clip_chid;
+    int32_t clip_data;           double sigma_clip_low, sigma_clip_up;
+    int32_t nchannels;           /* ChanResizer target (input cube always has 3 identical channels) */
+    int32_t zscale_stretch;      double zscale_contrasts[3];
+    int32_t chan3_preproc;       double sigma_clip_baseline;
+    int32_t normalize_minmax;    double norm_min, norm_max;
+    int32_t enabled;             /* --preprocessing: 0 => the whole chain is skipped (dp = None) */
+} cy_pp_config;
+
 const char* cy_last_error(void);
 int cy_version(void);
 /* CY_OK iff the current device is sm_100. */
 int cy_device_check(void);
+/* cudaMemcpyAsync device->device on `stream` (lets hosts without a CUDA binding read library-owned buffers). */
+int cy_memcpy_d2d(void* dst, const void* src, size_t nbytes, uintptr_t stream);
 
-/* ---- convolution layer primitive (ultralytics Conv = Conv2d+BN+SiLU fused; reference model call at
- *      caesar_yolo/evaluation.py:181-193).  NHWC bf16 in, weights [cout_pad, k*k*cin] bf16 (K-major, BN folded),
- *      bias fp32[cout_pad]; optional residual added after the activation; output bf16 or fp32 written into a
- *      channel slice [out_coff, out_coff+cout) of an NHWC buffer with out_ctot channels. */
+/* ------------------------------------------------------------------------------------------------ tiling (host)
+ * utils.generate_tiles (caesar_yolo/utils.py:622-697).  tiles_host == NULL: size query (ntiles only). */
+int cy_generate_tiles(int img_xmin, int img_xmax, int img_ymin, int img_ymax, int tile_x, int tile_y, double step_x,
+                      double step_y, cy_tile* tiles_host, int capacity, int* ntiles_host);
+/* Neighbour lists of SFinder.create_tile_tasks (caesar_yolo/inference.py:1034-1071, predicates :123-163) as CSR,
+ * ascending tile id, self excluded; nb_off_host has T+1 entries; nb_idx_host == NULL: size query. */
+int cy_tile_neighbors(const cy_tile* tiles_host, int T, int* nb_off_host, int* nb_idx_host, int capacity,
+                      int* total_host);
+
+/* ------------------------------------------------------------------------------------------------ preprocessing
+ * DataPreprocessor chain of caesar_yolo/preprocessing.py (BkgSubtractor :591-658, SigmaClipShifter :664-717,
+ * SigmaClipper :723-771, ChanResizer :1077-1133, ZScaleTransformer :934-971, Chan3Trasformer :1020-1072 with
+ * HistEqualizer :977-1012, MinMaxNormalizer :75-111) + Analyzer.predict's front part (evaluation.py:146-176) +
+ * the ultralytics predictor preprocess (LetterBox, channel reversal, /255).
+ *
+ * img: fp32 image in device memory, row-major with row_stride elements per row; big_endian != 0 means raw FITS
+ * byte order (byte-swapped on load); non-finite pixels become 0 (utils.py:219,394).  Tile b covers
+ * img[tile_y0[b] .. +Ty, tile_x0[b] .. +Tx].
+ * chain_out  [B,Ty,Tx,3] fp32  : chain output before the resize (parity entry; also the resize input)
+ * model_in   [B,Sh,Sw,4] bf16  : letterboxed, channel-reversed, /255, NHWC (4th channel 0) — cy_model_forward input
+ * model_in_f32 (optional) [B,3,Sh,Sw] fp32 NCHW: the same before bf16 rounding (parity entry)
+ * status [B]: 0 ok, -1 tile rejected like the reference (preprocess returned None / constant rows,
+ *             evaluation.py:164-176), -3 degenerate statistics (empty clip set). */
+int cy_letterbox_shape(int Ty, int Tx, int imgsz, int* Sh_host, int* Sw_host, cy_letterbox* lb_host);
+size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg_host, int B, int Ty, int Tx);
+int cy_preprocess(const cy_pp_config* cfg_host, const void* img, long long row_stride, int big_endian,
+                  const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz, float* chain_out,
+                  void* model_in, float* model_in_f32, int32_t* status, void* scratch, uintptr_t stream);
+
+/* ------------------------------------------------------------------------------------------------ convolution
+ * Layer primitive (ultralytics Conv = Conv2d+BN+SiLU fused; reference model call at
+ * caesar_yolo/evaluation.py:181-193).  NHWC bf16 in, weights [cout_pad, k*k*cin] bf16 (K-major, BN folded),
+ * bias fp32[cout_pad]; optional residual added after the activation; output bf16 or fp32 written into a
+ * channel slice [out_coff, out_coff+cout) of an NHWC buffer with out_ctot channels. */
 int cy_conv_block_n(int cout);
 int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ctot, int in_coff, int cin, const void* w,
                    const float* bias, int cout, int cout_pad, int ksize, int stride, void* out, int out_ctot,
                    int out_coff, int out_f32, const void* res, int res_ctot, int res_coff, int act,
                    uintptr_t stream);
+
+/* ------------------------------------------------------------------------------------------------ model
+ * Replaces `YOLO(weights)` (scripts/run.py:347) and `model(image, ...)` (caesar_yolo/evaluation.py:181-193):
+ * YOLOv8 n/s/m/l/x DetectionModel.forward with Conv+BN folded.  Tensors are given under their
+ * ultralytics state-dict names (model.0.conv.weight, model.0.bn.running_var, ..., model.22.cv3.2.2.bias), fp32,
+ * host memory.  forward: in = [B,Sh,Sw,4] bf16 NHWC (cy_preprocess output); heads_host receives three DEVICE
+ * pointers (owned by the model, valid until the next forward of the same shape) to the raw Detect maps
+ * [B, Sh/s, Sw/s, 80] fp32, s = 8,16,32: 64 DFL logits + nc class logits per anchor. */
+int cy_model_create(const char* variant, int nc, void** model_host);
+int cy_model_set_tensor(void* model, const char* name, const float* data_host, long long numel);
+int cy_model_finalize(void* model);
+int cy_model_forward(void* model, const void* in, int B, int Sh, int Sw, const float** heads_host, uintptr_t stream);
+/* info_host[0..7] = nparams, flops per forward of the last planned shape, #kernel launches per forward,
+ * activation bytes, c3, c4, c5, #convs */
+int cy_model_info(void* model, int B, int Sh, int Sw, double* info_host);
+/* Per-layer timing of one forward (CUDA events, after a warm-up): names_host receives up to cap pointers to
+ * internal strings, ms_host / flops_host the per-op numbers. Returns the number of ops in *nops_host. */
+int cy_model_profile(void* model, const void* in, int B, int Sh, int Sw, int cap, const char** names_host,
+                     float* ms_host, double* flops_host, int* nops_host, uintptr_t stream);
+int cy_model_destroy(void* model);
+
+/* ------------------------------------------------------------------------------------------------ detect / NMS
+ * Detect._inference (DFL softmax + dist2bbox + sigmoid): pred [B, 4+nc, A] fp32 (parity entry). */
+int cy_num_anchors(int Sh, int Sw);
+int cy_decode_pred(const float* h0, const float* h1, const float* h2, int B, int Sh, int Sw, int nc, float* pred,
+                   uintptr_t stream);
+/* Fused decode + ops.non_max_suppression (conf filter, best class, class-offset boxes, torchvision.ops.nms, max_det)
+ * + ops.scale_boxes/clip_boxes.  dets [B,max_det,6] = x1,y1,x2,y2,conf,cls in descending score order. */
+size_t cy_postprocess_scratch_bytes(int B, int Sh, int Sw, int max_det);
+int cy_postprocess(const float* h0, const float* h1, const float* h2, int B, int Sh, int Sw, int nc, float conf,
+                   float iou, int max_det, const cy_letterbox* lb, float* dets, int32_t* ndets, void* scratch,
+                   uintptr_t stream);
+/* == torchvision.ops.nms on each of B segments (boxes [B,N,4] xyxy, scores [B,N], counts [B] or NULL => N each):
+ * keep [B,N] int64 original indices in descending score order (ties: lower index first), nkeep [B]. */
+size_t cy_nms_scratch_bytes(int B, int N);
+int cy_nms_batched(const float* boxes, const float* scores, const int32_t* counts, int B, int N, double iou_thr,
+                   int max_keep, int64_t* keep, int32_t* nkeep, void* scratch, uintptr_t stream);
+
+/* ------------------------------------------------------------------------------------------------ merges
+ * Analyzer.process_detections (caesar_yolo/evaluation.py:252-346) with utils.get_iou (utils.py:54-107) and Graph
+ * (graph.py:2-41).  dets [B,det_stride,6]; keep_idx [B,det_stride] indices into the tile's dets in the
+ * reference's output order; status[b] = -2 if get_iou would assert (degenerate box). det_stride <= 320. */
+int cy_merge_tile(const float* dets, const int32_t* ndets, int B, int det_stride, float thr_score, float thr_soft,
+                  float thr_hard, int32_t* keep_idx, int32_t* nkeep, int32_t* status, uintptr_t stream);
+/* Analyzer.make_json_results (evaluation.py:418-469): records written at recs[tile_id*det_stride + i], nrec[tile_id]. */
+int cy_make_records(const float* dets, const int32_t* keep_idx, const int32_t* nkeep, const int32_t* status,
+                    int det_stride, const cy_tile* tiles, const int32_t* tile_ids, int B, cy_det_record* recs,
+                    int32_t* nrec, uintptr_t stream);
+size_t cy_compact_scratch_bytes(int T);
+int cy_compact_records(const cy_det_record* slots, const int32_t* counts, int T, int slot_stride,
+                       cy_det_record* out, int32_t* total, void* scratch, uintptr_t stream);
+/* SFinder.find_sources_at_edge (inference.py:663-726) + merge_edge_sources (:731-931): recs = n records in gathered
+ * order (tile-id major), tiles [T], CSR neighbour lists; out [>= n] sources in the reference's catalog order,
+ * nout (device int64).  Synchronises the stream (component count is data dependent). */
+int cy_merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const int32_t* nb_off,
+                    const int32_t* nb_idx, cy_source* out, int64_t* nout, uintptr_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,121 @@
+"""CPU-side tests: C-ABI library loads and exports every symbol of include/caesar_b200.h; host-side tiling logic
+vs the oracle's literal restatement of utils.generate_tiles / create_tile_tasks."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import inference as oinf, utils as outils
+
+
+def test_library_exports_every_declared_symbol():
+    from caesar_yolo_b200 import _capi
+    hdr = open(os.path.join(os.path.dirname(__file__), '..', 'include', 'caesar_b200.h')).read()
+    declared = set(re.findall(r'\b(cy_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, "no declarations parsed"
+    for s in declared:
+        assert hasattr(_capi.lib, s), "libcaesar_b200.so does not export %s" % s
+    assert declared == set(_capi.SYMBOLS)
+    assert _capi.lib.cy_version() >= 100
+
+
+@pytest.mark.parametrize("args", [
+    (0, 131, 0, 131, 64, 64, .5, .5),
+    (0, 16383, 0, 16383, 512, 512, 1.0, 1.0),
+    (0, 4095, 0, 4095, 512, 512, .5, .5),
+    (0, 999, 0, 777, 256, 128, .3, .7),
+    (10, 1009, 20, 531, 200, 100, 1.0, .5),
+    (0, 511, 0, 511, 512, 512, 1.0, 1.0),
+    (0, 2000, 0, 1000, 333, 111, .45, .55),
+])
+def test_generate_tiles_matches_oracle(args):
+    from caesar_yolo_b200 import ops
+    want = outils.generate_tiles(*args)
+    got = ops.generate_tiles(*args)
+    assert got is not None and len(got) == len(want)
+    assert [tuple(int(v) for v in t) for t in got] == [tuple(int(v) for v in t) for t in want]
+
+
+@pytest.mark.parametrize("args", [
+    (5, 4, 0, 100, 10, 10, 1, 1),       # xmax <= xmin
+    (0, 100, 0, 100, 0, 10, 1, 1),      # tile size 0
+    (0, 100, 0, 100, 10, 10, 0, 1),     # step 0
+    (0, 100, 0, 100, 10, 10, 1.5, 1),   # step > 1
+    (0, 100, 0, 100, 200, 10, 1, 1),    # tile larger than image
+])
+def test_generate_tiles_invalid(args):
+    from caesar_yolo_b200 import ops
+    assert outils.generate_tiles(*args) is None
+    assert ops.generate_tiles(*args) is None
+
+
+def _oracle_neighbors(tiles):
+    cfg = dict(image_path='x.fits')
+    tasks = [oinf.TileTask(tuple(int(v) for v in t), None, cfg) for t in tiles]
+    for i, t in enumerate(tasks):
+        t.set_task_id(i)
+    n = len(tasks)
+    for j in range(n):
+        for k in range(j + 1, n):
+            if tasks[j].is_task_tile_neighbor(tasks[k]):
+                tasks[j].add_neighbor_info(k, k, 0)
+                tasks[k].add_neighbor_info(j, j, 0)
+    return [sorted(t.neighborTaskId) for t in tasks]
+
+
+@pytest.mark.parametrize("args", [
+    (0, 131, 0, 131, 64, 64, .5, .5),
+    (0, 4095, 0, 4095, 512, 512, 1.0, 1.0),
+    (0, 4095, 0, 2047, 512, 512, .5, .5),
+    (0, 999, 0, 777, 256, 128, .3, .7),
+    (0, 2000, 0, 1000, 333, 111, .45, .55),
+])
+def test_tile_neighbors_match_oracle(args):
+    from caesar_yolo_b200 import ops
+    tiles = ops.generate_tiles(*args)
+    off, idx = ops.tile_neighbors(tiles)
+    want = _oracle_neighbors(tiles)
+    got = [list(idx[off[i]:off[i + 1]]) for i in range(len(tiles))]
+    assert got == want
+
+
+def test_tile_neighbors_nongrid_fallback():
+    from caesar_yolo_b200 import ops
+    rng = np.random.default_rng(3)
+    tiles = np.zeros(40, dtype=ops.TILE_DTYPE)
+    for i in range(40):
+        x, y = rng.integers(0, 500, 2)
+        tiles[i] = (x, x + rng.integers(10, 120), y, y + rng.integers(10, 120))
+    off, idx = ops.tile_neighbors(tiles)
+    want = _oracle_neighbors(tiles)
+    got = [list(idx[off[i]:off[i + 1]]) for i in range(len(tiles))]
+    assert got == want
+
+
+def test_neighbor_counts_of_baseline_grids():
+    """8 neighbours at step 1.0, 24 at step 0.5 for interior tiles."""
+    from caesar_yolo_b200 import ops
+    t = ops.generate_tiles(0, 16383, 0, 16383, 512, 512, 1.0, 1.0)
+    assert len(t) == 1024
+    off, _ = ops.tile_neighbors(t)
+    assert int(np.max(np.diff(off))) == 8
+    t = ops.generate_tiles(0, 32767, 0, 32767, 512, 512, .5, .5)
+    assert len(t) == 16384
+    off, _ = ops.tile_neighbors(t)
+    assert int(np.max(np.diff(off))) == 24
+
+
+@pytest.mark.parametrize("shape", [(512, 512, 640), (132, 132, 640), (512, 256, 640), (256, 512, 640), (256, 256, 640),
+                                   (512, 512, 1024), (512, 512, 512), (300, 500, 640), (100, 37, 640)])
+def test_letterbox_shape_matches_oracle(shape):
+    from caesar_yolo_b200 import ops
+    from oracle import yolo as oy
+    Ty, Tx, S = shape
+    img = np.zeros((Ty, Tx, 3), dtype=np.float64)
+    lb = oy.letterbox(img, (S, S))
+    Sh, Sw, info = ops.letterbox_shape(Ty, Tx, S)
+    assert (Sh, Sw) == lb.shape[:2]
+    gain = min(Sh / Ty, Sw / Tx)
+    assert info.gain == np.float32(gain)
+    assert info.pad_x == round((Sw - Tx * gain) / 2 - 0.1) and info.pad_y == round((Sh - Ty * gain) / 2 - 0.1)

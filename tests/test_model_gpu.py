@@ -1,0 +1,130 @@
+"""YOLOv8 forward on tcgen05 kernels vs the fp32 torch oracle (and vs the oracle with bf16-rounded weights and
+activations, which isolates kernel bugs from quantisation), Detect decode, and the fused decode+NMS+rescale."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolo as oy
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _input(B, Sh, Sw, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, Sh, Sw, generator=g)
+    # smooth-ish structure so that activations are image dependent
+    x = torch.nn.functional.avg_pool2d(x, 5, 1, 2) * 0.8 + 0.1 * x
+    return x
+
+
+def _to_nhwc4(x):
+    B, C, H, W = x.shape
+    out = torch.zeros(B, H, W, 4, dtype=torch.bfloat16)
+    out[..., :3] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out.contiguous()
+
+
+@pytest.fixture(scope="module")
+def model_n():
+    from caesar_yolo_b200 import ops, weights as W
+    w = W.make_random_weights('n', 5, seed=0)
+    return w, ops.DeviceModel(w)
+
+
+@pytest.mark.parametrize("B,Sh,Sw", [(1, 640, 640), (2, 640, 320), (3, 320, 320)])
+def test_forward_v8n_matches_oracle(model_n, B, Sh, Sw):
+    w, dm = model_n
+    x = _input(B, Sh, Sw, seed=B)
+    heads = dm.forward_tensors(_to_nhwc4(x).to(DEV))
+    torch.cuda.synchronize()
+    o_emu = oy.OracleYolo(w, emulate_bf16=True)
+    o_f32 = oy.OracleYolo(w, emulate_bf16=False)
+    with torch.no_grad():
+        he = o_emu.forward_heads(x)
+        hf = o_f32.forward_heads(x)
+    for l in range(3):
+        got = heads[l].cpu()[..., :64 + 5].permute(0, 3, 1, 2)
+        scale = hf[l].abs().max().item()
+        err_emu = (got - he[l]).abs().max().item() / scale
+        err_f32 = (got - hf[l]).abs().max().item() / scale
+        q = (he[l] - hf[l]).abs().max().item() / scale
+        # kernel vs same-precision oracle: only accumulation-order noise amplified through bf16 re-rounding
+        assert err_emu < 0.03, (l, err_emu, err_f32, q)
+        # vs the reference's fp32: bounded by the bf16 quantisation noise the emulated oracle shows
+        assert err_f32 < max(0.06, 3 * q), (l, err_emu, err_f32, q)
+
+
+def test_forward_v8l_small(model_n):
+    from caesar_yolo_b200 import ops, weights as W
+    w = W.make_random_weights('l', 5, seed=0)
+    dm = ops.DeviceModel(w)
+    x = _input(2, 320, 320, seed=7)
+    heads = dm.forward_tensors(_to_nhwc4(x).to(DEV))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        he = oy.OracleYolo(w, emulate_bf16=True).forward_heads(x)
+    for l in range(3):
+        got = heads[l].cpu()[..., :69].permute(0, 3, 1, 2)
+        scale = he[l].abs().max().item()
+        assert (got - he[l]).abs().max().item() / scale < 0.04
+    info = dm.info(1, 640, 640)
+    assert abs(info['flops'] / 1e9 - 164.82) < 0.5
+    assert abs(info['nparams'] / 1e6 - 43.61) < 0.1
+
+
+def _rand_heads(B, Sh, Sw, nc, seed, cls_bias=-2.0):
+    g = torch.Generator().manual_seed(seed)
+    heads = []
+    for s in (8, 16, 32):
+        h = torch.zeros(B, Sh // s, Sw // s, 80)
+        h[..., :64] = torch.randn(B, Sh // s, Sw // s, 64, generator=g) * 2.0
+        h[..., 64:64 + nc] = torch.randn(B, Sh // s, Sw // s, nc, generator=g) * 1.5 + cls_bias
+        heads.append(h)
+    return heads
+
+
+def _oracle_pred(heads, nc):
+    net = oy.OracleYolo.__new__(oy.OracleYolo)
+    net.nc = nc
+    return net.decode([h[..., :64 + nc].permute(0, 3, 1, 2).contiguous() for h in heads])
+
+
+@pytest.mark.parametrize("B,Sh,Sw", [(2, 640, 640), (1, 640, 320), (2, 1024, 1024)])
+def test_decode_matches_oracle(B, Sh, Sw):
+    from caesar_yolo_b200 import ops
+    heads = _rand_heads(B, Sh, Sw, 5, seed=Sh + Sw)
+    pred = ops.decode_pred([h.to(DEV) for h in heads], B, Sh, Sw, 5, DEV).cpu()
+    want = _oracle_pred(heads, 5)
+    assert pred.shape == want.shape
+    assert torch.allclose(pred[:, :4], want[:, :4], rtol=1e-5, atol=1e-3)
+    assert torch.allclose(pred[:, 4:], want[:, 4:], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,Sh,Sw,Ty,Tx,conf,bias", [
+    (2, 640, 640, 512, 512, 0.25, -3.0),
+    (2, 640, 640, 132, 132, 0.05, -2.0),
+    (1, 640, 320, 512, 256, 0.05, -1.0),
+    (2, 1024, 1024, 512, 512, 0.05, -0.5),   # dense: ~10k candidates per tile
+    (1, 640, 640, 512, 512, 0.99, -3.0),     # (almost) nothing above threshold
+])
+def test_postprocess_matches_oracle(B, Sh, Sw, Ty, Tx, conf, bias):
+    """Kept set and order must equal ultralytics NMS on the oracle's decode of the same head tensors; boxes equal up
+    to the fp32 rounding of expf (GPU libm vs CPU)."""
+    from caesar_yolo_b200 import ops
+    heads = _rand_heads(B, Sh, Sw, 5, seed=int(conf * 100) + Sh, cls_bias=bias)
+    _, _, lb = ops.letterbox_shape(Ty, Tx, max(Sh, Sw))
+    lbd = ops.letterbox_array([lb] * B, DEV)
+    dets, nd = ops.postprocess([h.to(DEV) for h in heads], B, Sh, Sw, 5, conf, 0.5, lbd, DEV)
+    dets, nd = dets.cpu(), nd.cpu()
+    # feed the GPU's own decode to the oracle NMS: isolates NMS/threshold/rescale logic from expf rounding
+    pred = ops.decode_pred([h.to(DEV) for h in heads], B, Sh, Sw, 5, DEV).cpu()
+    for b in range(B):
+        want = oy.nms_single(pred[b], conf, 0.5)
+        if want.shape[0]:
+            want[:, :4] = oy.scale_boxes((Sh, Sw), want[:, :4], (Ty, Tx))
+        n = int(nd[b])
+        assert n == want.shape[0]
+        got = dets[b, :n]
+        assert torch.equal(got[:, 4], want[:, 4]) and torch.equal(got[:, 5], want[:, 5])
+        assert torch.allclose(got[:, :4], want[:, :4], rtol=0, atol=2e-3)
