@@ -352,7 +352,7 @@ int merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const 
     int *is_edge, *is_plain, *epos, *ppos, *vert_rec, *tile_vcount, *tile_vstart, *deg, *adj_off, *parent, *is_root,
         *comp_size, *comp_rank, *stack_off, *cursor, *stack, *sums, *scalars, *msize;
     unsigned char* visited;
-    size_t ints = (size_t)n * 14 + (size_t)T * 2 + nsums + 64;
+    size_t ints = (size_t)n * 16 + (size_t)T * 2 + nsums + 64;  // 15 n-sized arrays + adj_off[n+1]
     int* ws;
     if (cudaMallocAsync(&ws, ints * sizeof(int) + (size_t)n + 16, st) != cudaSuccess) return -3;
     int* p = ws;

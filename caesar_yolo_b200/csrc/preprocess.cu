@@ -1,7 +1,958 @@
-// TEMPORARY stub (replaced by the real chain kernels in the next commit).
+// Preprocessing chain on the device: tile cut-out (FITS byte order, NaN -> 0), the run.py stage list of
+// caesar_yolo/preprocessing.py, and the ultralytics predictor preprocess (letterbox resize, channel flip, /255).
+//
+// Reference: BkgSubtractor (caesar_yolo/preprocessing.py:591-658), SigmaClipShifter (:664-717), SigmaClipper
+// (:723-771), ChanResizer (:1077-1133), ZScaleTransformer (:934-971), Chan3Trasformer (:1020-1072), HistEqualizer
+// (:977-1012), MinMaxNormalizer (:75-111), stage order scripts/run.py:272-293, Analyzer.predict front part
+// (caesar_yolo/evaluation.py:146-176); astropy sigma_clip / ZScaleInterval, skimage equalize_hist and the
+// ultralytics LetterBox semantics are restated in SURVEY.md App. A.1-A.4.
+//
+// Design.  Every stage of the chain is a monotone non-decreasing scalar map of the pixel value, and "0 means masked"
+// is sticky.  So each channel is represented by a short op list (scalars only) applied to the ORIGINAL pixel value
+// in fp64, never by a materialised fp64 image:
+//   kernel 1 (pp_sort_kernel):   one CTA per tile; cut-out + byte swap + NaN->0 into a native fp32 tile buffer, then
+//                                an in-L2 LSD radix sort of the non-masked pixels (order-preserving keys).
+//   kernel 2 (pp_chain_kernel):  one CTA per tile; runs the stage list.  Order statistics (medians, clip bounds,
+//                                histogram edges) are O(log n) lookups in the sorted array through the monotone op
+//                                list; means/standard deviations are two-pass fp64 block reductions (numpy's
+//                                definition) with warp-shuffle trees; zscale sorts its 1000 positional samples in
+//                                shared memory and does the iterative line fit in fp64.  Writes the chain output
+//                                (fp32 HWC) with one fused evaluation of the final op lists.
+//   kernel 3 (pp_resize_kernel): half-pixel bilinear letterbox resize (double-precision source coordinates like
+//                                cv2.resize on float64), pad 114, channel reversal, /255, bf16 NHWC(4) store.
 #include "common.h"
-extern "C" size_t cy_preprocess_scratch_bytes(const cy_pp_config*, int, int, int) { return 256; }
-extern "C" int cy_preprocess(const cy_pp_config*, const void*, long long, int, const int32_t*, const int32_t*, int, int,
-                             int, int, float*, void*, float*, int32_t*, void*, uintptr_t) {
-    return cy::set_error(CY_ERR_STATE, "cy_preprocess not built yet");
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace cy {
+
+static constexpr int kPPThreads = 1024;
+static constexpr int kPPWarps = kPPThreads / 32;
+static constexpr int kMaxOps = 12;
+static constexpr int kMaxZero = 8;
+
+enum OpKind { OP_SUB = 1, OP_SHIFT = 2, OP_CLAMP = 3, OP_ZSCALE = 4, OP_HISTEQ = 5, OP_MINMAX = 6 };
+
+struct Chan {
+    int nops;
+    int hid;  // history id: channels with equal hid hold identical data
+    int kind[kMaxOps];
+    double p0[kMaxOps], p1[kMaxOps], p2[kMaxOps], p3[kMaxOps];
+    int nz;  // zero (masked) index ranges in the sorted array, sorted + merged
+    int z0[kMaxZero], z1[kMaxZero];
+};
+
+struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per chain: Chan3 channel 2)
+    double edges[257];
+    double cdf[256];
+};
+
+struct PPParams {
+    cy_pp_config cfg;
+    const uint32_t* img;
+    long long row_stride;
+    int big_endian;
+    const int* x0;
+    const int* y0;
+    int B, Ty, Tx;
+    float* tilebuf;     // [B][N] native fp32, non-finite -> 0
+    uint32_t* keysA;    // [B][N] sorted live values (fp32 bits after the sort kernel)
+    uint32_t* keysB;    // [B][N] ping-pong
+    uint32_t* keysC;    // [B][N] sorted live values outside the bkg box (only when use_box_mask_in_bkg)
+    int* nlive;         // [B]
+    int* nbox;          // [B]
+    float* chain_out;   // [B][N][3]
+    int* status;        // [B]
+};
+
+// ------------------------------------------------------------------------------------------ small device helpers
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Block-wide sum of up to three doubles; result valid in all threads.  red: shared double[3*32+3].
+__device__ void block_sum3(double& a, double& b, double& c, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    __syncthreads();  // protect `red` from the previous use
+    if (lane == 0) {
+        red[w] = a;
+        red[32 + w] = b;
+        red[64 + w] = c;
+    }
+    __syncthreads();
+    if (w == 0) {
+        double x = red[lane], y = red[32 + lane], z = red[64 + lane];
+        x = warp_sum(x);
+        y = warp_sum(y);
+        z = warp_sum(z);
+        if (lane == 0) {
+            red[96] = x;
+            red[97] = y;
+            red[98] = z;
+        }
+    }
+    __syncthreads();
+    a = red[96];
+    b = red[97];
+    c = red[98];
+}
+__device__ void block_minmax(double& mn, double& mx, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __syncthreads();
+    if (lane == 0) {
+        red[w] = mn;
+        red[32 + w] = mx;
+    }
+    __syncthreads();
+    if (w == 0) {
+        double x = red[lane], y = red[32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+            y = fmax(y, __shfl_xor_sync(0xffffffffu, y, o));
+        }
+        if (lane == 0) {
+            red[96] = x;
+            red[97] = y;
+        }
+    }
+    __syncthreads();
+    mn = red[96];
+    mx = red[97];
+}
+
+// np.interp(v, centers, cdf) with centers = (edges[:-1] + edges[1:]) / 2 (skimage equalize_hist, App. A.3)
+__device__ double histeq_interp(const HistEq& h, double v) {
+    const double c0 = (h.edges[0] + h.edges[1]) / 2.0, c255 = (h.edges[255] + h.edges[256]) / 2.0;
+    if (!(v > c0)) return h.cdf[0];
+    if (v >= c255) return h.cdf[255];
+    int lo = 0, hi = 255;  // invariant: center[lo] <= v < center[hi]
+    while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        const double cm = (h.edges[m] + h.edges[m + 1]) / 2.0;
+        if (cm <= v) lo = m; else hi = m;
+    }
+    const double xl = (h.edges[lo] + h.edges[lo + 1]) / 2.0, xr = (h.edges[lo + 1] + h.edges[lo + 2]) / 2.0;
+    const double slope = __ddiv_rn(__dsub_rn(h.cdf[lo + 1], h.cdf[lo]), __dsub_rn(xr, xl));
+    return __dadd_rn(__dmul_rn(slope, __dsub_rn(v, xl)), h.cdf[lo]);
+}
+
+// Apply the first `nops` ops of channel c to the original pixel value x (fp64, reference operation order, no FMA
+// contraction).  STICKY: a value that is (or becomes) exactly 0 stays 0 — the reference's `out[~cond] = 0`.
+// !STICKY: the plain monotone composition (used to locate index ranges among live elements).
+template <bool STICKY>
+__device__ double eval_ops(const Chan& c, int nops, const HistEq& he, double v) {
+    for (int k = 0; k < nops; ++k) {
+        if (STICKY && v == 0.0) return 0.0;
+        switch (c.kind[k]) {
+            case OP_SUB: v = __dsub_rn(v, c.p0[k]); break;
+            case OP_SHIFT:
+                v = __dsub_rn(v, c.p0[k]);
+                if (v < 0.0) v = 0.0;
+                break;
+            case OP_CLAMP:
+                if (v < c.p0[k]) v = c.p0[k];
+                if (v > c.p1[k]) v = c.p1[k];
+                break;
+            case OP_ZSCALE:
+                v = __dsub_rn(v, c.p0[k]);
+                if (c.p1[k] != 0.0) v = __ddiv_rn(v, c.p1[k]);
+                v = fmin(fmax(v, 0.0), 1.0);
+                break;
+            case OP_HISTEQ: v = histeq_interp(he, v); break;
+            case OP_MINMAX:
+                v = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(v, c.p0[k]), c.p1[k]), c.p2[k]), c.p3[k]);
+                break;
+        }
+    }
+    return v;
+}
+
+// first index i in [a,b) with f*(S[i]) >= t (STRICT: > t); b if none.  Executed redundantly by every thread.
+template <bool STRICT>
+__device__ int lower_index(const Chan& c, int nops, const HistEq& he, const float* S, int a, int b, double t) {
+    int lo = a, hi = b;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        const double v = eval_ops<false>(c, nops, he, (double)S[m]);
+        const bool ok = STRICT ? (v > t) : (v >= t);
+        if (ok) hi = m; else lo = m + 1;
+    }
+    return lo;
+}
+
+__device__ void add_zero_range(Chan& c, int h0, int h1) {  // single thread
+    if (h1 <= h0) return;
+    int n = c.nz;
+    if (n < kMaxZero) {
+        c.z0[n] = h0;
+        c.z1[n] = h1;
+        ++n;
+    }
+    // insertion sort + merge
+    for (int i = n - 1; i > 0 && c.z0[i] < c.z0[i - 1]; --i) {
+        const int t0 = c.z0[i], t1 = c.z1[i];
+        c.z0[i] = c.z0[i - 1]; c.z1[i] = c.z1[i - 1];
+        c.z0[i - 1] = t0; c.z1[i - 1] = t1;
+    }
+    int m = 0;
+    for (int i = 1; i < n; ++i) {
+        if (c.z0[i] <= c.z1[m]) {
+            if (c.z1[i] > c.z1[m]) c.z1[m] = c.z1[i];
+        } else {
+            ++m;
+            c.z0[m] = c.z0[i];
+            c.z1[m] = c.z1[i];
+        }
+    }
+    c.nz = n ? m + 1 : 0;
+}
+__device__ int live_count(const Chan& c, int a, int b) {
+    int n = b - a;
+    for (int i = 0; i < c.nz; ++i) {
+        const int lo = max(a, c.z0[i]), hi = min(b, c.z1[i]);
+        if (hi > lo) n -= hi - lo;
+    }
+    return n;
+}
+// index of the k-th (0-based) live element at or after a
+__device__ int kth_live(const Chan& c, int a, int k) {
+    int pos = a;
+    for (int i = 0; i < c.nz; ++i) {
+        if (c.z1[i] <= pos) continue;
+        if (c.z0[i] <= pos) {
+            pos = c.z1[i];
+            continue;
+        }
+        const int gap = c.z0[i] - pos;
+        if (k < gap) return pos + k;
+        k -= gap;
+        pos = c.z1[i];
+    }
+    return pos + k;
+}
+
+struct Shared {
+    Chan ch[3];
+    HistEq he;
+    double red[3 * 32 + 4];
+    double zs[1024];         // zscale samples / flat residuals
+    unsigned char zbad[1024];
+    unsigned char zbad2[1024];
+    int hist[256];
+    int next_hid;
+    int fail;                // tile status
+};
+
+// mean / std (ddof 0, two-pass) / count of the live values f(S[i]), i in [a,b)
+__device__ void range_stats(const Chan& c, const HistEq& he, const float* S, int a, int b, double* red, double& mean,
+                            double& sd, int& cnt) {
+    double s = 0.0, n = 0.0, z = 0.0;
+    for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
+        const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
+        if (v != 0.0) {
+            s += v;
+            n += 1.0;
+        }
+    }
+    block_sum3(s, n, z, red);
+    cnt = (int)n;
+    mean = n > 0 ? s / n : 0.0;
+    double q = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
+        const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
+        if (v != 0.0) {
+            const double d = v - mean;
+            q += d * d;
+        }
+    }
+    block_sum3(q, z1, z2, red);
+    sd = n > 0 ? sqrt(q / n) : 0.0;
+}
+
+__device__ double live_median(const Chan& c, const HistEq& he, const float* S, int a, int cnt) {
+    // numpy median: middle element, or mean of the two middle elements
+    if (cnt & 1) return eval_ops<true>(c, c.nops, he, (double)S[kth_live(c, a, cnt >> 1)]);
+    const double x = eval_ops<true>(c, c.nops, he, (double)S[kth_live(c, a, (cnt >> 1) - 1)]);
+    const double y = eval_ops<true>(c, c.nops, he, (double)S[kth_live(c, a, cnt >> 1)]);
+    return (x + y) / 2.0;
+}
+
+// astropy SigmaClip (axis=None, median/std, maxiters 5; App. A.1) over the live values of channel c in S[0..n).
+// Outputs the bounds of the last iteration and the (mean, std) of the survivors.  Returns false if the set is empty.
+__device__ bool sigma_clip(Shared& sh, const Chan& c, const float* S, int n, double sig_lo, double sig_hi, double& lo,
+                           double& hi, double& mean, double& sd) {
+    int a = 0, b = n;
+    int cnt;
+    range_stats(c, sh.he, S, a, b, sh.red, mean, sd, cnt);
+    if (cnt <= 0) return false;
+    lo = hi = 0.0;
+    for (int it = 0; it < 5; ++it) {
+        const double med = live_median(c, sh.he, S, a, cnt);
+        lo = med - sd * sig_lo;
+        hi = med + sd * sig_hi;
+        const int na = lower_index<false>(c, c.nops, sh.he, S, a, b, lo);   // first f >= lo
+        const int nb = lower_index<true>(c, c.nops, sh.he, S, na, b, hi);   // first f > hi
+        const int ncnt = live_count(c, na, nb);
+        const int changed = cnt - ncnt;
+        a = na;
+        b = nb;
+        if (changed == 0) break;
+        range_stats(c, sh.he, S, a, b, sh.red, mean, sd, cnt);
+        if (cnt <= 0) return false;
+    }
+    return true;
+}
+
+// Append an op to channel c and register the pixels it newly maps to exactly 0 (they become masked).
+__device__ void push_op(Shared& sh, int ci, const float* S, int n, int kind, double p0, double p1, double p2, double p3) {
+    Chan& c = sh.ch[ci];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int k = c.nops;
+        if (k < kMaxOps) {
+            c.kind[k] = kind;
+            c.p0[k] = p0; c.p1[k] = p1; c.p2[k] = p2; c.p3[k] = p3;
+            c.nops = k + 1;
+        } else {
+            sh.fail = -4;
+        }
+    }
+    __syncthreads();
+    // zero set of the plain composition is a contiguous index range (monotone): [first >= 0, first > 0)
+    const int h0 = lower_index<false>(c, c.nops, sh.he, S, 0, n, 0.0);
+    const int h1 = lower_index<true>(c, c.nops, sh.he, S, h0, n, 0.0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        add_zero_range(c, h0, h1);
+        c.hid = sh.next_hid++;
+    }
+    __syncthreads();
+}
+
+__device__ void copy_chan(Shared& sh, int dst, int src) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.ch[dst] = sh.ch[src];
+    __syncthreads();
+}
+
+// astropy ZScaleInterval.get_limits (App. A.2) on channel c (positional samples of the current image, zeros
+// included), then the OP_ZSCALE op.
+__device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const float* S, int n, double contrast) {
+    const Chan& c = sh.ch[ci];
+    const int t = threadIdx.x;
+    const int stride = (int)fmax(1.0, (double)N / 1000.0);
+    int npix = (N + stride - 1) / stride;
+    if (npix > 1000) npix = 1000;
+    __syncthreads();
+    sh.zs[t] = (t < npix) ? eval_ops<true>(c, c.nops, sh.he, (double)tile[(long long)t * stride]) : INFINITY;
+    __syncthreads();
+    // bitonic sort ascending, 1024 elements, one compare-exchange per thread pair
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int p = t ^ j;
+            if (p > t) {
+                const double x = sh.zs[t], y = sh.zs[p];
+                const bool asc = ((t & k) == 0);
+                if (asc ? (x > y) : (x < y)) {
+                    sh.zs[t] = y;
+                    sh.zs[p] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const double y = t < npix ? sh.zs[t] : 0.0;
+    const double x = (double)t;
+    double vmin = sh.zs[0], vmax = sh.zs[npix - 1];
+    const int minpix = max(5, (int)(npix * 0.5));
+    int ngood = npix, last = npix + 1;
+    const int ngrow = max(1, (int)(npix * 0.01));
+    sh.zbad[t] = 0;
+    double slope = 0.0, icpt = 0.0;
+    bool fitted = false;
+    __syncthreads();
+    for (int it = 0; it < 5; ++it) {
+        if (ngood >= last || ngood < minpix) break;
+        const bool good = (t < npix) && !sh.zbad[t];
+        // weighted (0/1) least squares line, centred for stability (== np.polyfit deg 1 up to rounding)
+        double sw = good ? 1.0 : 0.0, sx = good ? x : 0.0, sy = good ? y : 0.0;
+        block_sum3(sw, sx, sy, sh.red);
+        const double xm = sx / sw, ym = sy / sw;
+        double sxx = good ? (x - xm) * (x - xm) : 0.0, sxy = good ? (x - xm) * (y - ym) : 0.0, zz = 0.0;
+        block_sum3(sxx, sxy, zz, sh.red);
+        slope = sxy / sxx;
+        icpt = ym - slope * xm;
+        fitted = true;
+        const double flat = y - (slope * x + icpt);
+        double sf = good ? flat : 0.0, z1 = 0.0, z2 = 0.0;
+        block_sum3(sf, z1, z2, sh.red);
+        const double fm = sf / sw;
+        double sq = good ? (flat - fm) * (flat - fm) : 0.0;
+        z1 = z2 = 0.0;
+        block_sum3(sq, z1, z2, sh.red);
+        const double thr = 2.5 * sqrt(sq / sw);
+        if (t < npix && (flat < -thr || flat > thr)) sh.zbad[t] = 1;
+        __syncthreads();
+        // np.convolve(badpix, ones(ngrow), 'same') on bools: out[i] = OR bad[i - ngrow/2 .. i + (ngrow-1)/2]
+        unsigned char nb = 0;
+        if (t < npix) {
+            const int l0 = max(0, t - ngrow / 2), l1 = min(npix - 1, t + (ngrow - 1) / 2);
+            for (int q = l0; q <= l1; ++q) nb |= sh.zbad[q];
+        }
+        sh.zbad2[t] = nb;
+        __syncthreads();
+        sh.zbad[t] = sh.zbad2[t];
+        double g = (t < npix && !nb) ? 1.0 : 0.0;
+        z1 = z2 = 0.0;
+        block_sum3(g, z1, z2, sh.red);
+        last = ngood;
+        ngood = (int)g;
+    }
+    if (ngood >= minpix && fitted) {
+        double sl = slope;
+        if (contrast > 0) sl = sl / contrast;
+        const int center = (npix - 1) / 2;
+        const double med = (npix & 1) ? sh.zs[npix / 2] : (sh.zs[npix / 2 - 1] + sh.zs[npix / 2]) / 2.0;
+        vmin = fmax(vmin, med - (double)(center - 1) * sl);
+        vmax = fmin(vmax, med + (double)(npix - center) * sl);
+    }
+    push_op(sh, ci, S, n, OP_ZSCALE, vmin, vmax - vmin, 0.0, 0.0);
+}
+
+// skimage equalize_hist (App. A.3) on channel c: 256-bin histogram over [min,max] of ALL pixels (masked zeros
+// included), CDF, then OP_HISTEQ.
+__device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const float* S, int n) {
+    const Chan& c = sh.ch[ci];
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += kPPThreads) {
+        const double v = eval_ops<true>(c, c.nops, sh.he, (double)tile[i]);
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    block_minmax(mn, mx, sh.red);
+    double first = mn, last = mx;
+    if (first == last) {  // numpy _get_outer_edges
+        first -= 0.5;
+        last += 0.5;
+    }
+    __syncthreads();
+    // np.linspace(first, last, 257): arange * step + first, endpoint forced
+    const double step = (last - first) / 256.0;
+    for (int i = threadIdx.x; i < 257; i += kPPThreads)
+        sh.he.edges[i] = i == 256 ? last : __dadd_rn(__dmul_rn((double)i, step), first);
+    for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.hist[i] = 0;
+    __syncthreads();
+    const double denom = last - first;
+    for (int i = threadIdx.x; i < N; i += kPPThreads) {
+        const double v = eval_ops<true>(c, c.nops, sh.he, (double)tile[i]);
+        // numpy histogram fast path for uniform bins
+        int idx = (int)(__dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), 256.0));
+        if (idx == 256) idx = 255;
+        if (idx < 0) idx = 0;
+        if (idx > 255) idx = 255;
+        if (v < sh.he.edges[idx]) --idx;
+        else if (idx != 255 && v >= sh.he.edges[idx + 1]) ++idx;
+        if (idx < 0) idx = 0;
+        atomicAdd(&sh.hist[idx], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long cum = 0;
+        for (int i = 0; i < 256; ++i) {
+            cum += sh.hist[i];
+            sh.he.cdf[i] = (double)cum;
+        }
+        const double tot = (double)cum;
+        for (int i = 0; i < 256; ++i) sh.he.cdf[i] = sh.he.cdf[i] / tot;
+    }
+    __syncthreads();
+    push_op(sh, ci, S, n, OP_HISTEQ, 0.0, 0.0, 0.0, 0.0);
+}
+
+// SigmaClipper._clip (preprocessing.py:735-751) on channel ci
+__device__ bool sigma_clipper_stage(Shared& sh, int ci, const float* S, int n, double s_lo, double s_hi) {
+    // astropy: sigma_lower = sigma_lower or sigma(=3.0): a falsy 0 falls back to 3 (App. A.1 / B#1)
+    const double slo = s_lo != 0.0 ? s_lo : 3.0, shi = s_hi != 0.0 ? s_hi : 3.0;
+    double lo, hi, mean, sd;
+    if (!sigma_clip(sh, sh.ch[ci], S, n, slo, shi, lo, hi, mean, sd)) return false;
+    push_op(sh, ci, S, n, OP_CLAMP, lo, hi, 0.0, 0.0);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ kernel 1: cut-out + sort
+
+__device__ __forceinline__ float load_pixel(const PPParams& p, int b, int idx) {
+    const int y = idx / p.Tx, x = idx - y * p.Tx;
+    uint32_t raw = p.img[(long long)(p.y0[b] + y) * p.row_stride + p.x0[b] + x];
+    if (p.big_endian) raw = __byte_perm(raw, 0, 0x0123);
+    const float f = __uint_as_float(raw);
+    return isfinite(f) ? f : 0.0f;  // utils.py:219,394
+}
+
+// LSD radix sort (4 x 8 bit) of `n` keys in global memory with one CTA: each warp owns a contiguous segment; ranks
+// inside a 32-key group come from __match_any_sync, so every pass is stable.
+__device__ void block_radix_sort(uint32_t* a, uint32_t* b, int n, int (*hist)[256], int* dtot) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int seg = (n + kPPWarps - 1) / kPPWarps;
+    seg = (seg + 31) & ~31;
+    const int s0 = min(n, w * seg), s1 = min(n, s0 + seg);
+    uint32_t* src = a;
+    uint32_t* dst = b;
+    for (int shift = 0; shift < 32; shift += 8) {
+        for (int i = threadIdx.x; i < kPPWarps * 256; i += kPPThreads) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        for (int i = s0 + lane; i < s1; i += 32) atomicAdd(&hist[w][(src[i] >> shift) & 255u], 1);
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            int tot = 0;
+            for (int q = 0; q < kPPWarps; ++q) {
+                const int cnt = hist[q][threadIdx.x];
+                hist[q][threadIdx.x] = tot;
+                tot += cnt;
+            }
+            dtot[threadIdx.x] = tot;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive scan of the 256 digit totals by one warp (8 per lane)
+            int v[8], s = 0;
+            for (int q = 0; q < 8; ++q) {
+                v[q] = dtot[lane * 8 + q];
+                s += v[q];
+            }
+            int inc = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            int run = inc - s;
+            for (int q = 0; q < 8; ++q) {
+                dtot[lane * 8 + q] = run;
+                run += v[q];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            const int base = dtot[threadIdx.x];
+            for (int q = 0; q < kPPWarps; ++q) hist[q][threadIdx.x] += base;
+        }
+        __syncthreads();
+        for (int i0 = s0; i0 < s1; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < s1;
+            const uint32_t m = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const uint32_t key = src[i];
+                const uint32_t d = (key >> shift) & 255u;
+                const uint32_t peers = __match_any_sync(m, d);
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                const int pos = hist[w][d] + rank;
+                dst[pos] = key;
+                __syncwarp(m);
+                if (rank == 0) hist[w][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t* t = src;
+        src = dst;
+        dst = t;
+    }
+    // 4 passes: result is back in `a`
+}
+
+__global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_constant__ PPParams p) {
+    __shared__ int hist[kPPWarps][256];
+    __shared__ int dtot[256];
+    __shared__ int s_n, s_nb;
+    const int b = blockIdx.x;
+    const int N = p.Ty * p.Tx;
+    float* tile = p.tilebuf + (long long)b * N;
+    uint32_t* A = p.keysA + (long long)b * N;
+    uint32_t* Bk = p.keysB + (long long)b * N;
+    uint32_t* C = p.keysC ? p.keysC + (long long)b * N : nullptr;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_nb = 0;
+    }
+    __syncthreads();
+    // box of BkgSubtractor (preprocessing.py:610-621)
+    const int xc = p.Tx / 2, yc = p.Ty / 2;
+    const int dy = (int)(p.Ty * p.cfg.bkg_box_mask_fract / 2.0), dx = (int)(p.Tx * p.cfg.bkg_box_mask_fract / 2.0);
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < N; i0 += kPPThreads) {
+        const int i = i0 + threadIdx.x;
+        float f = 0.f;
+        if (i < N) {
+            f = load_pixel(p, b, i);
+            tile[i] = f;
+        }
+        const bool live = (i < N) && (f != 0.0f);
+        const uint32_t m = __ballot_sync(0xffffffffu, live);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) A[base + __popc(m & ((1u << lane) - 1u))] = f2key(f);
+        if (C) {
+            const int y = i / p.Tx, x = i - y * p.Tx;
+            const bool inbox = (y >= yc - dy && y < yc + dy && x >= xc - dx && x < xc + dx);
+            const bool lb = live && !inbox;
+            const uint32_t m2 = __ballot_sync(0xffffffffu, lb);
+            int base2 = 0;
+            if (lane == 0 && m2) base2 = atomicAdd(&s_nb, __popc(m2));
+            base2 = __shfl_sync(0xffffffffu, base2, 0);
+            if (lb) C[base2 + __popc(m2 & ((1u << lane) - 1u))] = f2key(f);
+        }
+    }
+    __syncthreads();
+    const int n = s_n, nb = s_nb;
+    block_radix_sort(A, Bk, n, hist, dtot);
+    for (int i = threadIdx.x; i < n; i += kPPThreads) A[i] = __float_as_uint(key2f(A[i]));
+    if (C) {
+        __syncthreads();
+        block_radix_sort(C, Bk, nb, hist, dtot);
+        for (int i = threadIdx.x; i < nb; i += kPPThreads) C[i] = __float_as_uint(key2f(C[i]));
+    }
+    if (threadIdx.x == 0) {
+        p.nlive[b] = n;
+        p.nbox[b] = nb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ kernel 2: the chain
+
+__device__ __forceinline__ bool chan_selected(int chid, int c) { return chid == -1 || chid == c; }
+
+__global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_constant__ PPParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+    const int b = blockIdx.x;
+    const int N = p.Ty * p.Tx;
+    const float* tile = p.tilebuf + (long long)b * N;
+    const float* S = reinterpret_cast<const float*>(p.keysA + (long long)b * N);
+    const float* Sbox = p.keysC ? reinterpret_cast<const float*>(p.keysC + (long long)b * N) : nullptr;
+    const int n = p.nlive[b];
+    const cy_pp_config& cfg = p.cfg;
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 3; ++c) {
+            sh.ch[c].nops = 0;
+            sh.ch[c].hid = 0;
+            sh.ch[c].nz = 0;
+        }
+        sh.next_hid = 1;
+        sh.fail = 0;
+    }
+    __syncthreads();
+    bool ok = true;  // uniform across the block
+
+    // Channel de-duplication: a stage applied with equal parameters to channels that hold identical data (equal
+    // history id) gives identical results, so it is computed once and the channel state is copied.  `in_hid[c]` is
+    // the history id channel c had when the current stage processed it (-1: not processed).
+    int in_hid[3];
+    auto find_same = [&](int c) {
+        for (int q = 0; q < c; ++q)
+            if (in_hid[q] >= 0 && in_hid[q] == sh.ch[c].hid) return q;
+        return -1;
+    };
+
+    if (cfg.enabled) {
+        // ---- BkgSubtractor (preprocessing.py:591-658): x - clipped mean
+        if (cfg.subtract_bkg) {
+            in_hid[0] = in_hid[1] = in_hid[2] = -1;
+            for (int c = 0; c < 3 && ok; ++c) {
+                if (!chan_selected(cfg.bkg_chid, c)) continue;
+                const int q = find_same(c), hid = sh.ch[c].hid;
+                if (q >= 0) {
+                    copy_chan(sh, c, q);
+                } else {
+                    double lo, hi, mean, sd;
+                    const float* Sb = cfg.use_box_mask_in_bkg ? Sbox : S;
+                    const int nb = cfg.use_box_mask_in_bkg ? p.nbox[b] : n;
+                    const double sg = cfg.sigma_bkg != 0 ? cfg.sigma_bkg : 3.0;
+                    ok = sigma_clip(sh, sh.ch[c], Sb, nb, sg, sg, lo, hi, mean, sd);
+                    if (ok) push_op(sh, c, S, n, OP_SUB, mean, 0, 0, 0);
+                }
+                in_hid[c] = hid;
+            }
+        }
+        // ---- SigmaClipShifter (preprocessing.py:664-717): x - (clipmean + sigma*std), negatives -> 0
+        if (cfg.clip_shift_data && ok) {
+            in_hid[0] = in_hid[1] = in_hid[2] = -1;
+            for (int c = 0; c < 3 && ok; ++c) {
+                if (!chan_selected(cfg.clip_chid, c)) continue;
+                const int q = find_same(c), hid = sh.ch[c].hid;
+                if (q >= 0) {
+                    copy_chan(sh, c, q);
+                } else {
+                    double lo, hi, mean, sd;
+                    const double sg = cfg.sigma_clip != 0 ? cfg.sigma_clip : 3.0;
+                    ok = sigma_clip(sh, sh.ch[c], S, n, sg, sg, lo, hi, mean, sd);
+                    if (ok) push_op(sh, c, S, n, OP_SHIFT, mean + cfg.sigma_clip * sd, 0, 0, 0);
+                }
+                in_hid[c] = hid;
+            }
+        }
+        // ---- SigmaClipper (preprocessing.py:723-771)
+        if (cfg.clip_data && ok) {
+            in_hid[0] = in_hid[1] = in_hid[2] = -1;
+            for (int c = 0; c < 3 && ok; ++c) {
+                if (!chan_selected(cfg.clip_chid, c)) continue;
+                const int q = find_same(c), hid = sh.ch[c].hid;
+                if (q >= 0) copy_chan(sh, c, q);
+                else ok = sigma_clipper_stage(sh, c, S, n, cfg.sigma_clip_low, cfg.sigma_clip_up);
+                in_hid[c] = hid;
+            }
+        }
+        // ---- ChanResizer: the cube already has 3 channels (evaluation.py:146-154) -> no-op for nchannels 1 or 3
+        // ---- ZScaleTransformer (preprocessing.py:934-971)
+        if (cfg.zscale_stretch && ok) {
+            in_hid[0] = in_hid[1] = in_hid[2] = -1;
+            for (int c = 0; c < 3; ++c) {
+                int q = -1;
+                for (int k = 0; k < c; ++k)
+                    if (in_hid[k] == sh.ch[c].hid && cfg.zscale_contrasts[k] == cfg.zscale_contrasts[c]) q = k;
+                const int hid = sh.ch[c].hid;
+                if (q >= 0) copy_chan(sh, c, q);
+                else zscale_stage(sh, c, tile, N, S, n, cfg.zscale_contrasts[c]);
+                in_hid[c] = hid;
+            }
+        }
+        // ---- Chan3Trasformer (preprocessing.py:1020-1072)
+        if (cfg.chan3_preproc && ok) {
+            const int hid0 = sh.ch[0].hid, hid1 = sh.ch[1].hid;
+            ok = sigma_clipper_stage(sh, 0, S, n, cfg.sigma_clip_baseline, cfg.sigma_clip_up);
+            if (ok) zscale_stage(sh, 0, tile, N, S, n, cfg.zscale_contrasts[0]);
+            if (ok) {
+                const double blo = cfg.sigma_clip_baseline != 0.0 ? cfg.sigma_clip_baseline : 3.0;
+                const double llo = cfg.sigma_clip_low != 0.0 ? cfg.sigma_clip_low : 3.0;
+                if (hid0 == hid1 && blo == llo) {
+                    copy_chan(sh, 1, 0);
+                } else {
+                    ok = sigma_clipper_stage(sh, 1, S, n, cfg.sigma_clip_low, cfg.sigma_clip_up);
+                    if (ok) zscale_stage(sh, 1, tile, N, S, n, cfg.zscale_contrasts[0]);
+                }
+            }
+            if (ok) histeq_stage(sh, 2, tile, N, S, n);
+        }
+        // ---- MinMaxNormalizer (preprocessing.py:75-111)
+        if (cfg.normalize_minmax && ok) {
+            in_hid[0] = in_hid[1] = in_hid[2] = -1;
+            for (int c = 0; c < 3 && ok; ++c) {
+                const int q = find_same(c), hid = sh.ch[c].hid;
+                if (q >= 0) {
+                    copy_chan(sh, c, q);
+                } else {
+                    const Chan& ch = sh.ch[c];
+                    double mn = INFINITY, mx = -INFINITY;
+                    for (int i = threadIdx.x; i < n; i += kPPThreads) {
+                        const double v = eval_ops<true>(ch, ch.nops, sh.he, (double)S[i]);
+                        if (v != 0.0) {
+                            mn = fmin(mn, v);
+                            mx = fmax(mx, v);
+                        }
+                    }
+                    block_minmax(mn, mx, sh.red);
+                    if (!(mn <= mx)) ok = false;  // no non-zero pixel -> None (preprocessing.py:101-103)
+                    else push_op(sh, c, S, n, OP_MINMAX, mn, mx - mn, cfg.norm_max - cfg.norm_min, cfg.norm_min);
+                }
+                in_hid[c] = hid;
+            }
+        }
+    }
+
+    // ---- chain output (fp32 HWC) + the reference's degenerate-image check on rows 0..2 (evaluation.py:171-176)
+    float* out = p.chain_out + (long long)b * N * 3;
+    if (!ok) {
+        for (int i = threadIdx.x; i < N * 3; i += kPPThreads) out[i] = 0.f;
+        if (threadIdx.x == 0) p.status[b] = sh.fail ? sh.fail : -1;
+        return;
+    }
+    const bool same01 = sh.ch[0].hid == sh.ch[1].hid, same02 = sh.ch[0].hid == sh.ch[2].hid,
+               same12 = sh.ch[1].hid == sh.ch[2].hid;
+    for (int i = threadIdx.x; i < N; i += kPPThreads) {
+        const double x = (double)tile[i];
+        const double v0 = eval_ops<true>(sh.ch[0], sh.ch[0].nops, sh.he, x);
+        const double v1 = same01 ? v0 : eval_ops<true>(sh.ch[1], sh.ch[1].nops, sh.he, x);
+        const double v2 = same02 ? v0 : (same12 ? v1 : eval_ops<true>(sh.ch[2], sh.ch[2].nops, sh.he, x));
+        out[(long long)i * 3 + 0] = (float)v0;
+        out[(long long)i * 3 + 1] = (float)v1;
+        out[(long long)i * 3 + 2] = (float)v2;
+    }
+    int bad = 0;
+    for (int r = 0; r < 3 && r < p.Ty; ++r) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (int i = threadIdx.x; i < p.Tx; i += kPPThreads) {
+            const double x = (double)tile[r * p.Tx + i];
+            for (int c = 0; c < 3; ++c) {
+                const double v = eval_ops<true>(sh.ch[c], sh.ch[c].nops, sh.he, x);
+                mn = fmin(mn, v);
+                mx = fmax(mx, v);
+            }
+        }
+        block_minmax(mn, mx, sh.red);
+        if (mn == mx) bad = 1;
+    }
+    if (threadIdx.x == 0) p.status[b] = sh.fail ? sh.fail : (bad ? -1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------ kernel 3: letterbox resize
+
+struct ResizeParams {
+    const float* chain;  // [B,Ty,Tx,3]
+    __nv_bfloat16* out;  // [B,Sh,Sw,4]
+    float* out_f32;      // optional [B,3,Sh,Sw]
+    int B, Ty, Tx, Sh, Sw;
+    int new_h, new_w, top, left;
+    double scale_y, scale_x;  // 1 / (dst/src), as cv2.resize computes it
+};
+
+__global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)r.B * r.Sh * r.Sw;
+    if (idx >= total) return;
+    const int ox = (int)(idx % r.Sw);
+    const int oy = (int)((idx / r.Sw) % r.Sh);
+    const int b = (int)(idx / ((long long)r.Sw * r.Sh));
+    float v[3] = {114.f, 114.f, 114.f};  // cv2.copyMakeBorder value
+    const int ry = oy - r.top, rx = ox - r.left;
+    if (ry >= 0 && ry < r.new_h && rx >= 0 && rx < r.new_w) {
+        // cv2.resize INTER_LINEAR: half-pixel centres, clamp at the borders
+        double fy = ((double)ry + 0.5) * r.scale_y - 0.5;
+        double fx = ((double)rx + 0.5) * r.scale_x - 0.5;
+        int y0 = (int)floor(fy), x0 = (int)floor(fx);
+        float wy = (float)(fy - (double)y0), wx = (float)(fx - (double)x0);
+        if (y0 < 0) { y0 = 0; wy = 0.f; }
+        if (y0 >= r.Ty - 1) { y0 = r.Ty - 1; wy = 0.f; }
+        if (x0 < 0) { x0 = 0; wx = 0.f; }
+        if (x0 >= r.Tx - 1) { x0 = r.Tx - 1; wx = 0.f; }
+        const int y1 = min(y0 + 1, r.Ty - 1), x1 = min(x0 + 1, r.Tx - 1);
+        const float* base = r.chain + (long long)b * r.Ty * r.Tx * 3;
+        const float* p00 = base + ((long long)y0 * r.Tx + x0) * 3;
+        const float* p01 = base + ((long long)y0 * r.Tx + x1) * 3;
+        const float* p10 = base + ((long long)y1 * r.Tx + x0) * 3;
+        const float* p11 = base + ((long long)y1 * r.Tx + x1) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t0 = __ldg(p00 + c) * (1.f - wx) + __ldg(p01 + c) * wx;
+            const float t1 = __ldg(p10 + c) * (1.f - wx) + __ldg(p11 + c) * wx;
+            v[c] = t0 * (1.f - wy) + t1 * wy;
+        }
+    }
+    // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
+    const float m0 = v[2] / 255.f, m1 = v[1] / 255.f, m2 = v[0] / 255.f;
+    uint2 pk;
+    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+    p2[0] = __floats2bfloat162_rn(m0, m1);
+    p2[1] = __floats2bfloat162_rn(m2, 0.f);
+    *reinterpret_cast<uint2*>(r.out + idx * 4) = pk;
+    if (r.out_f32) {
+        const long long plane = (long long)r.Sh * r.Sw;
+        float* o = r.out_f32 + (long long)b * 3 * plane + (long long)oy * r.Sw + ox;
+        o[0] = m0;
+        o[plane] = m1;
+        o[2 * plane] = m2;
+    }
+}
+
+}  // namespace cy
+
+// ------------------------------------------------------------------------------------------ C ABI
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg, int B, int Ty, int Tx) {
+    const size_t N = (size_t)Ty * Tx;
+    const int nbuf = 3 + ((cfg && cfg->enabled && cfg->subtract_bkg && cfg->use_box_mask_in_bkg) ? 1 : 0);
+    return (size_t)nbuf * align256((size_t)B * N * 4) + 2 * align256((size_t)B * 4) + 256;
+}
+
+extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long row_stride, int big_endian,
+                             const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz,
+                             float* chain_out, void* model_in, float* model_in_f32, int32_t* status, void* scratch,
+                             uintptr_t stream) {
+    using namespace cy;
+    if (!cfg || !img || !tile_x0 || !tile_y0 || !chain_out || !status || !scratch)
+        return set_error(CY_ERR_INVALID, "cy_preprocess: null argument");
+    if (B <= 0 || Ty <= 0 || Tx <= 0) return set_error(CY_ERR_INVALID, "cy_preprocess: invalid shape");
+    if ((long long)Ty * Tx >= (1ll << 30)) return set_error(CY_ERR_INVALID, "cy_preprocess: tile too large");
+    if (cfg->enabled) {
+        if (cfg->nchannels != 1 && cfg->nchannels != 3)
+            return set_error(CY_ERR_INVALID, "nchannels must be 1 or 3 (the model takes 3-channel images)");
+        if (cfg->chan3_preproc && cfg->nchannels != 3)
+            return set_error(CY_ERR_INVALID, "chan3_preproc requires nchannels == 3 (scripts/run.py:253-256)");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PPParams p;
+    p.cfg = *cfg;
+    p.img = (const uint32_t*)img;
+    p.row_stride = row_stride;
+    p.big_endian = big_endian;
+    p.x0 = tile_x0;
+    p.y0 = tile_y0;
+    p.B = B; p.Ty = Ty; p.Tx = Tx;
+    const size_t N = (size_t)Ty * Tx;
+    const size_t buf = align256((size_t)B * N * 4);
+    char* s = (char*)scratch;
+    p.tilebuf = (float*)s; s += buf;
+    p.keysA = (uint32_t*)s; s += buf;
+    p.keysB = (uint32_t*)s; s += buf;
+    const bool box = cfg->enabled && cfg->subtract_bkg && cfg->use_box_mask_in_bkg;
+    p.keysC = nullptr;
+    if (box) {
+        p.keysC = (uint32_t*)s;
+        s += buf;
+    }
+    p.nlive = (int*)s; s += align256((size_t)B * 4);
+    p.nbox = (int*)s;
+    p.chain_out = chain_out;
+    p.status = status;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
+        attr_done = true;
+    }
+    pp_sort_kernel<<<B, kPPThreads, 0, st>>>(p);
+    pp_chain_kernel<<<B, kPPThreads, sizeof(Shared), st>>>(p);
+    CY_CUDA_CHECK(cudaGetLastError());
+    if (model_in) {
+        int Sh, Sw;
+        cy_letterbox lb;
+        int rc = cy_letterbox_shape(Ty, Tx, imgsz, &Sh, &Sw, &lb);
+        if (rc) return rc;
+        ResizeParams r;
+        r.chain = chain_out;
+        r.out = (__nv_bfloat16*)model_in;
+        r.out_f32 = model_in_f32;
+        r.B = B; r.Ty = Ty; r.Tx = Tx; r.Sh = Sh; r.Sw = Sw;
+        const double rr = fmin((double)imgsz / Ty, (double)imgsz / Tx);
+        r.new_w = (int)nearbyint(Tx * rr);
+        r.new_h = (int)nearbyint(Ty * rr);
+        r.top = (int)nearbyint(((imgsz - r.new_h) % 32) / 2.0 - 0.1);
+        r.left = (int)nearbyint(((imgsz - r.new_w) % 32) / 2.0 - 0.1);
+        r.scale_x = 1.0 / ((double)r.new_w / (double)Tx);
+        r.scale_y = 1.0 / ((double)r.new_h / (double)Ty);
+        const long long total = (long long)B * Sh * Sw;
+        pp_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
+        CY_CUDA_CHECK(cudaGetLastError());
+    }
+    return CY_OK;
 }
