@@ -106,9 +106,9 @@ extern "C" int cy_nms_batched(const float* boxes, const float* scores, const int
     return CY_OK;
 }
 extern "C" int cy_merge_tile(const float* dets, const int32_t* ndets, int B, int det_stride, float thr_score,
-                             float thr_soft, float thr_hard, int32_t* keep_idx, int32_t* nkeep, int32_t* status,
-                             uintptr_t stream) {
-    CY_LAUNCH_CHECK(merge_tiles(dets, ndets, B, det_stride, thr_score, thr_soft, thr_hard, keep_idx, nkeep, status,
+                             float thr_soft, float thr_hard, const int32_t* pre_status, int32_t* keep_idx,
+                             int32_t* nkeep, int32_t* status, uintptr_t stream) {
+    CY_LAUNCH_CHECK(merge_tiles(dets, ndets, B, det_stride, thr_score, thr_soft, thr_hard, pre_status, keep_idx, nkeep, status,
                                 (cudaStream_t)stream),
                     "merge_tile");
     return CY_OK;

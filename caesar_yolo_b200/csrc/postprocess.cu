@@ -376,8 +376,9 @@ static constexpr int kMergeWords = kMergeMaxN / 32;  // 10
 // first member in DFS preorder with strictly greatest score (score_best starts at 0).
 __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict__ dets, const int* __restrict__ ndets,
                                                          int det_stride, float thr_score, float thr_soft,
-                                                         float thr_hard, int* __restrict__ keep_idx,
-                                                         int* __restrict__ nkeep, int* __restrict__ status) {
+                                                         float thr_hard, const int* __restrict__ pre_status,
+                                                         int* __restrict__ keep_idx, int* __restrict__ nkeep,
+                                                         int* __restrict__ status) {
     __shared__ float4 s_box[kMergeMaxN];
     __shared__ float s_score[kMergeMaxN];
     __shared__ int s_cls[kMergeMaxN];
@@ -385,6 +386,13 @@ __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict
     __shared__ uint32_t s_adj[kMergeMaxN][kMergeWords];
     __shared__ int s_N, s_bad;
     const int b = blockIdx.x;
+    if (pre_status && pre_status[b] != 0) {  // tile rejected upstream (predict returned -1): no detections
+        if (threadIdx.x == 0) {
+            nkeep[b] = 0;
+            status[b] = pre_status[b];
+        }
+        return;
+    }
     const int n_in = min(ndets[b], kMergeMaxN);
     const float* D = dets + (long long)b * det_stride * 6;
     if (threadIdx.x == 0) {
@@ -551,10 +559,10 @@ int nms_batched(const float* boxes, const float* scores, const int* counts, int 
 }
 
 int merge_tiles(const float* dets, const int* ndets, int B, int det_stride, float thr_score, float thr_soft,
-                float thr_hard, int* keep_idx, int* nkeep, int* status, cudaStream_t st) {
+                float thr_hard, const int* pre_status, int* keep_idx, int* nkeep, int* status, cudaStream_t st) {
     if (det_stride > kMergeMaxN) return -1;
-    merge_tile_kernel<<<B, 128, 0, st>>>(dets, ndets, det_stride, thr_score, thr_soft, thr_hard, keep_idx, nkeep,
-                                         status);
+    merge_tile_kernel<<<B, 128, 0, st>>>(dets, ndets, det_stride, thr_score, thr_soft, thr_hard, pre_status, keep_idx,
+                                         nkeep, status);
     return (int)cudaGetLastError();
 }
 

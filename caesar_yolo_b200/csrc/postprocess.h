@@ -19,6 +19,6 @@ size_t nms_scratch_bytes(int B, int N);
 int nms_batched(const float* boxes, const float* scores, const int* counts, int B, int N, double thr, int max_keep,
                 long long* keep, int* nkeep, void* scratch, cudaStream_t st);
 int merge_tiles(const float* dets, const int* ndets, int B, int det_stride, float thr_score, float thr_soft,
-                float thr_hard, int* keep_idx, int* nkeep, int* status, cudaStream_t st);
+                float thr_hard, const int* pre_status, int* keep_idx, int* nkeep, int* status, cudaStream_t st);
 
 }  // namespace cy

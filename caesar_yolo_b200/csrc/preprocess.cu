@@ -933,26 +933,32 @@ extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long
     pp_sort_kernel<<<B, kPPThreads, 0, st>>>(p);
     pp_chain_kernel<<<B, kPPThreads, sizeof(Shared), st>>>(p);
     CY_CUDA_CHECK(cudaGetLastError());
-    if (model_in) {
-        int Sh, Sw;
-        cy_letterbox lb;
-        int rc = cy_letterbox_shape(Ty, Tx, imgsz, &Sh, &Sw, &lb);
-        if (rc) return rc;
-        ResizeParams r;
-        r.chain = chain_out;
-        r.out = (__nv_bfloat16*)model_in;
-        r.out_f32 = model_in_f32;
-        r.B = B; r.Ty = Ty; r.Tx = Tx; r.Sh = Sh; r.Sw = Sw;
-        const double rr = fmin((double)imgsz / Ty, (double)imgsz / Tx);
-        r.new_w = (int)nearbyint(Tx * rr);
-        r.new_h = (int)nearbyint(Ty * rr);
-        r.top = (int)nearbyint(((imgsz - r.new_h) % 32) / 2.0 - 0.1);
-        r.left = (int)nearbyint(((imgsz - r.new_w) % 32) / 2.0 - 0.1);
-        r.scale_x = 1.0 / ((double)r.new_w / (double)Tx);
-        r.scale_y = 1.0 / ((double)r.new_h / (double)Ty);
-        const long long total = (long long)B * Sh * Sw;
-        pp_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r);
-        CY_CUDA_CHECK(cudaGetLastError());
-    }
+    if (model_in) return cy_letterbox_resize(chain_out, B, Ty, Tx, imgsz, model_in, model_in_f32, stream);
+    return CY_OK;
+}
+
+extern "C" int cy_letterbox_resize(const float* chain, int B, int Ty, int Tx, int imgsz, void* model_in,
+                                   float* model_in_f32, uintptr_t stream) {
+    using namespace cy;
+    if (!chain || !model_in || B <= 0) return set_error(CY_ERR_INVALID, "cy_letterbox_resize: invalid argument");
+    int Sh, Sw;
+    cy_letterbox lb;
+    int rc = cy_letterbox_shape(Ty, Tx, imgsz, &Sh, &Sw, &lb);
+    if (rc) return rc;
+    ResizeParams r;
+    r.chain = chain;
+    r.out = (__nv_bfloat16*)model_in;
+    r.out_f32 = model_in_f32;
+    r.B = B; r.Ty = Ty; r.Tx = Tx; r.Sh = Sh; r.Sw = Sw;
+    const double rr = fmin((double)imgsz / Ty, (double)imgsz / Tx);
+    r.new_w = (int)nearbyint(Tx * rr);
+    r.new_h = (int)nearbyint(Ty * rr);
+    r.top = (int)nearbyint(((imgsz - r.new_h) % 32) / 2.0 - 0.1);
+    r.left = (int)nearbyint(((imgsz - r.new_w) % 32) / 2.0 - 0.1);
+    r.scale_x = 1.0 / ((double)r.new_w / (double)Tx);
+    r.scale_y = 1.0 / ((double)r.new_h / (double)Ty);
+    const long long total = (long long)B * Sh * Sw;
+    pp_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r);
+    CY_CUDA_CHECK(cudaGetLastError());
     return CY_OK;
 }

@@ -1,0 +1,169 @@
+"""Drop-in for caesar_yolo/inference.py: `SFinder(model, config).run()` / `.run_parallel()` with the same config
+dictionary, return codes (0 / -1) and output files, driven by the CUDA engine (pipeline.Engine).
+
+Differences by design (B200-first): tiles are processed in batches on the GPU instead of one `model(...)` call per
+tile; ranks are torch.distributed ranks (one per GPU) that own contiguous bands of tile rows instead of mpi4py
+round-robin workers; the gather is one NCCL all-gather of 32-byte records; the neighbour table and both merges are
+native/CUDA.  Catalog content and order equal the reference run with nproc=1."""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import catalog, ops
+from .fits import FitsImage
+from .pipeline import Engine, make_pp_config, run_image
+from .preprocessing import DataPreprocessor
+
+logger = logging.getLogger(__name__)
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class SFinder(object):
+    """caesar_yolo/inference.py:280-1290."""
+
+    def __init__(self, model, config):
+        self.model = model
+        self.config = config
+        self.class_names = model.names
+        self.sources = {"sources": []}
+        self.results = {}
+        self.outfile_json = config.get('outfile_json', '') if False else ''  # reference ignores the option (App. B#12)
+        self.outfile_ds9 = ''
+        self.write_to_json = config.get('save_catalog', True)
+        self.write_to_ds9 = config.get('save_region', True)
+        self.outdir = config.get('outdir', '.')
+        self.procId, self.nproc = _dist_info()
+        self.timing = {}
+        self.engine = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def _pp_config(self):
+        dp = self.config.get('preprocess_fcn')
+        if dp is None:
+            return make_pp_config(enabled=False)
+        if isinstance(dp, DataPreprocessor):
+            return dp.pp_config
+        raise NotImplementedError("config['preprocess_fcn'] must be a caesar_yolo_b200.preprocessing.DataPreprocessor "
+                                  "(arbitrary Python callables cannot run inside the CUDA tile pipeline)")
+
+    def _device(self):
+        devs = self.config.get('devices') or ['cuda:0']
+        d = str(devs[self.procId % len(devs)] if self.config.get('use_multi_gpu') else devs[0])
+        if d == 'cpu':
+            raise ops.CaesarB200Error("--devices=cpu: the B200 build has no CPU path (use cuda:N)")
+        if 'LOCAL_RANK' in os.environ and self.nproc > 1:
+            return torch.device('cuda:%d' % int(os.environ['LOCAL_RANK']))
+        return torch.device(d if ':' in d else 'cuda:%s' % d)
+
+    def _engine(self):
+        if self.engine is None:
+            weights = self.model.weights if hasattr(self.model, 'weights') else self.model
+            dev = self._device()
+            torch.cuda.set_device(dev)
+            dm = self.model.device_model() if hasattr(self.model, 'device_model') else weights
+            self.engine = Engine(dm, self._pp_config(), imgsz=self.config['img_size'],
+                                 score_thr=self.config['score_thr'], iou_thr=self.config['iou_thr'],
+                                 thr_soft=self.config['merge_overlap_iou_thr_soft'],
+                                 thr_hard=self.config['merge_overlap_iou_thr_hard'], device=dev,
+                                 batch_tiles=self.config.get('batch_tiles', 32))
+        return self.engine
+
+    def set_img_size_params(self):
+        """inference.py:354-477 (pixel geometry only; WCS/beam metadata are not used by the catalog)."""
+        try:
+            self.fits = FitsImage(self.config['image_path'])
+        except Exception as e:
+            logger.error("Failed to read image header (err=%s)", e)
+            return -1
+        c = self.config
+        xmin, xmax, ymin, ymax = c['image_xmin'], c['image_xmax'], c['image_ymin'], c['image_ymax']
+        if xmin >= 0 and xmax >= 0 and ymin >= 0 and ymax >= 0 and not (xmin == xmax == ymin == ymax == 0):
+            self.xmin, self.xmax, self.ymin, self.ymax = xmin, xmax, ymin, ymax
+            self.nx, self.ny = xmax - xmin + 1, ymax - ymin + 1
+        else:
+            self.nx, self.ny = self.fits.nx, self.fits.ny
+            self.xmin, self.xmax, self.ymin, self.ymax = 0, self.nx - 1, 0, self.ny - 1
+        self.image_id = os.path.splitext(os.path.basename(os.path.abspath(c['image_path'])))[0]
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------
+    def run(self):
+        """Single image (inference.py:485-552): the whole (sub-)image is one tile; outputs come from the Analyzer
+        (out_<id>.json / out_<id>.reg, evaluation.py:216-234)."""
+        if self.set_img_size_params() < 0:
+            return -1
+        c = self.config
+        full = all(v in (0, -1) for v in (c['image_xmin'], c['image_xmax'], c['image_ymin'], c['image_ymax']))
+        if full:
+            x0, x1, y0, y1 = 0, self.fits.nx, 0, self.fits.ny
+        else:  # read_fits_crop: max EXCLUSIVE (utils.py:382)
+            x0, x1, y0, y1 = c['image_xmin'], c['image_xmax'], c['image_ymin'], c['image_ymax']
+            if min(x0, x1, y0, y1) < 0 or x1 <= x0 or y1 <= y0:
+                return -1
+        eng = self._engine()
+        tiles = np.zeros(1, dtype=ops.TILE_DTYPE)
+        tiles[0] = (x0, x1, y0, y1)
+        img = self.fits.rows(y0, y1)
+        t0 = time.time()
+        eng.begin(tiles)
+        dev_img = torch.from_numpy(np.ascontiguousarray(img).view(np.int32)).to(eng.device)
+        eng.process_tiles(dev_img, self.fits.nx, self.fits.is_raw_f32, 0, y0, [0])
+        packed, n = eng.finish()
+        recs = packed.cpu().numpy().view(ops.REC_DTYPE)
+        status = 0
+        # predict() adds no offsets in the serial path (image_xmin/ymin default 0, inference.py:530)
+        recs = recs.copy()
+        recs['x1'] -= x0; recs['x2'] -= x0; recs['y1'] -= y0; recs['y2'] -= y0
+        self.timing['run_s'] = time.time() - t0
+        self.results = {"image_id": self.image_id, "objs": catalog.records_to_objs(recs, self.class_names)}
+        if self.write_to_json:
+            catalog.write_json(self.results, os.path.join(self.outdir, 'out_' + str(self.image_id) + '.json'))
+        if self.write_to_ds9:
+            catalog.write_ds9(self.results['objs'], os.path.join(self.outdir, 'out_' + str(self.image_id) + '.reg'),
+                              merged_key=False)
+        return status
+
+    def run_parallel(self):
+        """Tiled path (inference.py:578-658)."""
+        t0 = time.time()
+        if self.set_img_size_params() < 0:
+            return -1
+        c = self.config
+        tiles = ops.generate_tiles(self.xmin, self.xmax, self.ymin, self.ymax, c['tile_xsize'], c['tile_ysize'],
+                                   c['tile_xstep'], c['tile_ystep'])
+        if tiles is None:
+            logger.error("Failed to generate tile grid")
+            return -1
+        T = len(tiles)
+        ntasks_max = -(-T // self.nproc)
+        if ntasks_max > c['max_ntasks_per_worker']:  # inference.py:1150-1160
+            logger.error("Too many tasks per worker (%d > %d), increase --max_ntasks_per_worker or the GPU count",
+                         ntasks_max, c['max_ntasks_per_worker'])
+            return -1
+        eng = self._engine()
+        img = self.fits.raw if self.fits.is_raw_f32 else self.fits.rows(0, self.fits.ny)
+        src, n = run_image(eng, img, self.fits.is_raw_f32, tiles, rank=self.procId, world=self.nproc)
+        self.timing['run_s'] = time.time() - t0
+        if self.procId == 0:
+            self.sources = {"sources": catalog.sources_to_dicts(src, self.class_names)}
+            self.save()
+            logger.info("Run completed in %d seconds", int(time.time() - t0))
+        return 0
+
+    def save(self):
+        """inference.py:1167-1194."""
+        if self.procId != 0:
+            return
+        if self.write_to_json:
+            catalog.write_json(self.sources, os.path.join(self.outdir, 'catalog_' + str(self.image_id) + '.json'))
+        if self.write_to_ds9:
+            catalog.write_ds9(self.sources['sources'], os.path.join(self.outdir, 'ds9_' + str(self.image_id) + '.reg'))

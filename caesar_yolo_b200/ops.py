@@ -84,6 +84,17 @@ def preprocess(cfg, img, row_stride, big_endian, tile_x0, tile_y0, Ty, Tx, imgsz
     return chain_out, model_in, f32, status
 
 
+def letterbox_resize(chain, imgsz, want_f32=False):
+    """chain: [B,Ty,Tx,3] f32 device -> model_in [B,Sh,Sw,4] bf16 (+ optional f32 NCHW)."""
+    B, Ty, Tx, _ = chain.shape
+    Sh, Sw, _ = letterbox_shape(Ty, Tx, imgsz)
+    model_in = torch.empty((B, Sh, Sw, 4), dtype=torch.bfloat16, device=chain.device)
+    f32 = torch.empty((B, 3, Sh, Sw), dtype=torch.float32, device=chain.device) if want_f32 else None
+    check(lib.cy_letterbox_resize(ptr(chain), c_int(B), c_int(Ty), c_int(Tx), c_int(imgsz), ptr(model_in), ptr(f32),
+                                  cur_stream()))
+    return model_in, f32
+
+
 # ------------------------------------------------------------------------------------------------ conv primitive
 
 def conv_block_n(cout):
@@ -228,7 +239,7 @@ def nms_batched(boxes, scores, iou_thr, counts=None, max_keep=0):
 
 # ------------------------------------------------------------------------------------------------ merges
 
-def merge_tile(dets, ndets, thr_score, thr_soft, thr_hard, keep_idx=None, nkeep=None, status=None):
+def merge_tile(dets, ndets, thr_score, thr_soft, thr_hard, keep_idx=None, nkeep=None, status=None, pre_status=None):
     B, stride, _ = dets.shape
     dev = dets.device
     if keep_idx is None:
@@ -238,7 +249,7 @@ def merge_tile(dets, ndets, thr_score, thr_soft, thr_hard, keep_idx=None, nkeep=
     if status is None:
         status = torch.zeros((B,), dtype=torch.int32, device=dev)
     check(lib.cy_merge_tile(ptr(dets), ptr(ndets), c_int(B), c_int(stride), c_float(thr_score), c_float(thr_soft),
-                            c_float(thr_hard), ptr(keep_idx), ptr(nkeep), ptr(status), cur_stream()))
+                            c_float(thr_hard), ptr(pre_status), ptr(keep_idx), ptr(nkeep), ptr(status), cur_stream()))
     return keep_idx, nkeep, status
 
 

@@ -34,3 +34,232 @@ def make_pp_config(enabled=True, subtract_bkg=False, sigma_bkg=3.0, use_box_mask
     c.norm_min = float(norm_min)
     c.norm_max = float(norm_max)
     return c
+
+
+# ======================================================================================================= engine
+
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from ._capi import CaesarB200Error, Letterbox
+
+
+class Engine(object):
+    """One GPU's share of the hot path.  Holds the device model and reusable buffers; `process_tiles` runs
+    preprocessing -> forward -> decode/NMS -> per-tile merge -> records for a list of tiles cut out of an image that
+    is already in device memory; `finish` compacts the records; `global_merge` builds the catalog.
+
+    Replaces TileTask.find_sources + Analyzer.predict (caesar_yolo/inference.py:173-275, evaluation.py:128-245) for
+    all tiles of a rank at once (the reference runs them one by one, batch 1)."""
+
+    def __init__(self, weights, pp_cfg, imgsz=640, score_thr=0.7, iou_thr=0.5, thr_soft=0.3, thr_hard=0.8,
+                 device=None, batch_tiles=32):
+        if not torch.cuda.is_available():
+            raise CaesarB200Error("no CUDA device: the B200 path has no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        ops.check(ops.lib.cy_device_check())
+        self.model = weights if isinstance(weights, ops.DeviceModel) else ops.DeviceModel(weights)
+        self.nc = self.model.nc
+        self.names = self.model.names
+        self.pp_cfg = pp_cfg if pp_cfg is not None else make_pp_config(enabled=False)
+        self.imgsz = int(imgsz)
+        self.score_thr, self.iou_thr = float(score_thr), float(iou_thr)
+        self.thr_soft, self.thr_hard = float(thr_soft), float(thr_hard)
+        self.batch_tiles = int(batch_tiles)
+        self._buf = {}
+        self.launches = 0      # kernels launched by this engine (bench.py's gpu_launches)
+        self._fwd_launches = {}
+
+    # ---- buffers -----------------------------------------------------------------------------------------
+    def _get(self, key, shape, dtype):
+        t = self._buf.get(key)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty((n,), dtype=dtype, device=self.device)
+            self._buf[key] = t
+        return t[:n].view(*shape)
+
+    def begin(self, tiles):
+        """tiles: structured array (ops.TILE_DTYPE) of ALL tiles of the mosaic (global ids = row-major index)."""
+        self.tiles = np.ascontiguousarray(tiles)
+        self.T = len(tiles)
+        self.tiles_dev = ops.to_device_bytes(self.tiles, self.device)
+        self.rec_slots = self._get('rec_slots', (self.T * ops.MAX_DET * 32,), torch.uint8)
+        self.nrec = self._get('nrec', (self.T,), torch.int32)
+        self.nrec.zero_()
+        self.launches += 1
+
+    def process_tiles(self, img_dev, row_stride, big_endian, origin_x, origin_y, tile_ids):
+        """img_dev covers mosaic rows/cols starting at (origin_x, origin_y); tile_ids: global ids of the tiles to
+        process (all must lie inside img_dev).  Groups by tile shape (edge tiles are smaller, SURVEY App. B#24)."""
+        tile_ids = np.asarray(tile_ids, dtype=np.int32)
+        if tile_ids.size == 0:
+            return
+        t = self.tiles[tile_ids]
+        w = t['xmax'] - t['xmin']
+        h = t['ymax'] - t['ymin']
+        shapes = sorted(set(zip(h.tolist(), w.tolist())), reverse=True)
+        for (Ty, Tx) in shapes:
+            ids = tile_ids[(h == Ty) & (w == Tx)]
+            for s in range(0, len(ids), self.batch_tiles):
+                self._run_batch(img_dev, row_stride, big_endian, origin_x, origin_y, ids[s:s + self.batch_tiles], Ty, Tx)
+
+    def _run_batch(self, img_dev, row_stride, big_endian, ox, oy, ids, Ty, Tx):
+        B = len(ids)
+        dev = self.device
+        tl = self.tiles[ids]
+        meta = np.concatenate([(tl['xmin'] - ox).astype(np.int32), (tl['ymin'] - oy).astype(np.int32),
+                               ids.astype(np.int32)])
+        meta_dev = torch.from_numpy(meta).to(dev, non_blocking=True)
+        x0, y0, ids_dev = meta_dev[:B], meta_dev[B:2 * B], meta_dev[2 * B:]
+        Sh, Sw, lb = ops.letterbox_shape(Ty, Tx, self.imgsz)
+        key = (B, Ty, Tx)
+        lbd = self._buf.get(('lb',) + key)
+        if lbd is None:
+            lbd = ops.letterbox_array([lb] * B, dev)
+            self._buf[('lb',) + key] = lbd
+        chain = self._get('chain', (B, Ty, Tx, 3), torch.float32)
+        model_in = self._get('model_in', (B, Sh, Sw, 4), torch.bfloat16)
+        status = self._get('pp_status', (B,), torch.int32)
+        need = int(ops.lib.cy_preprocess_scratch_bytes(ops.ctypes.byref(self.pp_cfg), B, Ty, Tx))
+        scratch = self._get('pp_scratch', (need,), torch.uint8)
+        ops.preprocess(self.pp_cfg, img_dev, row_stride, big_endian, x0, y0, Ty, Tx, self.imgsz, scratch=scratch,
+                       chain_out=chain, model_in=model_in, status=status)
+        heads = self.model.forward(model_in)
+        need = int(ops.lib.cy_postprocess_scratch_bytes(B, Sh, Sw, ops.MAX_DET))
+        pscr = self._get('post_scratch', (need,), torch.uint8)
+        dets = self._get('dets', (B, ops.MAX_DET, 6), torch.float32)
+        ndets = self._get('ndets', (B,), torch.int32)
+        ops.postprocess(heads, B, Sh, Sw, self.nc, self.score_thr, self.iou_thr, lbd, dev, scratch=pscr, dets=dets,
+                        ndets=ndets)
+        keep = self._get('keep', (B, ops.MAX_DET), torch.int32)
+        nkeep = self._get('nkeep', (B,), torch.int32)
+        mstat = self._get('mstat', (B,), torch.int32)
+        ops.merge_tile(dets, ndets, self.score_thr, self.thr_soft, self.thr_hard, keep_idx=keep, nkeep=nkeep,
+                       status=mstat, pre_status=status)
+        ops.make_records(dets, keep, nkeep, mstat, self.tiles_dev, ids_dev, self.rec_slots, self.nrec)
+        fl = self._fwd_launches.get((B, Sh, Sw))
+        if fl is None:
+            fl = int(self.model.info(B, Sh, Sw)['launches'])
+            self._fwd_launches[(B, Sh, Sw)] = fl
+        # sort + chain + resize (3) + forward + memset/score/nms (3) + merge + records (2)
+        self.launches += 3 + fl + 3 + 2
+
+    def finish(self):
+        """Compacts the per-tile record slots -> (packed uint8 tensor of n cy_det_record, n) in tile-id order."""
+        total = self._get('total', (1,), torch.int32)
+        packed = self._get('packed', (self.T * ops.MAX_DET * 32,), torch.uint8)
+        ops.compact_records(self.rec_slots, self.nrec, self.T, ops.MAX_DET, packed, total)
+        self.launches += 4
+        n = int(total.item())
+        return packed[:n * 32], n
+
+    def global_merge(self, packed, n, nb_off=None, nb_idx=None):
+        """find_sources_at_edge + merge_edge_sources -> numpy structured array (ops.SRC_DTYPE)."""
+        if nb_off is None:
+            nb_off, nb_idx = ops.tile_neighbors(self.tiles)
+        key = ('nb', self.T, int(nb_off[-1]))
+        if key not in self._buf:
+            self._buf[key] = (torch.from_numpy(nb_off).to(self.device),
+                              torch.from_numpy(nb_idx if len(nb_idx) else np.zeros(1, np.int32)).to(self.device))
+        off_dev, idx_dev = self._buf[key]
+        out = self._get('sources', (max(n, 1) * 32,), torch.uint8)
+        self.launches += 30
+        return ops.merge_global(packed, n, self.tiles_dev, self.T, off_dev, idx_dev, out=out)
+
+
+def split_tile_rows(tiles, nparts):
+    """Partition of the row-major tile grid into `nparts` contiguous bands of whole tile rows, balanced by tile count.
+    Returns list of (first_tile_id, last_tile_id_exclusive).  (Replaces the reference's round-robin tile->rank map,
+    inference.py:1008-1029; the gathered list stays in tile-id order for any rank count.)"""
+    T = len(tiles)
+    ymins = tiles['ymin']
+    row_starts = [0] + [i for i in range(1, T) if ymins[i] != ymins[i - 1]] + [T]
+    nrows = len(row_starts) - 1
+    parts = []
+    for r in range(nparts):
+        a = row_starts[(nrows * r) // nparts]
+        b = row_starts[(nrows * (r + 1)) // nparts]
+        parts.append((a, b))
+    return parts
+
+
+def allgather_records(packed, n, world_size):
+    """Exchange step of the path (replaces SFinder.gather_task_data_from_workers, inference.py:936-984): all-gather of
+    the fixed 32-byte detection records over NCCL (counts first, then records padded to the max count)."""
+    import torch.distributed as dist
+    if world_size == 1:
+        return packed, n
+    dev = packed.device
+    cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(world_size)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    send = torch.zeros((mx * 32,), dtype=torch.uint8, device=dev)
+    send[:n * 32] = packed[:n * 32]
+    recv = torch.empty((world_size * mx * 32,), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    parts = [recv[r * mx * 32: r * mx * 32 + counts[r] * 32] for r in range(world_size)]
+    return torch.cat(parts), sum(counts)
+
+
+def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, max_chunk_bytes=1 << 29, on_rank0_only=True):
+    """FITS payload in HOST memory -> catalog.  img_host: 2-D array [ny,nx] of 4-byte pixels (numpy array / memmap, or
+    a pinned torch tensor for zero-copy staging); big_endian: raw FITS byte order.  Tiles of this rank (contiguous
+    band of tile rows) are uploaded in row chunks on a copy stream and processed as they arrive.
+    Returns (sources structured array or None on ranks != 0, n_records_total)."""
+    engine.begin(tiles)
+    a, b = split_tile_rows(tiles, world)[rank]
+    ids = np.arange(a, b, dtype=np.int32)
+    is_torch = isinstance(img_host, torch.Tensor)
+    ny, nx = (img_host.shape[0], img_host.shape[1])
+    if len(ids):
+        ymin = tiles['ymin'][ids]
+        row_keys = np.unique(ymin)
+        copy_stream = engine._buf.get('copy_stream')
+        if copy_stream is None:
+            copy_stream = torch.cuda.Stream(device=engine.device)
+            engine._buf['copy_stream'] = copy_stream
+        compute = torch.cuda.current_stream()
+        # chunks of whole tile rows
+        chunks, cur = [], []
+        for rk in row_keys:
+            cur.append(rk)
+            sel = ids[np.isin(ymin, cur)]
+            y0c, y1c = int(tiles['ymin'][sel].min()), int(tiles['ymax'][sel].max())
+            if (y1c - y0c) * nx * 4 >= max_chunk_bytes:
+                chunks.append(cur)
+                cur = []
+        if cur:
+            chunks.append(cur)
+        slabs = []
+        for ci, ch in enumerate(chunks):
+            sel = ids[np.isin(ymin, ch)]
+            y0c, y1c = int(tiles['ymin'][sel].min()), int(tiles['ymax'][sel].max())
+            slab_dev = torch.empty(((y1c - y0c), nx), dtype=torch.int32, device=engine.device)
+            with torch.cuda.stream(copy_stream):
+                if is_torch:
+                    src = img_host[y0c:y1c]
+                else:
+                    stage = torch.empty(((y1c - y0c), nx), dtype=torch.int32, pin_memory=True)
+                    np.copyto(stage.numpy().view(np.uint8).reshape(y1c - y0c, nx * 4),
+                              np.ascontiguousarray(img_host[y0c:y1c]).view(np.uint8).reshape(y1c - y0c, nx * 4))
+                    src = stage
+                slab_dev.copy_(src.view(torch.int32) if src.dtype != torch.int32 else src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            compute.wait_event(ev)
+            slab_dev.record_stream(compute)
+            engine.process_tiles(slab_dev, nx, big_endian, 0, y0c, sel)
+            slabs.append(slab_dev)
+    packed, n = engine.finish()
+    if world > 1:
+        packed, n = allgather_records(packed, n, world)
+    if rank == 0 or not on_rank0_only:
+        return engine.global_merge(packed, n), n
+    return None, n

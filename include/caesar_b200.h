@@ -86,6 +86,11 @@ size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg_host, int B, int Ty, 
 int cy_preprocess(const cy_pp_config* cfg_host, const void* img, long long row_stride, int big_endian,
                   const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz, float* chain_out,
                   void* model_in, float* model_in_f32, int32_t* status, void* scratch, uintptr_t stream);
+/* The predictor-preprocess part alone (LetterBox bilinear resize + pad 114 + channel reversal + /255, App. A.4) for
+ * an already preprocessed HWC image: chain [B,Ty,Tx,3] fp32 -> model_in / model_in_f32 as above.  This is what the
+ * `model(image, imgsz=...)` call of the reference does before the forward (caesar_yolo/evaluation.py:181-193). */
+int cy_letterbox_resize(const float* chain, int B, int Ty, int Tx, int imgsz, void* model_in, float* model_in_f32,
+                        uintptr_t stream);
 
 /* ------------------------------------------------------------------------------------------------ convolution
  * Layer primitive (ultralytics Conv = Conv2d+BN+SiLU fused; reference model call at
@@ -138,9 +143,12 @@ int cy_nms_batched(const float* boxes, const float* scores, const int32_t* count
 /* ------------------------------------------------------------------------------------------------ merges
  * Analyzer.process_detections (caesar_yolo/evaluation.py:252-346) with utils.get_iou (utils.py:54-107) and Graph
  * (graph.py:2-41).  dets [B,det_stride,6]; keep_idx [B,det_stride] indices into the tile's dets in the
- * reference's output order; status[b] = -2 if get_iou would assert (degenerate box). det_stride <= 320. */
+ * reference's output order; status[b] = -2 if get_iou would assert (degenerate box). det_stride <= 320.
+ * pre_status (optional, [B]): tiles with a non-zero entry were rejected upstream (cy_preprocess status; the
+ * reference's predict() returned -1) and yield no detections; their status is passed through. */
 int cy_merge_tile(const float* dets, const int32_t* ndets, int B, int det_stride, float thr_score, float thr_soft,
-                  float thr_hard, int32_t* keep_idx, int32_t* nkeep, int32_t* status, uintptr_t stream);
+                  float thr_hard, const int32_t* pre_status, int32_t* keep_idx, int32_t* nkeep, int32_t* status,
+                  uintptr_t stream);
 /* Analyzer.make_json_results (evaluation.py:418-469): records written at recs[tile_id*det_stride + i], nrec[tile_id]. */
 int cy_make_records(const float* dets, const int32_t* keep_idx, const int32_t* nkeep, const int32_t* status,
                     int det_stride, const cy_tile* tiles, const int32_t* tile_ids, int B, cy_det_record* recs,

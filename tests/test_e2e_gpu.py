@@ -1,0 +1,160 @@
+"""End-to-end: FITS mosaic -> merged catalog through the drop-in SFinder, against the oracle's restatement of the
+reference's run_parallel / run (CPU, fp32 torch).  Catalogs are compared as sets with IoU >= 0.9 matching
+(north_star).  Two oracles are used: the reference's fp32 arithmetic, and the same with weights/activations rounded to
+bf16 (what the tcgen05 path stores) — the second isolates kernel/logic errors from bf16 quantisation."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inference as oinf, preprocessing as opp, yolo as oy
+
+pytestmark = pytest.mark.gpu
+
+PP = dict(subtract_bkg=True, clip_data=True, zscale_stretch=True, chan3_preproc=True, normalize_minmax=True,
+          nchannels=3, norm_max=255.)
+
+
+def iou(a, b):
+    xl, yt = max(a[0], b[0]), max(a[1], b[1])
+    xr, yb = min(a[2], b[2]), min(a[3], b[3])
+    if xr <= xl or yb <= yt:
+        return 0.0
+    inter = (xr - xl) * (yb - yt)
+    return inter / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter)
+
+
+def match_fraction(got, want, thr=0.9):
+    """Fraction of `want` sources that have a distinct partner in `got` with IoU >= thr and the same class, and the
+    symmetric fraction; returns the smaller of the two."""
+    def one_way(A, Bs):
+        used = set()
+        m = 0
+        for a in A:
+            best, bj = 0.0, -1
+            for j, b in enumerate(Bs):
+                if j in used or a['class_id'] != b['class_id']:
+                    continue
+                if abs(a['x1'] - b['x1']) > 64 or abs(a['y1'] - b['y1']) > 64:
+                    continue
+                v = iou((a['x1'], a['y1'], a['x2'], a['y2']), (b['x1'], b['y1'], b['x2'], b['y2']))
+                if v > best:
+                    best, bj = v, j
+            if best >= thr:
+                used.add(bj)
+                m += 1
+        return m / max(len(A), 1)
+    if not want and not got:
+        return 1.0
+    return min(one_way(want, got), one_way(got, want))
+
+
+def _config(path, outdir, dp, split, **kw):
+    cfg = dict(img_size=640, preprocess_fcn=dp, image_path=path, image_xmin=-1, image_xmax=-1, image_ymin=-1,
+               image_ymax=-1, mpi=None, split_image_in_tiles=split, tile_xsize=512, tile_ysize=512, tile_xstep=1.0,
+               tile_ystep=1.0, max_ntasks_per_worker=10000, devices=['cuda:0'], use_multi_gpu=False, iou_thr=0.5,
+               merge_overlap_iou_thr_soft=0.3, merge_overlap_iou_thr_hard=0.8, score_thr=0.5, save_catalog=True,
+               save_region=True, outdir=outdir)
+    cfg.update(kw)
+    return cfg
+
+
+def _run_ours(weights, path, outdir, split, **kw):
+    from caesar_yolo_b200.inference import SFinder
+    from caesar_yolo_b200.model import YOLO
+    from caesar_yolo_b200.preprocessing import (BkgSubtractor, SigmaClipper, ChanResizer, ZScaleTransformer,
+                                                Chan3Trasformer, MinMaxNormalizer, DataPreprocessor)
+    dp = DataPreprocessor([BkgSubtractor(sigma=3), SigmaClipper(sigma_low=10, sigma_up=10), ChanResizer(nchans=3),
+                           ZScaleTransformer(contrasts=[.25, .25, .25]),
+                           Chan3Trasformer(sigma_clip_baseline=0, sigma_clip_low=10, sigma_clip_up=10, zscale_contrast=.25),
+                           MinMaxNormalizer(norm_min=0, norm_max=255.)])
+    sf = SFinder(YOLO(weights), _config(path, outdir, dp, split, **kw))
+    rc = sf.run_parallel() if split else sf.run()
+    assert rc == 0
+    return sf
+
+
+def _run_oracle(weights, path, outdir, split, emulate_bf16, **kw):
+    dp = opp.DataPreprocessor(opp.build_stages(**PP))
+    cfg = _config(path, outdir, dp, split, devices=['cpu'], **kw)
+    sf = oinf.SFinder(oy.OracleModel(weights, emulate_bf16=emulate_bf16), cfg)
+    rc = sf.run_parallel() if split else sf.run()
+    assert rc == 0
+    return sf
+
+
+@pytest.mark.parametrize("step", [1.0, 0.5])
+def test_tiled_mosaic_catalog_matches_oracle(tmp_path, step):
+    from caesar_yolo_b200 import synth, weights as W
+    ny, nx = (1536, 2048) if step == 1.0 else (1024, 1280)
+    mosaic = synth.make_mosaic(ny, nx, seed=31, nan_border_frac=0.0)
+    mosaic[-90:, :] = np.nan          # masked strip (bottom: top-row NaNs make the reference reject the tile)
+    mosaic[:, -40:] = np.nan
+    path = str(tmp_path / "mosaic.fits")
+    synth.write_fits(path, mosaic)
+    w = W.make_random_weights('n', 5, seed=0, cls_bias=-16.0)
+    kw = dict(tile_xstep=step, tile_ystep=step)
+    ours = _run_ours(w, path, str(tmp_path), True, **kw)
+    got = json.load(open(str(tmp_path / "catalog_mosaic.json")))['sources']
+    assert os.path.exists(str(tmp_path / "ds9_mosaic.reg"))
+    os.rename(str(tmp_path / "catalog_mosaic.json"), str(tmp_path / "ours.json"))
+    emu = _run_oracle(w, path, str(tmp_path), True, True, **kw).sources['sources']
+    f32 = _run_oracle(w, path, str(tmp_path), True, False, **kw).sources['sources']
+    assert len(emu) > 50, "threshold too high: the test would be vacuous"
+    m_emu, m_f32 = match_fraction(got, emu), match_fraction(got, f32)
+    m_ref = match_fraction(emu, f32)   # how much of the disagreement is bf16 quantisation itself
+    print("step %.1f: ours %d, oracle(bf16-emulated) %d, oracle(fp32) %d sources; matched@IoU0.9: vs emu %.4f, vs fp32 "
+          "%.4f (emu vs fp32 %.4f)" % (step, len(got), len(emu), len(f32), m_emu, m_f32, m_ref))
+    assert m_emu >= 0.97, m_emu
+    assert m_f32 >= min(0.995, m_ref - 0.03), (m_f32, m_ref)
+    # catalog format
+    keys = {'class_id', 'class_name', 'edge', 'merged', 'name', 'score', 'x1', 'x2', 'y1', 'y2'}
+    assert all(set(s.keys()) == keys for s in got)
+    assert [s['name'] for s in got] == ['S%d' % (i + 1) for i in range(len(got))]
+
+
+def test_single_image_galaxy0001(tmp_path):
+    """BASELINE config 1: galaxy0001 (132x132), no tiling, YOLOv8n random-init, flags of test/run_inference.sh."""
+    from caesar_yolo_b200 import synth, weights as W
+    from caesar_yolo_b200.inference import SFinder
+    from caesar_yolo_b200.model import YOLO
+    from caesar_yolo_b200.preprocessing import ZScaleTransformer, MinMaxNormalizer, DataPreprocessor
+    data = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'galaxy0001.npy'))
+    path = str(tmp_path / "galaxy0001.fits")
+    synth.write_fits(path, data)
+    w = W.make_random_weights('n', 5, seed=0, cls_bias=-16.0)
+    dp = DataPreprocessor([ZScaleTransformer(contrasts=[.25, .25, .25]), MinMaxNormalizer(norm_min=0, norm_max=255.)])
+    cfg = _config(path, str(tmp_path), dp, False, score_thr=0.5)
+    sf = SFinder(YOLO(w), cfg)
+    assert sf.run() == 0
+    got = json.load(open(str(tmp_path / "out_galaxy0001.json")))
+    assert got['image_id'] == 'galaxy0001'
+    odp = opp.DataPreprocessor(opp.build_stages(zscale_stretch=True, normalize_minmax=True, norm_max=255.))
+    osf = oinf.SFinder(oy.OracleModel(w, emulate_bf16=True), _config(path, str(tmp_path), odp, False, devices=['cpu']))
+    assert osf.run() == 0
+    want = osf.analyzer.results['objs']
+    print("galaxy0001: ours %d objs, oracle %d" % (len(got['objs']), len(want)))
+    assert len(want) > 0
+    assert match_fraction(got['objs'], want) >= 0.9
+    keys = {'name', 'x1', 'x2', 'y1', 'y2', 'class_id', 'class_name', 'score', 'edge'}
+    assert all(set(o.keys()) == keys for o in got['objs'])
+
+
+def test_model_call_seam_matches_oracle():
+    """The `model(image, imgsz=, conf=, iou=)` seam of evaluation.py:181-193 on a preprocessed image."""
+    from caesar_yolo_b200 import synth, weights as W
+    from caesar_yolo_b200.model import YOLO
+    w = W.make_random_weights('n', 5, seed=0, cls_bias=-16.0)
+    tile = synth.make_mosaic(512, 512, seed=3, nan_border_frac=0.0).astype(np.float64)
+    img = opp.DataPreprocessor(opp.build_stages(**PP))(np.stack([tile] * 3, -1))
+    res = YOLO(w)(img, save=False, device='cuda:0', imgsz=640, conf=0.5, iou=0.5)
+    got = res[0].boxes
+    want = oy.OracleModel(w, emulate_bf16=True)(img, imgsz=640, conf=0.5, iou=0.5)[0].boxes
+    g = [dict(x1=float(b[0]), y1=float(b[1]), x2=float(b[2]), y2=float(b[3]), class_id=int(c)) for b, c in
+         zip(got.xyxy.cpu().numpy(), got.cls.cpu().numpy())]
+    wl = [dict(x1=float(b[0]), y1=float(b[1]), x2=float(b[2]), y2=float(b[3]), class_id=int(c)) for b, c in
+          zip(want.xyxy.numpy(), want.cls.numpy())]
+    assert len(wl) > 5
+    assert match_fraction(g, wl) >= 0.9

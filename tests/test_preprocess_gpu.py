@@ -48,6 +48,16 @@ def run_oracle(tile, kw):
     return opp.DataPreprocessor(stages)(cube) if stages else cube
 
 
+def oracle_status(want):
+    """Analyzer.predict's checks after the chain (evaluation.py:164-176): None -> -1; rows 0..2 constant -> -1."""
+    if want is None:
+        return -1
+    for i in range(want.shape[-1]):
+        if np.min(want[i]) == np.max(want[i]):
+            return -1
+    return 0
+
+
 def assert_close(got, want, what):
     scale = np.abs(want).max()
     err = np.abs(got.astype(np.float64) - want)
@@ -65,7 +75,7 @@ def synth_tile(seed, T=512, nan_frac=0.0, ny=None, nx=None):
     if nan_frac > 0:
         rng = np.random.default_rng(seed)
         k = int(ny * nan_frac)
-        img[:k, :] = np.nan
+        img[-k:, :] = np.nan   # not the first rows: the reference rejects images whose rows 0..2 are constant
         img[:, :k // 2] = np.nan
         img[rng.integers(0, ny, 50), rng.integers(0, nx, 50)] = np.inf
     return img
@@ -124,8 +134,20 @@ def test_chain_synthetic_512(name, nan_frac):
     chain, _, _, status = run_gpu(tiles, kw)
     for b in range(len(tiles)):
         want = run_oracle(tiles[b], kw)
-        assert status[b] == 0
+        assert status[b] == oracle_status(want) == 0
         assert_close(chain[b], want, '%s tile %d' % (name, b))
+
+
+def test_nan_top_rows_rejected_like_reference():
+    """Reference quirk (evaluation.py:171-176 indexes ROWS 0..2): a tile whose first rows are masked (NaN border of a
+    mosaic) is rejected even though the rest of the tile is fine.  The chain output itself still matches."""
+    kw = FLAGSETS['config2']
+    t = synth_tile(4)
+    t[:40, :] = np.nan
+    chain, _, _, status = run_gpu(t[None], kw)
+    want = run_oracle(t, kw)
+    assert oracle_status(want) == -1 and status[0] == -1
+    assert_close(chain[0], want, 'nan-top tile')
 
 
 def test_chain_big_endian_and_mosaic_offsets():
