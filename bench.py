@@ -261,9 +261,15 @@ def main():
     ms_dev, wall_ms, (src, nrec) = timed(step_resident, args.steps)
     launches = eng.launches - l0
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(2, args.warmup - 1)):
         step_e2e()
     ms_e2e, wall_e2e, (src2, _) = timed(step_e2e, args.steps)
+
+    # one extra resident step with per-stage CUDA events (outside the timed region)
+    eng.stage_events = []
+    step_resident()
+    stage_ms = {k: round(v, 3) for k, v in eng.stage_times_ms().items()}
+    eng.stage_events = None
 
     if rank != 0:
         if world > 1:
@@ -282,7 +288,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": int(args.mosaic) * int(args.mosaic) * 4,
                     "d2h_bytes_per_step": int(len(src2)) * 32 * world, "ms_per_step": e2e_ms,
                     "mpix_per_s": mpix / (e2e_ms * 1e-3)},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "gpu_launches": int(launches), "clocks": clocks, "stage_ms_per_step": stage_ms}
 
     # ---- roofline of the dominant kernel (the tcgen05 implicit-GEMM conv), measured live with CUDA events on the
     # launching stream: per-op events around one batch forward (Model::profile), summed over the conv launches.

@@ -263,30 +263,32 @@ struct Shared {
     int fail;                // tile status
 };
 
-// mean / std (ddof 0, two-pass) / count of the live values f(S[i]), i in [a,b)
-__device__ void range_stats(const Chan& c, const HistEq& he, const float* S, int a, int b, double* red, double& mean,
-                            double& sd, int& cnt) {
-    double s = 0.0, n = 0.0, z = 0.0;
+// Pivoted moment sums of the live values f(S[i]), i in [a,b) U [a2,b2):  n, sum(v-p), sum((v-p)^2)   (fp64)
+__device__ void range_sums(const Chan& c, const HistEq& he, const float* S, int a, int b, int a2, int b2, double p,
+                           double* red, double& s0, double& s1, double& s2) {
+    double n = 0.0, u = 0.0, q = 0.0;
     for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
         const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
         if (v != 0.0) {
-            s += v;
+            const double d = v - p;
             n += 1.0;
-        }
-    }
-    block_sum3(s, n, z, red);
-    cnt = (int)n;
-    mean = n > 0 ? s / n : 0.0;
-    double q = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
-        const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
-        if (v != 0.0) {
-            const double d = v - mean;
+            u += d;
             q += d * d;
         }
     }
-    block_sum3(q, z1, z2, red);
-    sd = n > 0 ? sqrt(q / n) : 0.0;
+    for (int i = a2 + threadIdx.x; i < b2; i += kPPThreads) {
+        const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
+        if (v != 0.0) {
+            const double d = v - p;
+            n += 1.0;
+            u += d;
+            q += d * d;
+        }
+    }
+    block_sum3(n, u, q, red);
+    s0 = n;
+    s1 = u;
+    s2 = q;
 }
 
 __device__ double live_median(const Chan& c, const HistEq& he, const float* S, int a, int cnt) {
@@ -299,27 +301,47 @@ __device__ double live_median(const Chan& c, const HistEq& he, const float* S, i
 
 // astropy SigmaClip (axis=None, median/std, maxiters 5; App. A.1) over the live values of channel c in S[0..n).
 // Outputs the bounds of the last iteration and the (mean, std) of the survivors.  Returns false if the set is empty.
+// One full pass builds the moment sums about a pivot (the initial median, so mean-pivot = O(std): no cancellation);
+// every iteration keeps a contiguous index range of the sorted array, so it only subtracts the sums of the clipped
+// tails: mean = p + S1/n, std = sqrt(S2/n - (S1/n)^2)  (== numpy's two-pass definition up to fp64 rounding).
 __device__ bool sigma_clip(Shared& sh, const Chan& c, const float* S, int n, double sig_lo, double sig_hi, double& lo,
                            double& hi, double& mean, double& sd) {
     int a = 0, b = n;
-    int cnt;
-    range_stats(c, sh.he, S, a, b, sh.red, mean, sd, cnt);
+    int cnt = live_count(c, a, b);
     if (cnt <= 0) return false;
+    const double p = live_median(c, sh.he, S, a, cnt);
+    double s0, s1, s2;
+    range_sums(c, sh.he, S, a, b, 0, 0, p, sh.red, s0, s1, s2);
+    if ((int)s0 != cnt) {  // index-range bookkeeping and evaluation disagree: never expected
+        if (threadIdx.x == 0) sh.fail = -5;
+        cnt = (int)s0;
+        if (cnt <= 0) return false;
+    }
     lo = hi = 0.0;
     for (int it = 0; it < 5; ++it) {
+        const double m1 = s1 / s0;
+        mean = p + m1;
+        sd = sqrt(fmax(s2 / s0 - m1 * m1, 0.0));
         const double med = live_median(c, sh.he, S, a, cnt);
         lo = med - sd * sig_lo;
         hi = med + sd * sig_hi;
         const int na = lower_index<false>(c, c.nops, sh.he, S, a, b, lo);   // first f >= lo
         const int nb = lower_index<true>(c, c.nops, sh.he, S, na, b, hi);   // first f > hi
         const int ncnt = live_count(c, na, nb);
-        const int changed = cnt - ncnt;
+        if (ncnt == cnt) break;
+        if (ncnt <= 0) return false;
+        double t0, t1, t2;
+        range_sums(c, sh.he, S, a, na, nb, b, p, sh.red, t0, t1, t2);      // the clipped tails only
+        s0 -= t0;
+        s1 -= t1;
+        s2 -= t2;
         a = na;
         b = nb;
-        if (changed == 0) break;
-        range_stats(c, sh.he, S, a, b, sh.red, mean, sd, cnt);
-        if (cnt <= 0) return false;
+        cnt = ncnt;
     }
+    const double m1 = s1 / s0;
+    mean = p + m1;
+    sd = sqrt(fmax(s2 / s0 - m1 * m1, 0.0));
     return true;
 }
 

@@ -56,7 +56,7 @@ class Engine(object):
     all tiles of a rank at once (the reference runs them one by one, batch 1)."""
 
     def __init__(self, weights, pp_cfg, imgsz=640, score_thr=0.7, iou_thr=0.5, thr_soft=0.3, thr_hard=0.8,
-                 device=None, batch_tiles=32):
+                 device=None, batch_tiles=32, pp_tiles=296):
         if not torch.cuda.is_available():
             raise CaesarB200Error("no CUDA device: the B200 path has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -70,9 +70,30 @@ class Engine(object):
         self.score_thr, self.iou_thr = float(score_thr), float(iou_thr)
         self.thr_soft, self.thr_hard = float(thr_soft), float(thr_hard)
         self.batch_tiles = int(batch_tiles)
+        self.pp_tiles = max(int(pp_tiles), self.batch_tiles)
         self._buf = {}
         self.launches = 0      # kernels launched by this engine (bench.py's gpu_launches)
+        self.stage_events = None   # set to [] to collect (stage, start_event, end_event) triples (bench breakdown)
         self._fwd_launches = {}
+
+    def _mark(self):
+        if self.stage_events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _stage(self, name, e0):
+        if e0 is not None:
+            self.stage_events.append((name, e0, self._mark()))
+
+    def stage_times_ms(self):
+        """Sum of CUDA-event durations per stage since stage_events was last reset (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.stage_events or []:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
     # ---- buffers -----------------------------------------------------------------------------------------
     def _get(self, key, shape, dtype):
@@ -95,7 +116,9 @@ class Engine(object):
 
     def process_tiles(self, img_dev, row_stride, big_endian, origin_x, origin_y, tile_ids):
         """img_dev covers mosaic rows/cols starting at (origin_x, origin_y); tile_ids: global ids of the tiles to
-        process (all must lie inside img_dev).  Groups by tile shape (edge tiles are smaller, SURVEY App. B#24)."""
+        process (all must lie inside img_dev).  Groups by tile shape (edge tiles are smaller).
+        Preprocessing runs in groups of `pp_tiles` tiles (one CTA per tile: a multiple of the SM count keeps all 148
+        SMs busy); the conv stack and the detect/merge kernels run in batches of `batch_tiles`."""
         tile_ids = np.asarray(tile_ids, dtype=np.int32)
         if tile_ids.size == 0:
             return
@@ -105,49 +128,65 @@ class Engine(object):
         shapes = sorted(set(zip(h.tolist(), w.tolist())), reverse=True)
         for (Ty, Tx) in shapes:
             ids = tile_ids[(h == Ty) & (w == Tx)]
-            for s in range(0, len(ids), self.batch_tiles):
-                self._run_batch(img_dev, row_stride, big_endian, origin_x, origin_y, ids[s:s + self.batch_tiles], Ty, Tx)
+            for s in range(0, len(ids), self.pp_tiles):
+                self._run_group(img_dev, row_stride, big_endian, origin_x, origin_y, ids[s:s + self.pp_tiles], Ty, Tx)
 
-    def _run_batch(self, img_dev, row_stride, big_endian, ox, oy, ids, Ty, Tx):
-        B = len(ids)
+    def _run_group(self, img_dev, row_stride, big_endian, ox, oy, ids, Ty, Tx):
+        G = len(ids)
         dev = self.device
         tl = self.tiles[ids]
         meta = np.concatenate([(tl['xmin'] - ox).astype(np.int32), (tl['ymin'] - oy).astype(np.int32),
                                ids.astype(np.int32)])
         meta_dev = torch.from_numpy(meta).to(dev, non_blocking=True)
-        x0, y0, ids_dev = meta_dev[:B], meta_dev[B:2 * B], meta_dev[2 * B:]
+        x0, y0, ids_dev = meta_dev[:G], meta_dev[G:2 * G], meta_dev[2 * G:]
         Sh, Sw, lb = ops.letterbox_shape(Ty, Tx, self.imgsz)
+        chain = self._get('chain', (G, Ty, Tx, 3), torch.float32)
+        model_in = self._get('model_in', (G, Sh, Sw, 4), torch.bfloat16)
+        status = self._get('pp_status', (G,), torch.int32)
+        need = int(ops.lib.cy_preprocess_scratch_bytes(ops.ctypes.byref(self.pp_cfg), G, Ty, Tx))
+        scratch = self._get('pp_scratch', (need,), torch.uint8)
+        e = self._mark()
+        ops.preprocess(self.pp_cfg, img_dev, row_stride, big_endian, x0, y0, Ty, Tx, self.imgsz, scratch=scratch,
+                       chain_out=chain, model_in=model_in, status=status)
+        self._stage('preprocess', e)
+        self.launches += 3
+        for s in range(0, G, self.batch_tiles):
+            e = min(G, s + self.batch_tiles)
+            self._run_batch(model_in[s:e], status[s:e], ids_dev[s:e], Ty, Tx, Sh, Sw, lb)
+
+    def _run_batch(self, model_in, status, ids_dev, Ty, Tx, Sh, Sw, lb):
+        B = model_in.shape[0]
+        dev = self.device
         key = (B, Ty, Tx)
         lbd = self._buf.get(('lb',) + key)
         if lbd is None:
             lbd = ops.letterbox_array([lb] * B, dev)
             self._buf[('lb',) + key] = lbd
-        chain = self._get('chain', (B, Ty, Tx, 3), torch.float32)
-        model_in = self._get('model_in', (B, Sh, Sw, 4), torch.bfloat16)
-        status = self._get('pp_status', (B,), torch.int32)
-        need = int(ops.lib.cy_preprocess_scratch_bytes(ops.ctypes.byref(self.pp_cfg), B, Ty, Tx))
-        scratch = self._get('pp_scratch', (need,), torch.uint8)
-        ops.preprocess(self.pp_cfg, img_dev, row_stride, big_endian, x0, y0, Ty, Tx, self.imgsz, scratch=scratch,
-                       chain_out=chain, model_in=model_in, status=status)
+        e = self._mark()
         heads = self.model.forward(model_in)
+        self._stage('forward', e)
+        e = self._mark()
         need = int(ops.lib.cy_postprocess_scratch_bytes(B, Sh, Sw, ops.MAX_DET))
         pscr = self._get('post_scratch', (need,), torch.uint8)
         dets = self._get('dets', (B, ops.MAX_DET, 6), torch.float32)
         ndets = self._get('ndets', (B,), torch.int32)
         ops.postprocess(heads, B, Sh, Sw, self.nc, self.score_thr, self.iou_thr, lbd, dev, scratch=pscr, dets=dets,
                         ndets=ndets)
+        self._stage('decode_nms', e)
+        e = self._mark()
         keep = self._get('keep', (B, ops.MAX_DET), torch.int32)
         nkeep = self._get('nkeep', (B,), torch.int32)
         mstat = self._get('mstat', (B,), torch.int32)
         ops.merge_tile(dets, ndets, self.score_thr, self.thr_soft, self.thr_hard, keep_idx=keep, nkeep=nkeep,
                        status=mstat, pre_status=status)
         ops.make_records(dets, keep, nkeep, mstat, self.tiles_dev, ids_dev, self.rec_slots, self.nrec)
+        self._stage('merge_tile_records', e)
         fl = self._fwd_launches.get((B, Sh, Sw))
         if fl is None:
             fl = int(self.model.info(B, Sh, Sw)['launches'])
             self._fwd_launches[(B, Sh, Sw)] = fl
-        # sort + chain + resize (3) + forward + memset/score/nms (3) + merge + records (2)
-        self.launches += 3 + fl + 3 + 2
+        # forward + memset/score/nms (3) + merge + records (2)
+        self.launches += fl + 3 + 2
 
     def finish(self):
         """Compacts the per-tile record slots -> (packed uint8 tensor of n cy_det_record, n) in tile-id order."""
@@ -169,7 +208,10 @@ class Engine(object):
         off_dev, idx_dev = self._buf[key]
         out = self._get('sources', (max(n, 1) * 32,), torch.uint8)
         self.launches += 30
-        return ops.merge_global(packed, n, self.tiles_dev, self.T, off_dev, idx_dev, out=out)
+        e = self._mark()
+        res = ops.merge_global(packed, n, self.tiles_dev, self.T, off_dev, idx_dev, out=out)
+        self._stage('merge_global', e)
+        return res
 
 
 def split_tile_rows(tiles, nparts):
@@ -190,7 +232,10 @@ def split_tile_rows(tiles, nparts):
 
 def allgather_records(packed, n, world_size):
     """Exchange step of the path (replaces SFinder.gather_task_data_from_workers, inference.py:936-984): all-gather of
-    the fixed 32-byte detection records over NCCL (counts first, then records padded to the max count)."""
+    the fixed 32-byte detection records (counts first, then records padded to the max count — NCCL has no
+    all-gather-v).  Ranks own ascending contiguous tile-id ranges, so concatenating in rank order keeps the list in
+    tile-id order, i.e. the reference's nproc=1 order, for any world size.  Works on CUDA tensors over NCCL and on
+    CPU tensors over gloo (tests)."""
     import torch.distributed as dist
     if world_size == 1:
         return packed, n
@@ -202,9 +247,14 @@ def allgather_records(packed, n, world_size):
     mx = max(max(counts), 1)
     send = torch.zeros((mx * 32,), dtype=torch.uint8, device=dev)
     send[:n * 32] = packed[:n * 32]
-    recv = torch.empty((world_size * mx * 32,), dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(recv, send)
-    parts = [recv[r * mx * 32: r * mx * 32 + counts[r] * 32] for r in range(world_size)]
+    if dev.type == 'cuda':
+        recv = torch.empty((world_size * mx * 32,), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        parts = [recv[r * mx * 32: r * mx * 32 + counts[r] * 32] for r in range(world_size)]
+    else:
+        bufs = [torch.empty((mx * 32,), dtype=torch.uint8) for _ in range(world_size)]
+        dist.all_gather(bufs, send)
+        parts = [bufs[r][:counts[r] * 32] for r in range(world_size)]
     return torch.cat(parts), sum(counts)
 
 
