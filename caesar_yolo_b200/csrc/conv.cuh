@@ -9,6 +9,13 @@
 // shifted by the tap offset (out-of-bounds rows/cols are zero-filled by TMA = the conv padding).
 // Stride-2 convs use four parity-shifted tensor maps (even/odd rows x even/odd cols) so that every tap is
 // again a dense box.  bw*bh*bn == 128 == UMMA M.
+//
+// L2->SMEM traffic is what bounds this kernel (about 43 B/clk/SM against 8192 flop/clk/SM of tensor pipe), so a CTA
+// computes up to M = 256 rows (two 128-row halves = two TMEM accumulators sharing every B tile), and 3x3 stride-1
+// convs on maps that tile exactly use MODE 1: one K iteration = (channel chunk, horizontal tap dw) loads ONE input
+// box of 16 x (8*halves + 2) pixels and the three weight tiles of the vertical taps; the vertical taps are the same
+// shared-memory box read at +0/+1/+2 image rows through the UMMA descriptor start address (16 px * row bytes is a
+// multiple of the swizzle atom, so the shift keeps the swizzle phase).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -33,6 +40,9 @@ struct ConvKParams {
     int act;                       // 1 = SiLU
     int out_f32;                   // 1 = write fp32
     int stages;
+    int mode;                      // 0: one K iteration per (tap, chunk); 1: per (chunk, dw) with vertical tap reuse
+    int halves;                    // 128-row accumulators per CTA (1 or 2)
+    int n_mtiles;                  // number of 128-row M tiles (mode 0) / of CTA tiles (mode 1)
     signed char tap_map[9], tap_dh[9], tap_dw[9];
 };
 
@@ -51,6 +61,7 @@ struct ConvDesc {
 struct ConvPlan {
     ConvKParams kp;
     dim3 grid;
+    int threads;
     int block_n;
     size_t smem;
     double flops;
