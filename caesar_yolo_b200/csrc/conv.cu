@@ -8,147 +8,77 @@
 
 namespace cy {
 
-static constexpr int kConvThreads = 192;  // warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2-5 = epilogue
+// warp roles: 0 = A-box TMA producer, 1 = TMEM alloc + MMA issuer, 2 = weight-tile TMA producer, 3..10 = epilogue
+static constexpr int kNumEpiWarps = 8;
+static constexpr int kFirstEpiWarp = 3;
+static constexpr int kConvThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;
 static constexpr int kBlockM = 128;
+static constexpr int kEpiBufBytes = 4096;   // 32 rows x 128 B staging buffer of one epilogue warp
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+struct HalfCoord {
+    int w0, h0, n0;
+};
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t row_bytes = p.kc * 2;
-    const uint32_t a_bytes = kBlockM * row_bytes;
-    const uint32_t b_bytes_raw = BLOCK_N * row_bytes;
-    const uint32_t b_bytes = (b_bytes_raw + 1023u) & ~1023u;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
-    const int stages = p.stages;
-
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + stages;
-    uint64_t* accum_bar = empty_bar + stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-
-    // tile coordinates: blockIdx.x = N tile (fast, shares the A tile through L2), blockIdx.y = M tile
-    const int n_tile = blockIdx.x;
-    int mt = blockIdx.y;
-    const int tw = mt % p.tiles_w;
-    mt /= p.tiles_w;
-    const int th = mt % p.tiles_h;
-    const int tn = mt / p.tiles_h;
-    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmA[0]);
-        tma_prefetch_desc(&p.tmB);
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(accum_bar, 1);
-        fence_mbar_init();
+__device__ __forceinline__ HalfCoord half_coord(const ConvKParams& p, int ht) {
+    HalfCoord c;
+    if (ht >= p.n_half_tiles) {  // padding half of the last unit: fully out of bounds -> zero box, masked stores
+        c.w0 = 0;
+        c.h0 = 0;
+        c.n0 = p.B;
+        return c;
     }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const int tw = ht % p.tiles_w;
+    ht /= p.tiles_w;
+    const int th = ht % p.tiles_h;
+    const int tn = ht / p.tiles_h;
+    c.w0 = tw * p.bw;
+    c.h0 = th * p.bh;
+    c.n0 = tn * p.bn;
+    return c;
+}
 
-    const int k_iters = p.ntaps * p.cchunks;
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+           (layout << 61);
+}
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const CUtensorMap* ma = &p.tmA[p.tap_map[tap]];
-                const int cw = w0 + p.tap_dw[tap];
-                const int ch = h0 + p.tap_dh[tap];
-                for (int ck = 0; ck < p.cchunks; ++ck, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + (size_t)s * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes_raw);
-                    tma_load_4d(sa, ma, &full_bar[s], ck * p.kc, cw, ch, n0);
-                    tma_load_2d(sb, &p.tmB, &full_bar[s], tap * p.cin + ck * p.kc, n_tile * BLOCK_N);
-                }
+// SiLU(y) = y * sigmoid(y) = h + h * tanh(h), h = y / 2: one MUFU op per element (tanh.approx.f32, abs. error <= 2^-11
+// on tanh, i.e. below the bf16 rounding of the stored activation) instead of ex2 + rcp.
+__device__ __forceinline__ float silu_f(float y) {
+    const float h = 0.5f * y;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+// 32 (or 16) accumulator columns of one row -> bias, SiLU, (+ residual read in place), 16-byte chunks into the
+// swizzled staging row.  cc0 = first column inside the store group.
+template <bool F32OUT>
+__device__ __forceinline__ void epi_cols32(const uint32_t (&v)[32], const float4 (&bias4)[8], int act, bool has_res,
+                                           uint8_t* sbuf, uint32_t my_row, uint32_t sw_mask, int cc0, int ncols) {
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+        if (g8 * 8 < ncols) {
+            const float4 ba = bias4[2 * g8], bb = bias4[2 * g8 + 1];
+            float y[8] = {__uint_as_float(v[g8 * 8 + 0]) + ba.x, __uint_as_float(v[g8 * 8 + 1]) + ba.y,
+                          __uint_as_float(v[g8 * 8 + 2]) + ba.z, __uint_as_float(v[g8 * 8 + 3]) + ba.w,
+                          __uint_as_float(v[g8 * 8 + 4]) + bb.x, __uint_as_float(v[g8 * 8 + 5]) + bb.y,
+                          __uint_as_float(v[g8 * 8 + 6]) + bb.z, __uint_as_float(v[g8 * 8 + 7]) + bb.w};
+            if (act == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+            } else if (act == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = __fdividef(y[j], 1.0f + __expf(-y[j]));
             }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
-        const int ksteps = p.kc >> 4;
-        for (int it = 0; it < k_iters; ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (it / stages) & 1;
-            mbar_wait(&full_bar[s], ph);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t da = make_smem_desc(sa, row_bytes);
-                const uint64_t db = make_smem_desc(sa + a_bytes, row_bytes);
-                for (int k = 0; k < ksteps; ++k) {
-                    // advancing 16 bf16 (=32 B) along K inside the swizzle atom = +2 in the 16-byte address field
-                    umma_bf16(tmem_base, da + 2u * k, db + 2u * k, idesc, (it | k) != 0);
-                }
-                umma_commit(&empty_bar[s]);
-                if (it == k_iters - 1) umma_commit(accum_bar);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ---------------- epilogue: TMEM -> registers -> bias + SiLU (+ residual) -> global NHWC
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const int lw = row % p.bw;
-        const int lh = (row / p.bw) % p.bh;
-        const int ln = row / (p.bw * p.bh);
-        const int ow = w0 + lw, oh = h0 + lh, on = n0 + ln;
-        const bool valid = (ow < p.W) && (oh < p.H) && (on < p.B);
-        const long long pix = ((long long)on * p.H + oh) * p.W + ow;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        constexpr int CW = BLOCK_N >= 32 ? 32 : 16;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += CW) {
-            __syncwarp();
-            float x[CW];
-            if constexpr (CW == 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-            } else {
-                uint32_t v[16];
-                tmem_ld_32x16(taddr + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-            }
-            const int col0 = n_tile * BLOCK_N + c0;
-            if (!valid) continue;
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int g = 0; g < CW / 8; ++g) {
-                const int col = col0 + g * 8;
-                if (col + 8 > p.cout_store) break;
-                const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
-                float y[8] = {x[g * 8 + 0] + ba.x, x[g * 8 + 1] + ba.y, x[g * 8 + 2] + ba.z, x[g * 8 + 3] + ba.w,
-                              x[g * 8 + 4] + bb.x, x[g * 8 + 5] + bb.y, x[g * 8 + 6] + bb.z, x[g * 8 + 7] + bb.w};
-                if (p.act) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) y[j] = __fdividef(y[j], 1.0f + __expf(-y[j]));
-                }
-                if (p.res) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + col));
+            const int cc = cc0 + g8 * 8;
+            if (!F32OUT) {
+                uint32_t a = my_row + (uint32_t)(cc >> 3) * 16u;
+                a ^= (a >> 3) & sw_mask;
+                uint4* dst = reinterpret_cast<uint4*>(sbuf + a);
+                if (has_res) {
+                    const uint4 r = *dst;
                     const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -157,28 +87,316 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const __grid_c
                         y[2 * j + 1] += f.y;
                     }
                 }
-                if (p.out_f32) {
-                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cstride +
-                                                          p.out_coff + col);
-                    o[0] = make_float4(y[0], y[1], y[2], y[3]);
-                    o[1] = make_float4(y[4], y[5], y[6], y[7]);
-                } else {
-                    uint4 o;
-                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+                uint4 o;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride +
-                                              p.out_coff + col) = o;
+                for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                *dst = o;
+            } else {
+                uint32_t a0 = my_row + (uint32_t)(cc >> 2) * 16u;
+                uint32_t a1 = a0 + 16u;
+                a0 ^= (a0 >> 3) & sw_mask;
+                a1 ^= (a1 >> 3) & sw_mask;
+                *reinterpret_cast<float4*>(sbuf + a0) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4*>(sbuf + a1) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+        }
+    }
+}
+
+template <int HALVES, int KSTEPS>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t row_bytes = p.kc * 2;
+    const int a_stages = p.a_stages, b_stages = p.b_stages;
+
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + (size_t)a_stages * p.a_stage_bytes;
+    uint8_t* epi_ring = b_ring + (size_t)b_stages * p.b_stage_bytes;   // [kNumEpiWarps][2][kEpiBufBytes]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(epi_ring + (size_t)kNumEpiWarps * 2 * kEpiBufBytes);
+    uint64_t* a_empty = a_full + a_stages;
+    uint64_t* b_full = a_empty + a_stages;
+    uint64_t* b_empty = b_full + b_stages;
+    uint64_t* acc_full = b_empty + b_stages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* res_bar = acc_empty + 2;                       // [kNumEpiWarps][2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kNumEpiWarps);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA[0]);
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmO);
+        for (int s = 0; s < a_stages; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < b_stages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], kNumEpiWarps);
+        }
+        for (int s = 0; s < 2 * kNumEpiWarps; ++s) mbar_init(&res_bar[s], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr int halves = HALVES;
+
+    // The three single-issuer roles below run their loops with the WHOLE warp (all control flow warp-uniform) and
+    // gate only the issuing instructions with elect.sync: the compiler then keeps descriptors / coordinates in uniform
+    // registers and emits back-to-back UTCHMMA / UTMALDG without per-instruction R2UR waterfall loops.
+    if (warp == 0) {
+        // ------------------------------------------------------------ A-box producer
+        int s = 0;
+        uint32_t ph = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int mu = u / p.n_tiles_n;
+            const HalfCoord hc0 = half_coord(p, mu * HALVES);
+            const HalfCoord hc1 = half_coord(p, mu * HALVES + 1);
+            for (int ck = 0; ck < p.cchunks; ++ck) {
+                for (int al = 0; al < p.n_aloads; ++al) {
+                    const ConvALoad L = p.aload[al];
+                    mbar_wait(&a_empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        uint8_t* dst = a_ring + (size_t)s * p.a_stage_bytes;
+                        mbar_arrive_expect_tx(&a_full[s], p.a_box_bytes * HALVES);
+                        tma_load_4d(dst, &p.tmA[L.map], &a_full[s], ck * p.kc, hc0.w0 + L.dw, hc0.h0 + L.dh, hc0.n0);
+                        if (HALVES == 2)
+                            tma_load_4d(dst + p.a_half_stride, &p.tmA[L.map], &a_full[s], ck * p.kc, hc1.w0 + L.dw,
+                                        hc1.h0 + L.dh, hc1.n0);
+                    }
+                    __syncwarp();
+                    if (++s == a_stages) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
             }
         }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------ weight-tile producer
+        int s = 0;
+        uint32_t ph = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int n_tile = u % p.n_tiles_n;
+            for (int ck = 0; ck < p.cchunks; ++ck) {
+                for (int al = 0; al < p.n_aloads; ++al) {
+                    const ConvALoad L = p.aload[al];
+                    for (int t = 0; t < L.ntaps; ++t) {
+                        const int wtap = p.tap[L.tap0 + t].wtap;
+                        mbar_wait(&b_empty[s], ph ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&b_full[s], p.b_tile_bytes);
+                            tma_load_2d(b_ring + (size_t)s * p.b_stage_bytes, &p.tmB, &b_full[s],
+                                        wtap * p.cin + ck * p.kc, n_tile * p.block_n);
+                        }
+                        __syncwarp();
+                        if (++s == b_stages) {
+                            s = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one elected thread)
+        const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n);
+        const uint32_t a_ring_addr = smem_u32(a_ring);
+        const uint32_t b_ring_addr = smem_u32(b_ring);
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0;
+        int i = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+            const int buf = p.acc_bufs == 2 ? (i & 1) : 0;
+            const uint32_t use = p.acc_bufs == 2 ? (uint32_t)(i >> 1) : (uint32_t)i;
+            unsigned long long* dbg =
+                (p.dbg && i < p.dbg_units) ? p.dbg + ((size_t)blockIdx.x * p.dbg_units + i) * 8 : nullptr;
+            long long wait_a = 0, wait_b = 0;
+            if (dbg && lane == 0) dbg[0] = clock64();
+            mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+            tc_fence_after();
+            if (dbg && lane == 0) dbg[1] = clock64();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * HALVES * p.acc_stride);
+            uint32_t accum = 0;
+            for (int ck = 0; ck < p.cchunks; ++ck) {
+                for (int al = 0; al < p.n_aloads; ++al) {
+                    const ConvALoad L = p.aload[al];
+                    if (dbg) wait_a -= clock64();
+                    mbar_wait(&a_full[sa], pha);
+                    if (dbg) wait_a += clock64();
+                    const uint32_t a_addr = a_ring_addr + (uint32_t)sa * p.a_stage_bytes;
+                    for (int t = 0; t < L.ntaps; ++t) {
+                        const uint32_t a_off = p.tap[L.tap0 + t].a_off;
+                        if (dbg) wait_b -= clock64();
+                        mbar_wait(&b_full[sb], phb);
+                        if (dbg) wait_b += clock64();
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t db = make_desc_sbo(b_ring_addr + (uint32_t)sb * p.b_stage_bytes, row_bytes,
+                                                              8u * row_bytes);
+                            const uint64_t da0 = make_desc_sbo(a_addr + a_off, row_bytes, p.sbo_a);
+#pragma unroll
+                            for (int h = 0; h < HALVES; ++h) {
+                                const uint64_t da = da0 + (uint64_t)((h * p.a_half_stride) >> 4);
+                                const uint32_t td = tacc + (uint32_t)(h * p.acc_stride);
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k)
+                                    // advancing 16 bf16 (=32 B) along K inside the swizzle row = +2 in the 16 B field
+                                    umma_bf16(td, da + 2u * k, db + 2u * k, idesc, accum | (uint32_t)k);
+                            }
+                            umma_commit(&b_empty[sb]);
+                        }
+                        __syncwarp();
+                        accum = 1;
+                        if (++sb == b_stages) {
+                            sb = 0;
+                            phb ^= 1;
+                        }
+                    }
+                    if (elect_one()) umma_commit(&a_empty[sa]);
+                    __syncwarp();
+                    if (++sa == a_stages) {
+                        sa = 0;
+                        pha ^= 1;
+                    }
+                }
+            }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
+            if (dbg && lane == 0) {
+                dbg[2] = clock64();
+                dbg[3] = (unsigned long long)wait_b;
+                dbg[4] = (unsigned long long)wait_a;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        // TMEM -> registers -> bias + SiLU -> swizzled staging buffer (+ residual, TMA-loaded into the same buffer,
+        // added in place) -> TMA store of the warp's 32-row sub box.  Every warp owns two 4 KB staging buffers and
+        // issues its own loads/stores: no cross-warp synchronisation, out-of-image rows/channels are clipped by TMA.
+        const int e = warp - kFirstEpiWarp;
+        const int q = warp & 3;      // TMEM lane quarter this warp may access
+        const int part = e >> 2;     // the two warps of a quarter split halves (halves == 2) or column groups
+        uint8_t* stage_base = epi_ring + (size_t)e * 2 * kEpiBufBytes;
+        uint64_t* rbar = res_bar + e * 2;
+        const int r0 = q * 32;
+        const int sub_w = r0 % p.bw, sub_h = (r0 / p.bw) % p.bh, sub_n = r0 / (p.bw * p.bh);
+        const int gw = p.o_gw;
+        const int ngroups = (p.block_n + gw - 1) / gw;
+        int g_begin = 0, g_end = ngroups;
+        if (halves == 1) {
+            const int mid = (ngroups + 1) / 2;
+            if (part == 0) g_end = mid;
+            else g_begin = mid;
+        }
+        const int h = halves == 2 ? part : 0;
+        const uint32_t my_row = (uint32_t)lane * p.o_row_bytes;
+        int bufsel = 0;
+        uint32_t rphase0 = 0, rphase1 = 0;
+        int i = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+            const int buf = p.acc_bufs == 2 ? (i & 1) : 0;
+            const uint32_t use = p.acc_bufs == 2 ? (uint32_t)(i >> 1) : (uint32_t)i;
+            const int n_tile = u % p.n_tiles_n;
+            const int mu = u / p.n_tiles_n;
+            const HalfCoord hc = half_coord(p, mu * halves + h);
+            const bool valid_half = hc.n0 < p.B;
+            const int bw0 = hc.w0 + sub_w, bh0 = hc.h0 + sub_h, bn0 = hc.n0 + sub_n;
+            unsigned long long* dbg = (p.dbg && e == 0 && lane == 0 && i < p.dbg_units)
+                                          ? p.dbg + ((size_t)blockIdx.x * p.dbg_units + i) * 8
+                                          : nullptr;
+            if (dbg) dbg[5] = clock64();
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            if (dbg) dbg[6] = clock64();
+            const uint32_t taddr =
+                tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * halves + h) * p.acc_stride);
+            if (valid_half) {
+#pragma unroll 1
+                for (int g = g_begin; g < g_end; ++g) {
+                    const int c0 = g * gw;
+                    const int col0 = n_tile * p.block_n + c0;
+                    const int b = bufsel;
+                    bufsel ^= 1;
+                    uint8_t* sbuf = stage_base + (size_t)b * kEpiBufBytes;
+                    const uint32_t sbuf_a = smem_u32(sbuf);
+                    if (lane == 0) bulk_wait_read<1>();  // the store that used this buffer two groups ago has read it
+                    __syncwarp();
+                    if (p.res != nullptr && lane == 0) {
+                        mbar_arrive_expect_tx(&rbar[b], 32u * p.o_row_bytes);
+                        tma_load_4d(sbuf, &p.tmR, &rbar[b], col0, bw0, bh0, bn0);
+                    }
+                    const bool has_res = p.res != nullptr;
+                    bool res_ready = !has_res;
+#pragma unroll 1
+                    for (int cs = 0; cs < gw; cs += 32) {
+                        const int ncols = gw - cs >= 32 ? 32 : 16;
+                        // bias for these columns first: the loads overlap the TMEM read
+                        float4 bias4[8];
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + cs);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            bias4[j] = (j * 4 < ncols) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        uint32_t v[32];
+                        if (ncols == 32) {
+                            tmem_ld_32x32(taddr + c0 + cs, v);
+                        } else {
+                            uint32_t v16[16];
+                            tmem_ld_32x16(taddr + c0 + cs, v16);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = v16[j];
+#pragma unroll
+                            for (int j = 16; j < 32; ++j) v[j] = 0;
+                        }
+                        tmem_ld_wait();
+                        if (!res_ready) {
+                            mbar_wait(&rbar[b], b ? rphase1 : rphase0);
+                            if (b) rphase1 ^= 1;
+                            else rphase0 ^= 1;
+                            res_ready = true;
+                        }
+                        if (p.o_esz == 2)
+                            epi_cols32<false>(v, bias4, p.act, has_res, sbuf, my_row, p.o_sw_mask, cs, ncols);
+                        else
+                            epi_cols32<true>(v, bias4, p.act, false, sbuf, my_row, p.o_sw_mask, cs, ncols);
+                    }
+                    (void)sbuf_a;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&p.tmO, sbuf, col0, bw0, bh0, bn0);
+                        bulk_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (dbg) dbg[7] = clock64();
+        }
+        if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores that read it
+        __syncwarp();
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -233,27 +451,59 @@ static void choose_box(int B, int H, int W, int* bw, int* bh, int* bn) {
         }
 }
 
-template <int BN>
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+static unsigned long long* g_dbg = nullptr;
+static int g_dbg_units = 0;
+void conv_set_debug(unsigned long long* dev_buf, int units_per_cta) {
+    g_dbg = dev_buf;
+    g_dbg_units = units_per_cta;
+}
+
+template <int HALVES, int KSTEPS>
 static int launch_t(const ConvPlan& pl, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<HALVES, KSTEPS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    conv_igemm_kernel<BN><<<pl.grid, kConvThreads, pl.smem, st>>>(pl.kp);
+    if (g_dbg) {
+        ConvKParams kp = pl.kp;
+        kp.dbg = g_dbg;
+        kp.dbg_units = g_dbg_units;
+        conv_igemm_kernel<HALVES, KSTEPS><<<pl.grid, kConvThreads, pl.smem, st>>>(kp);
+    } else {
+        conv_igemm_kernel<HALVES, KSTEPS><<<pl.grid, kConvThreads, pl.smem, st>>>(pl.kp);
+    }
     return (int)cudaGetLastError();
 }
 
 int conv_launch(const ConvPlan& pl, cudaStream_t st) {
-    switch (pl.block_n) {
-        case 16: return launch_t<16>(pl, st);
-        case 32: return launch_t<32>(pl, st);
-        case 64: return launch_t<64>(pl, st);
-        case 128: return launch_t<128>(pl, st);
-        case 256: return launch_t<256>(pl, st);
+    const int key = pl.kp.halves * 10 + (pl.kp.kc >> 4);
+    switch (key) {
+        case 11: return launch_t<1, 1>(pl, st);
+        case 12: return launch_t<1, 2>(pl, st);
+        case 14: return launch_t<1, 4>(pl, st);
+        case 21: return launch_t<2, 1>(pl, st);
+        case 22: return launch_t<2, 2>(pl, st);
+        case 24: return launch_t<2, 4>(pl, st);
     }
-    return -1;
+    return (int)cudaErrorInvalidValue;
 }
 
 int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) {
@@ -281,11 +531,31 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     kp.B = d.B;
     kp.H = Hout;
     kp.W = Wout;
-    choose_box(d.B, Hout, Wout, &kp.bw, &kp.bh, &kp.bn);
+    const int ntaps = d.ksize * d.ksize;
+
+    // ---- mode: tap reuse for 3x3 stride-1 convs with 128-byte channel chunks on maps that 8 x 16 tiles cover well
+    int mode = 0;
+    if (d.ksize == 3 && d.stride == 1 && kc == 64) {
+        const double util = (double)Wout * Hout / ((double)((Wout + 7) / 8 * 8) * ((Hout + 15) / 16 * 16));
+        if (util >= 0.8) mode = 2;
+    }
+    const int max_mode = env_int("CY_CONV_MODE", 2);
+    if (mode > max_mode) mode = max_mode;
+    kp.mode = mode;
+    int box_w, box_h, box_n;          // TMA box in pixels
+    if (mode == 0) {
+        choose_box(d.B, Hout, Wout, &kp.bw, &kp.bh, &kp.bn);
+        box_w = kp.bw; box_h = kp.bh; box_n = kp.bn;
+        kp.sbo_a = 8u * row_bytes;
+    } else {
+        kp.bw = 8; kp.bh = 16; kp.bn = 1;
+        box_w = mode == 2 ? 10 : 8; box_h = 18; box_n = 1;
+        kp.sbo_a = (uint32_t)box_w * row_bytes;
+    }
     kp.tiles_w = (Wout + kp.bw - 1) / kp.bw;
     kp.tiles_h = (Hout + kp.bh - 1) / kp.bh;
     kp.tiles_n = (d.B + kp.bn - 1) / kp.bn;
-    kp.ntaps = d.ksize * d.ksize;
+    kp.n_half_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
     kp.kc = kc;
     kp.cin = d.cin;
     kp.cchunks = d.cin / kc;
@@ -297,15 +567,92 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     kp.res_cstride = d.res_ctot;
     kp.res_coff = d.res_coff;
     kp.cout_store = (d.cout + 7) / 8 * 8;
-    kp.act = d.act;
+    kp.act = d.act ? (env_int("CY_CONV_SILU_EXACT", 0) ? 2 : 1) : 0;   // 1: tanh.approx form, 2: ex2 + rcp
     kp.out_f32 = d.out_f32;
     if ((d.out_ctot % 8) || (d.out_coff % 8)) FAIL("output channel stride/offset must be multiples of 8");
     if (kp.cout_store + d.out_coff > d.out_ctot) FAIL("output slice exceeds buffer channels");
 
+    // ---- work decomposition: two half tiles per unit when that still fills the machine
+    kp.block_n = bn_;
+    kp.n_tiles_n = d.cout_pad / bn_;
+    int halves = ((kp.n_half_tiles + 1) / 2) * kp.n_tiles_n >= num_sms() ? 2 : 1;
+    const int force_halves = env_int("CY_CONV_HALVES", 0);
+    if (force_halves == 1 || force_halves == 2) halves = force_halves;
+    kp.halves = halves;
+    kp.n_units_m = (kp.n_half_tiles + halves - 1) / halves;
+    kp.n_units = kp.n_units_m * kp.n_tiles_n;
+    kp.acc_stride = bn_ < 32 ? 32 : bn_;
+    kp.acc_bufs = 2 * halves * kp.acc_stride <= 512 ? 2 : 1;
+    int cols = kp.acc_bufs * halves * kp.acc_stride;
+    int pow2 = 32;
+    while (pow2 < cols) pow2 *= 2;
+    if (pow2 > 512) FAIL("accumulators do not fit TMEM");
+    kp.tmem_cols = pow2;
+
+    // ---- A-load / tap lists
+    if (mode == 0) {
+        kp.n_aloads = ntaps;
+        for (int t = 0; t < ntaps; ++t) {
+            kp.aload[t].ntaps = 1;
+            kp.aload[t].tap0 = (signed char)t;
+            kp.tap[t].wtap = t;
+            kp.tap[t].a_off = 0;
+        }
+        if (d.stride == 1) {
+            int t = 0;
+            for (int kh = 0; kh < d.ksize; ++kh)
+                for (int kw = 0; kw < d.ksize; ++kw, ++t) {
+                    kp.aload[t].map = 0;
+                    kp.aload[t].dh = (signed char)(kh - d.ksize / 2);
+                    kp.aload[t].dw = (signed char)(kw - d.ksize / 2);
+                }
+        } else {
+            // input row ih = 2*oh + kh - 1: kh=0 -> odd rows, coord oh-1; kh=1 -> even rows, coord oh; kh=2 -> odd, oh
+            int t = 0;
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw, ++t) {
+                    const int ph = (kh != 1), pw = (kw != 1);
+                    kp.aload[t].map = (signed char)(ph * 2 + pw);
+                    kp.aload[t].dh = (signed char)(kh == 0 ? -1 : 0);
+                    kp.aload[t].dw = (signed char)(kw == 0 ? -1 : 0);
+                }
+        }
+    } else if (mode == 1) {
+        kp.n_aloads = 3;
+        for (int kw = 0; kw < 3; ++kw) {
+            kp.aload[kw].map = 0;
+            kp.aload[kw].dw = (signed char)(kw - 1);
+            kp.aload[kw].dh = -1;
+            kp.aload[kw].ntaps = 3;
+            kp.aload[kw].tap0 = (signed char)(3 * kw);
+            for (int kh = 0; kh < 3; ++kh) {
+                kp.tap[3 * kw + kh].wtap = kh * 3 + kw;
+                kp.tap[3 * kw + kh].a_off = (uint32_t)(kh * box_w * row_bytes);
+            }
+        }
+    } else {
+        kp.n_aloads = 1;
+        kp.aload[0].map = 0;
+        kp.aload[0].dw = -1;
+        kp.aload[0].dh = -1;
+        kp.aload[0].ntaps = 9;
+        kp.aload[0].tap0 = 0;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                kp.tap[kh * 3 + kw].wtap = kh * 3 + kw;
+                kp.tap[kh * 3 + kw].a_off = (uint32_t)((kh * box_w + kw) * row_bytes);
+            }
+    }
+    kp.a_box_bytes = (uint32_t)(box_w * box_h * box_n * row_bytes);
+    kp.a_half_stride = (kp.a_box_bytes + 1023u) & ~1023u;
+    kp.a_stage_bytes = kp.a_half_stride * halves;
+    kp.b_tile_bytes = (uint32_t)(bn_ * row_bytes);
+    kp.b_stage_bytes = (kp.b_tile_bytes + 1023u) & ~1023u;
+
     // ---- A tensor maps
     const CUtensorMapSwizzle sw = swizzle_for(row_bytes);
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kp.bw, (cuuint32_t)kp.bh, (cuuint32_t)kp.bn};
+    const cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
     const char* base = reinterpret_cast<const char*>(d.in) + (size_t)d.in_coff * 2;
     const size_t pixb = (size_t)d.in_ctot * 2;
     if (d.stride == 1) {
@@ -315,13 +662,6 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-        int t = 0;
-        for (int kh = 0; kh < d.ksize; ++kh)
-            for (int kw = 0; kw < d.ksize; ++kw, ++t) {
-                kp.tap_map[t] = 0;
-                kp.tap_dh[t] = (signed char)(kh - d.ksize / 2);
-                kp.tap_dw[t] = (signed char)(kw - d.ksize / 2);
-            }
     } else {
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw) {
@@ -334,20 +674,11 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(A s2) failed: %d", (int)r);
             }
-        // input row ih = 2*oh + kh - 1:  kh=0 -> odd rows, coord oh-1; kh=1 -> even rows, coord oh; kh=2 -> odd, oh
-        int t = 0;
-        for (int kh = 0; kh < 3; ++kh)
-            for (int kw = 0; kw < 3; ++kw, ++t) {
-                const int ph = (kh != 1), pw = (kw != 1);
-                kp.tap_map[t] = (signed char)(ph * 2 + pw);
-                kp.tap_dh[t] = (signed char)(kh == 0 ? -1 : 0);
-                kp.tap_dw[t] = (signed char)(kw == 0 ? -1 : 0);
-            }
     }
     // ---- B tensor map: weights [cout_pad, ntaps*cin], K fastest
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)kp.ntaps * d.cin, (cuuint64_t)d.cout_pad};
-        const cuuint64_t str[1] = {(cuuint64_t)kp.ntaps * d.cin * 2};
+        const cuuint64_t dims[2] = {(cuuint64_t)ntaps * d.cin, (cuuint64_t)d.cout_pad};
+        const cuuint64_t str[1] = {(cuuint64_t)ntaps * d.cin * 2};
         const cuuint32_t bbox[2] = {(cuuint32_t)kc, (cuuint32_t)bn_};
         const cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d.w, dims, str, bbox, es,
@@ -355,21 +686,64 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
-    // ---- pipeline depth from the shared-memory budget: aim for 2 CTAs per SM
-    const size_t a_bytes = (size_t)kBlockM * row_bytes;
-    const size_t b_bytes = ((size_t)bn_ * row_bytes + 1023) & ~(size_t)1023;
-    const size_t stage = a_bytes + b_bytes;
-    const size_t budget = bn_ >= 256 ? 200 * 1024 : 100 * 1024;
-    int stages = (int)(budget / stage);
-    const int k_iters = kp.ntaps * kp.cchunks;
-    if (stages > 8) stages = 8;
-    if (stages > k_iters) stages = k_iters;
-    if (stages < 1) stages = 1;
-    kp.stages = stages;
-    plan->smem = (size_t)stages * stage + (2 * stages + 1) * 8 + 16 + 1024;
+    // ---- output / residual tensor maps: one box = the 32 rows of an epilogue warp x o_gw channels (<= 128 bytes)
+    {
+        const int esz = d.out_f32 ? 4 : 2;
+        int gw = 128 / esz;
+        if (gw > bn_) gw = bn_;
+        kp.o_gw = gw;
+        kp.o_esz = esz;
+        kp.o_row_bytes = (uint32_t)(gw * esz);
+        kp.o_sw_mask = kp.o_row_bytes == 128 ? 0x70u : (kp.o_row_bytes == 64 ? 0x30u : 0x10u);
+        if (d.res && d.out_f32) FAIL("residual with fp32 output unsupported");
+        const int sw_ = kp.bw < 32 ? kp.bw : 32;
+        const int sh_ = kp.bh < 32 / sw_ ? kp.bh : 32 / sw_;
+        const int sn_ = 32 / (sw_ * sh_);
+        const cuuint32_t obox[4] = {(cuuint32_t)gw, (cuuint32_t)sw_, (cuuint32_t)sh_, (cuuint32_t)sn_};
+        const cuuint64_t odims[4] = {(cuuint64_t)kp.cout_store, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)d.B};
+        const size_t opix = (size_t)d.out_ctot * esz;
+        const cuuint64_t ostr[3] = {opix, opix * Wout, opix * Wout * Hout};
+        CUresult r = enc(&kp.tmO, d.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                         (char*)d.out + (size_t)d.out_coff * esz, odims, ostr, obox, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)kp.o_row_bytes),
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+        if (d.res) {
+            if ((d.res_ctot % 8) || (d.res_coff % 8)) FAIL("residual channel stride/offset must be multiples of 8");
+            const size_t rpix = (size_t)d.res_ctot * 2;
+            const cuuint64_t rstr[3] = {rpix, rpix * Wout, rpix * Wout * Hout};
+            r = enc(&kp.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (char*)d.res + (size_t)d.res_coff * 2, odims, rstr,
+                    obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for((int)kp.o_row_bytes),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(res) failed: %d", (int)r);
+        }
+    }
+    // ---- ring depths from the shared-memory budget (one persistent CTA per SM)
+    const size_t epi_bytes = (size_t)kNumEpiWarps * 2 * kEpiBufBytes;
+    const size_t budget = 227 * 1024 - 1024 - 512 - epi_bytes;
+    const int a_loads_per_unit = kp.cchunks * kp.n_aloads;
+    const int b_loads_per_unit = kp.cchunks * ntaps;
+    int a_stages, b_stages;
+    if (mode == 0) {
+        a_stages = (int)(budget / (kp.a_stage_bytes + kp.b_stage_bytes));
+        if (a_stages > 8) a_stages = 8;
+        b_stages = a_stages;
+    } else {
+        a_stages = 2;
+        b_stages = (int)((budget - (size_t)a_stages * kp.a_stage_bytes) / kp.b_stage_bytes);
+        if (b_stages > 12) b_stages = 12;
+    }
+    if (a_stages < 1 || b_stages < 1) FAIL("shared-memory budget too small for one stage");
+    (void)a_loads_per_unit;
+    (void)b_loads_per_unit;
+    kp.a_stages = a_stages;
+    kp.b_stages = b_stages;
+    plan->smem = (size_t)a_stages * kp.a_stage_bytes + (size_t)b_stages * kp.b_stage_bytes + epi_bytes +
+                 (size_t)(2 * a_stages + 2 * b_stages + 4 + 2 * kNumEpiWarps) * 8 + 16 + 1024;
     plan->block_n = bn_;
-    plan->grid = dim3(d.cout_pad / bn_, kp.tiles_w * kp.tiles_h * kp.tiles_n, 1);
-    plan->flops = 2.0 * d.B * Hout * Wout * (double)d.cout * kp.ntaps * d.cin;
+    const int g = kp.n_units < num_sms() ? kp.n_units : num_sms();
+    plan->grid = dim3(g, 1, 1);
+    plan->flops = 2.0 * d.B * Hout * Wout * (double)d.cout * ntaps * d.cin;
     return 0;
 #undef FAIL
 }

@@ -5,17 +5,25 @@
 //
 // GEMM view:  D[M = B*Hout*Wout, N = Cout] = sum over taps (kh,kw) and channel chunks of
 //             A_tap[M, KC] * W_tap[N, KC]^T.
-// A is never materialised: each K-step is one 4-D TMA box [KC channels, bw, bh, bn] of the NHWC input
-// shifted by the tap offset (out-of-bounds rows/cols are zero-filled by TMA = the conv padding).
-// Stride-2 convs use four parity-shifted tensor maps (even/odd rows x even/odd cols) so that every tap is
-// again a dense box.  bw*bh*bn == 128 == UMMA M.
+// A is never materialised: the K loop streams TMA boxes of the NHWC input (out-of-bounds rows/cols are zero-filled
+// by TMA = the conv padding).  Stride-2 convs use four parity-shifted tensor maps (even/odd rows x even/odd cols) so
+// that every tap is again a dense box.
 //
-// L2->SMEM traffic is what bounds this kernel (about 43 B/clk/SM against 8192 flop/clk/SM of tensor pipe), so a CTA
-// computes up to M = 256 rows (two 128-row halves = two TMEM accumulators sharing every B tile), and 3x3 stride-1
-// convs on maps that tile exactly use MODE 1: one K iteration = (channel chunk, horizontal tap dw) loads ONE input
-// box of 16 x (8*halves + 2) pixels and the three weight tiles of the vertical taps; the vertical taps are the same
-// shared-memory box read at +0/+1/+2 image rows through the UMMA descriptor start address (16 px * row bytes is a
-// multiple of the swizzle atom, so the shift keeps the swizzle phase).
+// What bounds this kernel is L2->SMEM traffic (LTS cap ~42 B/clk/SM against ~8192 flop/clk/SM of tensor pipe), so the
+// design is about bytes per flop:
+//  * persistent CTAs (one per SM), a work unit = up to two 128-row "half tiles" (two TMEM accumulators) that share
+//    every weight tile, x one BLOCK_N column tile; accumulators are double-buffered in TMEM so the epilogue of unit i
+//    overlaps the main loop of unit i+1;
+//  * the K loop is a list of "A loads" (one TMA box per half tile) each serving a list of taps; a tap = one weight
+//    tile + the MMAs that read the A box at a byte offset through the UMMA descriptor start address:
+//      MODE 0: one A load per tap (any box shape bw x bh x bn = 128 rows), 1x1 and stride-2 convs, odd map sizes;
+//      MODE 1: 3x3 stride 1: three A loads per channel chunk (one per horizontal tap), box 8 x 18 pixels; the three
+//              vertical taps are the same box read at +0/+1/+2 image rows (8 px * 128 B = one swizzle atom, so the
+//              shift keeps the 128B-swizzle phase);
+//      MODE 2: 3x3 stride 1: ONE A load per channel chunk, box 10 x 18 pixels (halo on all sides); all nine taps read
+//              it at (kh*10 + kw) * 128 B (the swizzle XOR is a function of the absolute shared-memory address, so a
+//              128 B shift is legal; stride between 8-row groups = 10 px * 128 B).
+//  * separate shared-memory rings for A boxes and weight tiles, each with its own TMA producer thread.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,26 +32,53 @@
 
 namespace cy {
 
+struct ConvALoad {
+    signed char map, dw, dh, ntaps, tap0;
+};
+struct ConvTap {
+    int wtap;          // tap index in the weight K layout (K = wtap*cin + c)
+    uint32_t a_off;    // byte offset of the tap's first row inside the A box
+};
+
 struct ConvKParams {
     CUtensorMap tmA[4];
     CUtensorMap tmB;
+    CUtensorMap tmO;               // output (TMA store), box = [o_gw channels, 32-row sub box of the half tile]
+    CUtensorMap tmR;               // residual (TMA load), same box
     const float* bias;             // [n_tiles*BLOCK_N], zero padded
     void* out;                     // bf16 or f32, NHWC with out_cstride channels per pixel
     const __nv_bfloat16* res;      // optional residual (added after activation), NHWC
     long long out_cstride, out_coff;
     long long res_cstride, res_coff;
     int B, H, W;                   // output extent
-    int bw, bh, bn;                // box = M tile decomposition, bw*bh*bn == 128
-    int tiles_w, tiles_h, tiles_n;
-    int ntaps, cchunks, kc, cin;   // K loop: ntaps x cchunks steps of kc channels
+    int bw, bh, bn;                // half tile = bw x bh pixels x bn images, bw*bh*bn == 128 == UMMA M
+    int tiles_w, tiles_h, tiles_n, n_half_tiles;
+    int halves;                    // half tiles per work unit (1 or 2)
+    int n_units_m, n_tiles_n, n_units;
+    int block_n;                   // UMMA N
+    int acc_stride;                // TMEM columns per accumulator
+    int acc_bufs;                  // 1 or 2 accumulator sets
+    int tmem_cols;                 // power of two >= 32
+    int cchunks, kc, cin;          // K loop: cchunks chunks of kc channels
+    int n_aloads;                  // A loads per channel chunk
+    int a_stages, b_stages;
+    uint32_t a_box_bytes;          // bytes one half-tile A load delivers
+    uint32_t a_half_stride;        // distance between the halves inside an A stage (multiple of 1024)
+    uint32_t a_stage_bytes;
+    uint32_t b_tile_bytes, b_stage_bytes;
+    uint32_t sbo_a;                // byte stride between 8-row groups of the A operand
     int cout_store;                // number of valid output columns (multiple of 8)
+    int o_gw;                      // output columns per epilogue group (one TMA store box)
+    uint32_t o_row_bytes;          // o_gw * element size (32 / 64 / 128)
+    uint32_t o_sw_mask;            // byte-address swizzle mask of the staging buffer: a ^= (a >> 3) & mask
+    int o_esz;                     // 2 (bf16) or 4 (fp32)
     int act;                       // 1 = SiLU
     int out_f32;                   // 1 = write fp32
-    int stages;
-    int mode;                      // 0: one K iteration per (tap, chunk); 1: per (chunk, dw) with vertical tap reuse
-    int halves;                    // 128-row accumulators per CTA (1 or 2)
-    int n_mtiles;                  // number of 128-row M tiles (mode 0) / of CTA tiles (mode 1)
-    signed char tap_map[9], tap_dh[9], tap_dw[9];
+    int mode;
+    unsigned long long* dbg;       // optional per-CTA timeline (clock64 stamps), 8 words per unit, see conv_probe
+    int dbg_units;
+    ConvALoad aload[9];
+    ConvTap tap[9];
 };
 
 // Host-side description of one convolution call.
@@ -61,7 +96,6 @@ struct ConvDesc {
 struct ConvPlan {
     ConvKParams kp;
     dim3 grid;
-    int threads;
     int block_n;
     size_t smem;
     double flops;
@@ -70,5 +104,6 @@ struct ConvPlan {
 // returns 0 on success, fills plan (encodes tensor maps).  err gets a message on failure.
 int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen);
 int conv_launch(const ConvPlan& plan, cudaStream_t stream);
+void conv_set_debug(unsigned long long* dev_buf, int units_per_cta);
 
 }  // namespace cy

@@ -17,17 +17,12 @@ int conv_block_n(int cout);
 
 // ------------------------------------------------------------------------------------------ small kernels
 
-// Stem: 3x3 stride-2 pad-1 conv, Cin=3 (input NHWC with 4 channels, 4th ignored), CUDA cores, fp32 accumulate.
-// One thread = one output pixel x all COUT channels (in register chunks of 16).
-template <int CHUNK>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const __nv_bfloat16* __restrict__ in,  // [B,H,W,4]
-                                                        const float* __restrict__ w,           // [27][cout]
-                                                        const float* __restrict__ bias,        // [cout]
-                                                        __nv_bfloat16* __restrict__ out,       // [B,H/2,W/2,cout]
-                                                        int B, int H, int W, int cout) {
-    extern __shared__ float sw[];  // [27*cout + cout]
-    for (int i = threadIdx.x; i < 28 * cout; i += blockDim.x) sw[i] = i < 27 * cout ? w[i] : bias[i - 27 * cout];
-    __syncthreads();
+// Stem (3x3 stride-2 pad-1 conv, Cin=3) runs on the tensor pipe as a 1x1 conv with K = 32 over an im2col tensor:
+// one thread = one output pixel gathers its 3x3x3 patch (input NHWC with 4 channels, 4th ignored) into 32 bf16
+// (k = (kh*3+kw)*3 + c, k >= 27 zero) = 64 contiguous bytes.  HBM-bound: reads 8 B/input pixel, writes 64 B/output pixel.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const __nv_bfloat16* __restrict__ in,  // [B,H,W,4]
+                                                          __nv_bfloat16* __restrict__ col,       // [B,H/2,W/2,32]
+                                                          int B, int H, int W) {
     const int Ho = H / 2, Wo = W / 2;
     const long long npix = (long long)B * Ho * Wo;
     const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,52 +30,33 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __nv_bfloat16* __r
     const int ow = (int)(pix % Wo);
     const int oh = (int)((pix / Wo) % Ho);
     const int b = (int)(pix / ((long long)Wo * Ho));
-    float x[27];
+    unsigned short v[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
         const int ih = 2 * oh + kh - 1;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
             const int iw = 2 * ow + kw - 1;
-            float a = 0.f, c = 0.f, d = 0.f;
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(in + (((long long)b * H + ih) * W + iw) * 4));
-                const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
-                const float2 f0 = __bfloat1622float2(p[0]), f1 = __bfloat1622float2(p[1]);
-                a = f0.x;
-                c = f0.y;
-                d = f1.x;
-            }
-            x[(kh * 3 + kw) * 3 + 0] = a;
-            x[(kh * 3 + kw) * 3 + 1] = c;
-            x[(kh * 3 + kw) * 3 + 2] = d;
+            uint2 q = make_uint2(0u, 0u);
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                q = __ldg(reinterpret_cast<const uint2*>(in + (((long long)b * H + ih) * W + iw) * 4));
+            const int t = (kh * 3 + kw) * 3;
+            v[t + 0] = (unsigned short)(q.x & 0xFFFFu);
+            v[t + 1] = (unsigned short)(q.x >> 16);
+            v[t + 2] = (unsigned short)(q.y & 0xFFFFu);
         }
     }
-    __nv_bfloat16* o = out + pix * cout;
-    for (int c0 = 0; c0 < cout; c0 += CHUNK) {
-        float acc[CHUNK];
+    uint4* o = reinterpret_cast<uint4*>(col + pix * 32);
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j) acc[j] = sw[27 * cout + c0 + j];
-#pragma unroll
-        for (int t = 0; t < 27; ++t) {
-            const float xv = x[t];
-            const float* wr = sw + t * cout + c0;
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < CHUNK; j += 8) {
-            uint4 pk;
-            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float y0 = acc[j + 2 * q], y1 = acc[j + 2 * q + 1];
-                y0 = __fdividef(y0, 1.0f + __expf(-y0));
-                y1 = __fdividef(y1, 1.0f + __expf(-y1));
-                p2[q] = __floats2bfloat162_rn(y0, y1);
-            }
-            *reinterpret_cast<uint4*>(o + c0 + j) = pk;
-        }
+    for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = (uint32_t)v[8 * j + 0] | ((uint32_t)v[8 * j + 1] << 16);
+        w.y = (uint32_t)v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16);
+        w.z = (uint32_t)v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16);
+        w.w = (uint32_t)v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16);
+        o[j] = w;
     }
 }
 
@@ -206,17 +182,20 @@ int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn) {
     }
     ConvW cw;
     cw.cin = cin; cw.cout = cout; cw.k = k;
-    if (cin == 3) {  // stem: fp32 [27][cout] of bf16-rounded folded weights
-        std::vector<float> hw(27 * cout);
+    if (cin == 3) {  // stem: packed bf16 [cout_pad][32], k = (kh*3+kw)*3 + c, zero for k >= 27 (1x1 conv over im2col)
+        const int bn_ = conv_block_n(cout);
+        cw.cout_pad = (cout + bn_ - 1) / bn_ * bn_;
+        std::vector<__nv_bfloat16> hw((size_t)cw.cout_pad * 32, __float2bfloat16(0.f));
         for (int o = 0; o < cout; ++o)
             for (int i = 0; i < 3; ++i)
                 for (int kh = 0; kh < 3; ++kh)
                     for (int kw = 0; kw < 3; ++kw)
-                        hw[((kh * 3 + kw) * 3 + i) * cout + o] =
-                            bf16_round((*w)[((o * 3 + i) * 3 + kh) * 3 + kw] * scale[o]);
-        cw.cout_pad = cout;
-        CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(float)));
-        CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+                        hw[(size_t)o * 32 + (kh * 3 + kw) * 3 + i] =
+                            __float2bfloat16((*w)[((o * 3 + i) * 3 + kh) * 3 + kw] * scale[o]);
+        CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(__nv_bfloat16)));
+        CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        cw.cin = 32;
+        cw.k = 1;
     } else {
         const int bn_ = conv_block_n(cout);
         cw.cout_pad = (cout + bn_ - 1) / bn_ * bn_;
@@ -400,12 +379,17 @@ int Model::get_plan(int B, int Sh, int Sw, Plan** out) {
     Buf x21 = pb.alloc(H32, W32, c5);
     PB(!x0.p || !x1.p || !x2.p || !x3.p || !cat14.p || !x5.p || !cat11.p || !x7.p || !x8.p || !sp.p || !cat20.p ||
        !cat17.p || !x15.p || !x18.p || !x21.p);
-    {   // model.0 stem
+    {   // model.0 stem = im2col gather + 1x1 conv (K = 32) on the tensor pipe
+        Buf col = pb.alloc(H2, W2, 32);
+        PB(!col.p);
         Op op;
-        op.type = Op::STEM; op.name = "model.0";
-        op.out = x0;
+        op.type = Op::IM2COL; op.name = "model.0.im2col";
+        op.out = col;
         pl->ops.push_back(op);
-        pl->flops += 2.0 * B * H2 * W2 * c1 * 27;
+        PB(pb.conv("model.0", col, 0, x0, 0, 1));
+        const double f27 = 2.0 * B * H2 * W2 * c1 * 27;   // count the real 27 taps, not the zero padding
+        pl->flops += f27 - pl->ops.back().conv.flops;
+        pl->ops.back().conv.flops = f27;
     }
     Buf inb; inb.p = nullptr;
     PB(pb.conv("model.1", x0, 0, x1, 0, 2));
@@ -471,16 +455,10 @@ int Model::get_plan(int B, int Sh, int Sw, Plan** out) {
 
 int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaStream_t st) {
     switch (op.type) {
-        case Op::STEM: {
-            const ConvW& w = convs["model.0"];
+        case Op::IM2COL: {
             const long long npix = (long long)B * (Sh / 2) * (Sw / 2);
-            const size_t smem = (size_t)28 * w.cout * sizeof(float);
-            if (w.cout % 16 == 0)
-                stem_conv_kernel<16><<<(unsigned)((npix + 127) / 128), 128, smem, st>>>(
-                    (const __nv_bfloat16*)in, (const float*)w.w, w.b, (__nv_bfloat16*)op.out.p, B, Sh, Sw, w.cout);
-            else
-                stem_conv_kernel<8><<<(unsigned)((npix + 127) / 128), 128, smem, st>>>(
-                    (const __nv_bfloat16*)in, (const float*)w.w, w.b, (__nv_bfloat16*)op.out.p, B, Sh, Sw, w.cout);
+            stem_im2col_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(
+                (const __nv_bfloat16*)in, (__nv_bfloat16*)op.out.p, B, Sh, Sw);
             break;
         }
         case Op::CONV: {
@@ -540,8 +518,7 @@ int Model::profile(const void* in, int B, int Sh, int Sw, int cap, const char** 
         cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
         if (ms) ms[i] = t;
         if (names) names[i] = pl->ops[i].name.c_str();
-        if (flops) flops[i] = pl->ops[i].type == Op::CONV ? pl->ops[i].conv.flops
-                              : (pl->ops[i].type == Op::STEM ? 2.0 * B * (Sh / 2) * (Sw / 2) * c1 * 27 : 0.0);
+        if (flops) flops[i] = pl->ops[i].type == Op::CONV ? pl->ops[i].conv.flops : 0.0;
     }
     for (auto& e : ev) cudaEventDestroy(e);
     if (nops) *nops = n;

@@ -98,6 +98,10 @@ int cy_letterbox_resize(const float* chain, int B, int Ty, int Tx, int imgsz, vo
  * bias fp32[cout_pad]; optional residual added after the activation; output bf16 or fp32 written into a
  * channel slice [out_coff, out_coff+cout) of an NHWC buffer with out_ctot channels. */
 int cy_conv_block_n(int cout);
+/* Diagnostics (tools/conv_probe.py): per-CTA clock64 timeline buffer for the conv kernel (NULL disables); the plan the
+ * kernel would use for a shape: info8 = {mode, halves, units, block_n, a_stages, b_stages, acc_bufs, grid}. */
+int cy_conv_set_debug(void* dev_buf, int units_per_cta);
+int cy_conv_plan_info(int B, int Hin, int Win, int cin, int cout, int ksize, int stride, int* info8);
 int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ctot, int in_coff, int cin, const void* w,
                    const float* bias, int cout, int cout_pad, int ksize, int stride, void* out, int out_ctot,
                    int out_coff, int out_f32, const void* res, int res_ctot, int res_coff, int act,

@@ -56,3 +56,31 @@ def _run_case(B, H, W, cin, cout, k, s, act, res, out_f32, in_extra=0, out_extra
 ])
 def test_conv_matches_torch(case):
     _run_case(**case)
+
+
+# Kernel variants: mode 0 = one A box per tap, 1 = vertical tap reuse, 2 = full 3x3 halo reuse; halves = 128-row
+# accumulators per work unit.  The planner picks these from the shape; the environment overrides exist for this test.
+VARIANT_SHAPES = [
+    dict(B=2, H=16, W=16, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False),
+    dict(B=3, H=40, W=40, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=1, H=80, W=40, cin=256, cout=256, k=3, s=1, act=True, res=False, out_f32=False, in_extra=64, out_extra=128),
+    dict(B=5, H=32, W=8, cin=64, cout=5, k=3, s=1, act=False, res=False, out_f32=True, out_extra=64),
+    dict(B=7, H=20, W=20, cin=192, cout=256, k=1, s=1, act=True, res=False, out_f32=False),
+    dict(B=3, H=40, W=40, cin=64, cout=128, k=3, s=2, act=True, res=False, out_f32=False),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("halves", [1, 2])
+@pytest.mark.parametrize("shape", range(len(VARIANT_SHAPES)))
+def test_conv_variants(monkeypatch, mode, halves, shape):
+    monkeypatch.setenv("CY_CONV_MODE", str(mode))
+    monkeypatch.setenv("CY_CONV_HALVES", str(halves))
+    _run_case(seed=shape + 1, **VARIANT_SHAPES[shape])
+
+
+def test_conv_large_batch_persistent():
+    """More work units than SMs: every CTA loops over several units (ring phases, TMEM double buffering)."""
+    _run_case(B=24, H=80, W=80, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False, seed=11)
+    _run_case(B=32, H=40, W=40, cin=256, cout=512, k=1, s=1, act=True, res=False, out_f32=False, seed=12)
+    _run_case(B=16, H=160, W=160, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False, seed=13)
