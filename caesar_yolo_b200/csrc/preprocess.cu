@@ -43,6 +43,19 @@ struct Chan {
     int z0[kMaxZero], z1[kMaxZero];
 };
 
+// Compiled form of a channel's op list for the full passes: every op except HISTEQ is affine + clamp with a positive
+// slope, so the composition collapses to v = clamp(a*x + b, l, h) (one optional HISTEQ in the middle splits it into
+// A and B).  Differs from the sequential fp64 evaluation only by rounding (~1e-16 relative); exact-zero (= masked)
+// decisions never come from it: they are the index ranges Chan::z0/z1 of the sorted array, i.e. x intervals.
+struct Comp {
+    double a0, b0, l0, h0;
+    double a1, b1, l1, h1;
+    int has_he;
+    int ok;                      // 0: not representable (non-finite / non-positive slope) -> interpreter
+    int nzx;
+    float zx0[8], zx1[8];        // zero intervals [zx0, zx1] of the ORIGINAL pixel value
+};
+
 struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per chain: Chan3 channel 2)
     double edges[257];
     double cdf[256];
@@ -200,6 +213,99 @@ __device__ int lower_index(const Chan& c, int nops, const HistEq& he, const floa
     return lo;
 }
 
+// np.interp on the uniform histogram centres with an O(1) bracket (same interpolation arithmetic as histeq_interp).
+__device__ __forceinline__ double histeq_interp_fast(const HistEq& h, double v) {
+    const double c0 = (h.edges[0] + h.edges[1]) / 2.0, c255 = (h.edges[255] + h.edges[256]) / 2.0;
+    if (!(v > c0)) return h.cdf[0];
+    if (v >= c255) return h.cdf[255];
+    const double step = (c255 - c0) / 255.0;
+    int lo = step > 0.0 ? (int)((v - c0) / step) : 0;
+    lo = max(0, min(254, lo));
+    while (lo > 0 && (h.edges[lo] + h.edges[lo + 1]) / 2.0 > v) --lo;
+    while (lo < 254 && (h.edges[lo + 1] + h.edges[lo + 2]) / 2.0 <= v) ++lo;
+    const double xl = (h.edges[lo] + h.edges[lo + 1]) / 2.0, xr = (h.edges[lo + 1] + h.edges[lo + 2]) / 2.0;
+    const double slope = __ddiv_rn(__dsub_rn(h.cdf[lo + 1], h.cdf[lo]), __dsub_rn(xr, xl));
+    return __dadd_rn(__dmul_rn(slope, __dsub_rn(v, xl)), h.cdf[lo]);
+}
+
+// Value of a NON-masked pixel through the compiled op list (callers decide masking by index / x interval).
+__device__ __forceinline__ double eval_fast(const Comp& cc, const Chan& c, const HistEq& he, double x) {
+    if (!cc.ok) return eval_ops<true>(c, c.nops, he, x);
+    double v = fmin(fmax(fma(cc.a0, x, cc.b0), cc.l0), cc.h0);
+    if (cc.has_he) {
+        v = histeq_interp_fast(he, v);
+        v = fmin(fmax(fma(cc.a1, v, cc.b1), cc.l1), cc.h1);
+    }
+    return v;
+}
+__device__ __forceinline__ bool in_zero_x(const Comp& cc, float x) {
+    bool z = (x == 0.0f);
+    for (int k = 0; k < cc.nzx; ++k) z = z || (x >= cc.zx0[k] && x <= cc.zx1[k]);
+    return z;
+}
+__device__ __forceinline__ bool in_zero_idx(const Chan& c, int i) {
+    bool z = false;
+    for (int k = 0; k < c.nz; ++k) z = z || (i >= c.z0[k] && i < c.z1[k]);
+    return z;
+}
+
+// (thread 0) rebuild the compiled form of channel c after its op list / zero ranges changed
+__device__ void compile_chan(const Chan& c, Comp& cc, const float* S) {
+    double a = 1.0, b = 0.0, l = -INFINITY, h = INFINITY;
+    cc.has_he = 0;
+    cc.ok = 1;
+    for (int k = 0; k < c.nops; ++k) {
+        switch (c.kind[k]) {
+            case OP_SUB:
+                b -= c.p0[k]; l -= c.p0[k]; h -= c.p0[k];
+                break;
+            case OP_SHIFT:
+                b -= c.p0[k];
+                l = fmax(l - c.p0[k], 0.0);
+                h = fmax(h - c.p0[k], l);
+                break;
+            case OP_CLAMP:
+                l = fmin(fmax(l, c.p0[k]), c.p1[k]);
+                h = fmin(fmax(h, c.p0[k]), c.p1[k]);
+                break;
+            case OP_ZSCALE: {
+                const double sc = c.p1[k] != 0.0 ? 1.0 / c.p1[k] : 1.0;
+                if (!(sc > 0.0) || !isfinite(sc)) cc.ok = 0;
+                a *= sc; b = (b - c.p0[k]) * sc; l = (l - c.p0[k]) * sc; h = (h - c.p0[k]) * sc;
+                l = fmin(fmax(l, 0.0), 1.0);
+                h = fmin(fmax(h, 0.0), 1.0);
+                break;
+            }
+            case OP_MINMAX: {
+                const double sc = c.p2[k] / c.p1[k];
+                if (!(sc > 0.0) || !isfinite(sc)) cc.ok = 0;
+                a *= sc; b = (b - c.p0[k]) * sc + c.p3[k]; l = (l - c.p0[k]) * sc + c.p3[k];
+                h = (h - c.p0[k]) * sc + c.p3[k];
+                break;
+            }
+            case OP_HISTEQ:
+                if (cc.has_he) cc.ok = 0;
+                cc.a0 = a; cc.b0 = b; cc.l0 = l; cc.h0 = h;
+                cc.has_he = 1;
+                a = 1.0; b = 0.0; l = -INFINITY; h = INFINITY;
+                break;
+            default: cc.ok = 0;
+        }
+    }
+    if (cc.has_he) {
+        cc.a1 = a; cc.b1 = b; cc.l1 = l; cc.h1 = h;
+    } else {
+        cc.a0 = a; cc.b0 = b; cc.l0 = l; cc.h0 = h;
+        cc.a1 = 1.0; cc.b1 = 0.0; cc.l1 = -INFINITY; cc.h1 = INFINITY;
+    }
+    if (!isfinite(a) || !isfinite(b) || !isfinite(cc.a0) || !isfinite(cc.b0) || isnan(l) || isnan(h)) cc.ok = 0;
+    cc.nzx = c.nz;
+    for (int k = 0; k < c.nz; ++k) {
+        cc.zx0[k] = S[c.z0[k]];
+        cc.zx1[k] = S[c.z1[k] - 1];
+    }
+}
+
 __device__ void add_zero_range(Chan& c, int h0, int h1) {  // single thread
     if (h1 <= h0) return;
     int n = c.nz;
@@ -253,6 +359,7 @@ __device__ int kth_live(const Chan& c, int a, int k) {
 
 struct Shared {
     Chan ch[3];
+    Comp cc[3];
     HistEq he;
     double red[3 * 32 + 4];
     double zs[1024];         // zscale samples / flat residuals
@@ -263,23 +370,22 @@ struct Shared {
     int fail;                // tile status
 };
 
-// Pivoted moment sums of the live values f(S[i]), i in [a,b) U [a2,b2):  n, sum(v-p), sum((v-p)^2)   (fp64)
-__device__ void range_sums(const Chan& c, const HistEq& he, const float* S, int a, int b, int a2, int b2, double p,
-                           double* red, double& s0, double& s1, double& s2) {
+// Pivoted moment sums of the live values f(S[i]), i in [a,b) U [a2,b2):  n, sum(v-p), sum((v-p)^2)   (fp64).
+// Values come from the compiled op list; masked elements are the zero index ranges of the channel.
+__device__ void range_sums(const Chan& c, const Comp& cc, const HistEq& he, const float* S, int a, int b, int a2,
+                           int b2, double p, double* red, double& s0, double& s1, double& s2) {
     double n = 0.0, u = 0.0, q = 0.0;
     for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
-        const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
-        if (v != 0.0) {
-            const double d = v - p;
+        if (!in_zero_idx(c, i)) {
+            const double d = eval_fast(cc, c, he, (double)S[i]) - p;
             n += 1.0;
             u += d;
             q += d * d;
         }
     }
     for (int i = a2 + threadIdx.x; i < b2; i += kPPThreads) {
-        const double v = eval_ops<true>(c, c.nops, he, (double)S[i]);
-        if (v != 0.0) {
-            const double d = v - p;
+        if (!in_zero_idx(c, i)) {
+            const double d = eval_fast(cc, c, he, (double)S[i]) - p;
             n += 1.0;
             u += d;
             q += d * d;
@@ -304,14 +410,14 @@ __device__ double live_median(const Chan& c, const HistEq& he, const float* S, i
 // One full pass builds the moment sums about a pivot (the initial median, so mean-pivot = O(std): no cancellation);
 // every iteration keeps a contiguous index range of the sorted array, so it only subtracts the sums of the clipped
 // tails: mean = p + S1/n, std = sqrt(S2/n - (S1/n)^2)  (== numpy's two-pass definition up to fp64 rounding).
-__device__ bool sigma_clip(Shared& sh, const Chan& c, const float* S, int n, double sig_lo, double sig_hi, double& lo,
-                           double& hi, double& mean, double& sd) {
+__device__ bool sigma_clip(Shared& sh, const Chan& c, const Comp& cc, const float* S, int n, double sig_lo,
+                           double sig_hi, double& lo, double& hi, double& mean, double& sd) {
     int a = 0, b = n;
     int cnt = live_count(c, a, b);
     if (cnt <= 0) return false;
     const double p = live_median(c, sh.he, S, a, cnt);
     double s0, s1, s2;
-    range_sums(c, sh.he, S, a, b, 0, 0, p, sh.red, s0, s1, s2);
+    range_sums(c, cc, sh.he, S, a, b, 0, 0, p, sh.red, s0, s1, s2);
     if ((int)s0 != cnt) {  // index-range bookkeeping and evaluation disagree: never expected
         if (threadIdx.x == 0) sh.fail = -5;
         cnt = (int)s0;
@@ -331,7 +437,7 @@ __device__ bool sigma_clip(Shared& sh, const Chan& c, const float* S, int n, dou
         if (ncnt == cnt) break;
         if (ncnt <= 0) return false;
         double t0, t1, t2;
-        range_sums(c, sh.he, S, a, na, nb, b, p, sh.red, t0, t1, t2);      // the clipped tails only
+        range_sums(c, cc, sh.he, S, a, na, nb, b, p, sh.red, t0, t1, t2);  // the clipped tails only
         s0 -= t0;
         s1 -= t1;
         s2 -= t2;
@@ -367,13 +473,17 @@ __device__ void push_op(Shared& sh, int ci, const float* S, int n, int kind, dou
     if (threadIdx.x == 0) {
         add_zero_range(c, h0, h1);
         c.hid = sh.next_hid++;
+        compile_chan(c, sh.cc[ci], S);
     }
     __syncthreads();
 }
 
 __device__ void copy_chan(Shared& sh, int dst, int src) {
     __syncthreads();
-    if (threadIdx.x == 0) sh.ch[dst] = sh.ch[src];
+    if (threadIdx.x == 0) {
+        sh.ch[dst] = sh.ch[src];
+        sh.cc[dst] = sh.cc[src];
+    }
     __syncthreads();
 }
 
@@ -462,16 +572,22 @@ __device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const
 }
 
 // skimage equalize_hist (App. A.3) on channel c: 256-bin histogram over [min,max] of ALL pixels (masked zeros
-// included), CDF, then OP_HISTEQ.
+// included), CDF, then OP_HISTEQ.  The channel is a monotone map of the sorted array, so min / max are its first / last
+// live element (and 0 if any pixel is masked) and the bin counts are differences of 257 binary searches at the bin
+// edges (numpy assigns v to the bin with edges[k] <= v < edges[k+1], last bin closed) -- no pass over the pixels.
 __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const float* S, int n) {
     const Chan& c = sh.ch[ci];
+    const int nlive = live_count(c, 0, n);
+    const int nzero = N - nlive;
     double mn = INFINITY, mx = -INFINITY;
-    for (int i = threadIdx.x; i < N; i += kPPThreads) {
-        const double v = eval_ops<true>(c, c.nops, sh.he, (double)tile[i]);
-        mn = fmin(mn, v);
-        mx = fmax(mx, v);
+    if (nlive > 0) {
+        mn = eval_ops<true>(c, c.nops, sh.he, (double)S[kth_live(c, 0, 0)]);
+        mx = eval_ops<true>(c, c.nops, sh.he, (double)S[kth_live(c, 0, nlive - 1)]);
     }
-    block_minmax(mn, mx, sh.red);
+    if (nzero > 0) {
+        mn = fmin(mn, 0.0);
+        mx = fmax(mx, 0.0);
+    }
     double first = mn, last = mx;
     if (first == last) {  // numpy _get_outer_edges
         first -= 0.5;
@@ -482,29 +598,32 @@ __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const
     const double step = (last - first) / 256.0;
     for (int i = threadIdx.x; i < 257; i += kPPThreads)
         sh.he.edges[i] = i == 256 ? last : __dadd_rn(__dmul_rn((double)i, step), first);
-    for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.hist[i] = 0;
     __syncthreads();
-    const double denom = last - first;
-    for (int i = threadIdx.x; i < N; i += kPPThreads) {
-        const double v = eval_ops<true>(c, c.nops, sh.he, (double)tile[i]);
-        // numpy histogram fast path for uniform bins
-        int idx = (int)(__dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), 256.0));
-        if (idx == 256) idx = 255;
-        if (idx < 0) idx = 0;
-        if (idx > 255) idx = 255;
-        if (v < sh.he.edges[idx]) --idx;
-        else if (idx != 255 && v >= sh.he.edges[idx + 1]) ++idx;
-        if (idx < 0) idx = 0;
-        atomicAdd(&sh.hist[idx], 1);
-    }
+    // cum[k] = number of live elements with value < edges[k]  (k = 256: all of them, the last bin is closed)
+    int* cum = reinterpret_cast<int*>(sh.zs);
+    for (int k = threadIdx.x; k < 257; k += kPPThreads)
+        cum[k] = k == 256 ? nlive : live_count(c, 0, lower_index<false>(c, c.nops, sh.he, S, 0, n, sh.he.edges[k]));
+    __syncthreads();
+    for (int k = threadIdx.x; k < 256; k += kPPThreads) sh.hist[k] = cum[k + 1] - cum[k];
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long cum = 0;
-        for (int i = 0; i < 256; ++i) {
-            cum += sh.hist[i];
-            sh.he.cdf[i] = (double)cum;
+        if (nzero > 0) {  // the masked pixels (value 0): numpy histogram fast path for uniform bins
+            const double v = 0.0, denom = last - first;
+            int idx = (int)(__dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), 256.0));
+            if (idx == 256) idx = 255;
+            if (idx < 0) idx = 0;
+            if (idx > 255) idx = 255;
+            if (v < sh.he.edges[idx]) --idx;
+            else if (idx != 255 && v >= sh.he.edges[idx + 1]) ++idx;
+            if (idx < 0) idx = 0;
+            sh.hist[idx] += nzero;
         }
-        const double tot = (double)cum;
+        long long run = 0;
+        for (int i = 0; i < 256; ++i) {
+            run += sh.hist[i];
+            sh.he.cdf[i] = (double)run;
+        }
+        const double tot = (double)run;
         for (int i = 0; i < 256; ++i) sh.he.cdf[i] = sh.he.cdf[i] / tot;
     }
     __syncthreads();
@@ -516,7 +635,7 @@ __device__ bool sigma_clipper_stage(Shared& sh, int ci, const float* S, int n, d
     // astropy: sigma_lower = sigma_lower or sigma(=3.0): a falsy 0 falls back to 3 (App. A.1 / B#1)
     const double slo = s_lo != 0.0 ? s_lo : 3.0, shi = s_hi != 0.0 ? s_hi : 3.0;
     double lo, hi, mean, sd;
-    if (!sigma_clip(sh, sh.ch[ci], S, n, slo, shi, lo, hi, mean, sd)) return false;
+    if (!sigma_clip(sh, sh.ch[ci], sh.cc[ci], S, n, slo, shi, lo, hi, mean, sd)) return false;
     push_op(sh, ci, S, n, OP_CLAMP, lo, hi, 0.0, 0.0);
     return true;
 }
@@ -531,80 +650,173 @@ __device__ __forceinline__ float load_pixel(const PPParams& p, int b, int idx) {
     return isfinite(f) ? f : 0.0f;  // utils.py:219,394
 }
 
-// LSD radix sort (4 x 8 bit) of `n` keys in global memory with one CTA: each warp owns a contiguous segment; ranks
-// inside a 32-key group come from __match_any_sync, so every pass is stable.
-__device__ void block_radix_sort(uint32_t* a, uint32_t* b, int n, int (*hist)[256], int* dtot) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int seg = (n + kPPWarps - 1) / kPPWarps;
-    seg = (seg + 31) & ~31;
-    const int s0 = min(n, w * seg), s1 = min(n, s0 + seg);
+// LSD radix sort (4 x 8 bit) of `n` keys in global memory with one CTA.  Every pass streams the keys in chunks of 8192
+// through shared memory: warp-striped loads, stable ranks inside the chunk from __match_any_sync + per-warp digit
+// counters, a counting sort of the chunk in shared memory, then a write-out in which consecutive threads carry
+// consecutive keys of one digit to consecutive addresses (full-sector stores; the direct per-key scatter this replaces
+// wrote 4 bytes per 32-byte sector).  The histogram of the NEXT digit is built during the write-out, so a pass reads
+// and writes every key once; passes whose digit is the same for all keys are skipped.
+static constexpr int kSortChunk = 8192;
+struct SortSmem {
+    int hist[256][kPPWarps + 1];  // [digit][warp] counters -> exclusive warp bases inside the chunk (+1: bank skew)
+    uint32_t sorted[kSortChunk];  // the chunk in digit order
+    int dtot[256], dbase[256], gcur[256];
+    int nh[2][256];               // digit histograms of the whole array (current / next pass)
+    int flag;
+};
+
+// lanes of `msk` whose 8-bit digit equals mine (eight independent ballots; MATCH.ANY is far slower than this)
+__device__ __forceinline__ uint32_t digit_peers(uint32_t msk, uint32_t d) {
+    uint32_t peers = msk;
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        const bool on = (d >> bit) & 1u;
+        const uint32_t b = __ballot_sync(msk, on);
+        peers &= on ? b : ~b;
+    }
+    return peers;
+}
+
+// exclusive scan of a[0..256) into out[0..256) by warp 0 (8 entries per lane); returns nothing
+__device__ __forceinline__ void scan256_warp0(const int* a, int* out) {
+    const int lane = threadIdx.x & 31;
+    int v[8], s = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        v[q] = a[lane * 8 + q];
+        s += v[q];
+    }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    int run = inc - s;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        out[lane * 8 + q] = run;
+        run += v[q];
+    }
+}
+
+// Returns the buffer (a or b) that holds the sorted keys.
+__device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem& sm) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     uint32_t* src = a;
     uint32_t* dst = b;
-    for (int shift = 0; shift < 32; shift += 8) {
-        for (int i = threadIdx.x; i < kPPWarps * 256; i += kPPThreads) (&hist[0][0])[i] = 0;
-        __syncthreads();
-        for (int i = s0 + lane; i < s1; i += 32) atomicAdd(&hist[w][(src[i] >> shift) & 255u], 1);
-        __syncthreads();
-        if (threadIdx.x < 256) {
-            int tot = 0;
-            for (int q = 0; q < kPPWarps; ++q) {
-                const int cnt = hist[q][threadIdx.x];
-                hist[q][threadIdx.x] = tot;
-                tot += cnt;
-            }
-            dtot[threadIdx.x] = tot;
+    for (int i = t; i < 512; i += kPPThreads) (&sm.nh[0][0])[i] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 4 * kPPThreads) {
+        uint32_t k[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * kPPThreads + t;
+            k[q] = i < n ? src[i] : 0xffffffffu;
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {  // exclusive scan of the 256 digit totals by one warp (8 per lane)
-            int v[8], s = 0;
-            for (int q = 0; q < 8; ++q) {
-                v[q] = dtot[lane * 8 + q];
-                s += v[q];
-            }
-            int inc = s;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += y;
-            }
-            int run = inc - s;
-            for (int q = 0; q < 8; ++q) {
-                dtot[lane * 8 + q] = run;
-                run += v[q];
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < 256) {
-            const int base = dtot[threadIdx.x];
-            for (int q = 0; q < kPPWarps; ++q) hist[q][threadIdx.x] += base;
-        }
-        __syncthreads();
-        for (int i0 = s0; i0 < s1; i0 += 32) {
-            const int i = i0 + lane;
-            const bool act = i < s1;
-            const uint32_t m = __ballot_sync(0xffffffffu, act);
-            if (act) {
-                const uint32_t key = src[i];
-                const uint32_t d = (key >> shift) & 255u;
-                const uint32_t peers = __match_any_sync(m, d);
-                const int rank = __popc(peers & ((1u << lane) - 1u));
-                const int pos = hist[w][d] + rank;
-                dst[pos] = key;
-                __syncwarp(m);
-                if (rank == 0) hist[w][d] += __popc(peers);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        uint32_t* t = src;
-        src = dst;
-        dst = t;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (i0 + q * kPPThreads + t < n) atomicAdd(&sm.nh[0][k[q] & 255u], 1);
     }
-    // 4 passes: result is back in `a`
+    __syncthreads();
+    int cur = 0;
+    for (int shift = 0; shift < 32; shift += 8, cur ^= 1) {
+        int* nh = sm.nh[cur];
+        int* nh_next = sm.nh[cur ^ 1];
+        if (t < 32) {
+            scan256_warp0(nh, sm.gcur);
+            int one = 0;
+            for (int q = 0; q < 8; ++q) one |= (nh[lane * 8 + q] == n);
+            one = __any_sync(0xffffffffu, one);
+            if (lane == 0) sm.flag = one;
+        }
+        for (int i = t; i < 256; i += kPPThreads) nh_next[i] = 0;
+        __syncthreads();
+        const bool trivial = sm.flag != 0;
+        const bool more = shift < 24;
+        if (trivial) {  // nothing moves; only the next digit's histogram is needed
+            if (more)
+                for (int i = t; i < n; i += kPPThreads) atomicAdd(&nh_next[(src[i] >> (shift + 8)) & 255u], 1);
+            __syncthreads();
+            continue;
+        }
+        for (int c0 = 0; c0 < n; c0 += kSortChunk) {
+            const int m = min(kSortChunk, n - c0);
+            for (int i = t; i < 256 * (kPPWarps + 1); i += kPPThreads) (&sm.hist[0][0])[i] = 0;
+            uint32_t key[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // independent loads first
+                const int li = w * 256 + j * 32 + lane;
+                key[j] = li < m ? src[c0 + li] : 0u;
+            }
+            __syncthreads();
+            int rnk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int li = w * 256 + j * 32 + lane;
+                const bool v = li < m;
+                rnk[j] = -1;
+                const uint32_t msk = __ballot_sync(0xffffffffu, v);
+                if (v) {
+                    const uint32_t d = (key[j] >> shift) & 255u;
+                    const uint32_t peers = digit_peers(msk, d);
+                    const int r = __popc(peers & ((1u << lane) - 1u));
+                    const int pre = sm.hist[d][w];
+                    __syncwarp(msk);
+                    if (r == 0) sm.hist[d][w] = pre + __popc(peers);
+                    rnk[j] = pre + r;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            // per digit: exclusive scan over the 32 warps (one warp per digit, 8 digits per warp)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int d = w * 8 + q;
+                const int v = sm.hist[d][lane];
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                sm.hist[d][lane] = inc - v;
+                if (lane == 31) sm.dtot[d] = inc;
+            }
+            __syncthreads();
+            if (t < 32) scan256_warp0(sm.dtot, sm.dbase);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (rnk[j] >= 0) {
+                    const uint32_t d = (key[j] >> shift) & 255u;
+                    sm.sorted[sm.dbase[d] + sm.hist[d][w] + rnk[j]] = key[j];
+                }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kSortChunk / kPPThreads; ++q) {
+                const int j = q * kPPThreads + t;
+                if (j < m) {
+                    const uint32_t k = sm.sorted[j];
+                    const uint32_t d = (k >> shift) & 255u;
+                    dst[sm.gcur[d] + (j - sm.dbase[d])] = k;
+                    if (more) atomicAdd(&nh_next[(k >> (shift + 8)) & 255u], 1);
+                }
+            }
+            __syncthreads();
+            if (t < 256) sm.gcur[t] += sm.dtot[t];
+        }
+        __syncthreads();
+        uint32_t* x = src;
+        src = dst;
+        dst = x;
+    }
+    return src;
 }
 
 __global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_constant__ PPParams p) {
-    __shared__ int hist[kPPWarps][256];
-    __shared__ int dtot[256];
+    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+    SortSmem& sm = *reinterpret_cast<SortSmem*>(sort_smem_raw);
     __shared__ int s_n, s_nb;
     const int b = blockIdx.x;
     const int N = p.Ty * p.Tx;
@@ -621,38 +833,46 @@ __global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_consta
     const int xc = p.Tx / 2, yc = p.Ty / 2;
     const int dy = (int)(p.Ty * p.cfg.bkg_box_mask_fract / 2.0), dx = (int)(p.Tx * p.cfg.bkg_box_mask_fract / 2.0);
     const int lane = threadIdx.x & 31;
-    for (int i0 = 0; i0 < N; i0 += kPPThreads) {
-        const int i = i0 + threadIdx.x;
-        float f = 0.f;
-        if (i < N) {
-            f = load_pixel(p, b, i);
-            tile[i] = f;
+    for (int i00 = 0; i00 < N; i00 += 4 * kPPThreads) {
+        float fq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // four independent loads in flight per thread
+            const int i = i00 + q * kPPThreads + threadIdx.x;
+            fq[q] = i < N ? load_pixel(p, b, i) : 0.f;
         }
-        const bool live = (i < N) && (f != 0.0f);
-        const uint32_t m = __ballot_sync(0xffffffffu, live);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (live) A[base + __popc(m & ((1u << lane) - 1u))] = f2key(f);
-        if (C) {
-            const int y = i / p.Tx, x = i - y * p.Tx;
-            const bool inbox = (y >= yc - dy && y < yc + dy && x >= xc - dx && x < xc + dx);
-            const bool lb = live && !inbox;
-            const uint32_t m2 = __ballot_sync(0xffffffffu, lb);
-            int base2 = 0;
-            if (lane == 0 && m2) base2 = atomicAdd(&s_nb, __popc(m2));
-            base2 = __shfl_sync(0xffffffffu, base2, 0);
-            if (lb) C[base2 + __popc(m2 & ((1u << lane) - 1u))] = f2key(f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i00 + q * kPPThreads + threadIdx.x;
+            const float f = fq[q];
+            if (i < N) tile[i] = f;
+            const bool live = (i < N) && (f != 0.0f);
+            const uint32_t m = __ballot_sync(0xffffffffu, live);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) A[base + __popc(m & ((1u << lane) - 1u))] = f2key(f);
+            if (C) {
+                const int y = i / p.Tx, x = i - y * p.Tx;
+                const bool inbox = (y >= yc - dy && y < yc + dy && x >= xc - dx && x < xc + dx);
+                const bool lb = live && !inbox;
+                const uint32_t m2 = __ballot_sync(0xffffffffu, lb);
+                int base2 = 0;
+                if (lane == 0 && m2) base2 = atomicAdd(&s_nb, __popc(m2));
+                base2 = __shfl_sync(0xffffffffu, base2, 0);
+                if (lb) C[base2 + __popc(m2 & ((1u << lane) - 1u))] = f2key(f);
+            }
         }
     }
     __syncthreads();
     const int n = s_n, nb = s_nb;
-    block_radix_sort(A, Bk, n, hist, dtot);
-    for (int i = threadIdx.x; i < n; i += kPPThreads) A[i] = __float_as_uint(key2f(A[i]));
+    {
+        const uint32_t* r = block_radix_sort(A, Bk, n, sm);
+        for (int i = threadIdx.x; i < n; i += kPPThreads) A[i] = __float_as_uint(key2f(r[i]));
+    }
     if (C) {
         __syncthreads();
-        block_radix_sort(C, Bk, nb, hist, dtot);
-        for (int i = threadIdx.x; i < nb; i += kPPThreads) C[i] = __float_as_uint(key2f(C[i]));
+        const uint32_t* r = block_radix_sort(C, Bk, nb, sm);
+        for (int i = threadIdx.x; i < nb; i += kPPThreads) C[i] = __float_as_uint(key2f(r[i]));
     }
     if (threadIdx.x == 0) {
         p.nlive[b] = n;
@@ -682,6 +902,7 @@ __global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_const
         }
         sh.next_hid = 1;
         sh.fail = 0;
+        for (int c = 0; c < 3; ++c) compile_chan(sh.ch[c], sh.cc[c], S);
     }
     __syncthreads();
     bool ok = true;  // uniform across the block
@@ -710,7 +931,7 @@ __global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_const
                     const float* Sb = cfg.use_box_mask_in_bkg ? Sbox : S;
                     const int nb = cfg.use_box_mask_in_bkg ? p.nbox[b] : n;
                     const double sg = cfg.sigma_bkg != 0 ? cfg.sigma_bkg : 3.0;
-                    ok = sigma_clip(sh, sh.ch[c], Sb, nb, sg, sg, lo, hi, mean, sd);
+                    ok = sigma_clip(sh, sh.ch[c], sh.cc[c], Sb, nb, sg, sg, lo, hi, mean, sd);
                     if (ok) push_op(sh, c, S, n, OP_SUB, mean, 0, 0, 0);
                 }
                 in_hid[c] = hid;
@@ -727,7 +948,7 @@ __global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_const
                 } else {
                     double lo, hi, mean, sd;
                     const double sg = cfg.sigma_clip != 0 ? cfg.sigma_clip : 3.0;
-                    ok = sigma_clip(sh, sh.ch[c], S, n, sg, sg, lo, hi, mean, sd);
+                    ok = sigma_clip(sh, sh.ch[c], sh.cc[c], S, n, sg, sg, lo, hi, mean, sd);
                     if (ok) push_op(sh, c, S, n, OP_SHIFT, mean + cfg.sigma_clip * sd, 0, 0, 0);
                 }
                 in_hid[c] = hid;
@@ -783,16 +1004,14 @@ __global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_const
                 if (q >= 0) {
                     copy_chan(sh, c, q);
                 } else {
+                    // min / max over the non-zero pixels = first / last live element of the sorted array
                     const Chan& ch = sh.ch[c];
                     double mn = INFINITY, mx = -INFINITY;
-                    for (int i = threadIdx.x; i < n; i += kPPThreads) {
-                        const double v = eval_ops<true>(ch, ch.nops, sh.he, (double)S[i]);
-                        if (v != 0.0) {
-                            mn = fmin(mn, v);
-                            mx = fmax(mx, v);
-                        }
+                    const int nl = live_count(ch, 0, n);
+                    if (nl > 0) {
+                        mn = eval_ops<true>(ch, ch.nops, sh.he, (double)S[kth_live(ch, 0, 0)]);
+                        mx = eval_ops<true>(ch, ch.nops, sh.he, (double)S[kth_live(ch, 0, nl - 1)]);
                     }
-                    block_minmax(mn, mx, sh.red);
                     if (!(mn <= mx)) ok = false;  // no non-zero pixel -> None (preprocessing.py:101-103)
                     else push_op(sh, c, S, n, OP_MINMAX, mn, mx - mn, cfg.norm_max - cfg.norm_min, cfg.norm_min);
                 }
@@ -811,10 +1030,14 @@ __global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_const
     const bool same01 = sh.ch[0].hid == sh.ch[1].hid, same02 = sh.ch[0].hid == sh.ch[2].hid,
                same12 = sh.ch[1].hid == sh.ch[2].hid;
     for (int i = threadIdx.x; i < N; i += kPPThreads) {
-        const double x = (double)tile[i];
-        const double v0 = eval_ops<true>(sh.ch[0], sh.ch[0].nops, sh.he, x);
-        const double v1 = same01 ? v0 : eval_ops<true>(sh.ch[1], sh.ch[1].nops, sh.he, x);
-        const double v2 = same02 ? v0 : (same12 ? v1 : eval_ops<true>(sh.ch[2], sh.ch[2].nops, sh.he, x));
+        const float xf = tile[i];
+        const double x = (double)xf;
+        const double v0 = in_zero_x(sh.cc[0], xf) ? 0.0 : eval_fast(sh.cc[0], sh.ch[0], sh.he, x);
+        const double v1 = same01 ? v0 : (in_zero_x(sh.cc[1], xf) ? 0.0 : eval_fast(sh.cc[1], sh.ch[1], sh.he, x));
+        const double v2 = same02 ? v0
+                                 : (same12 ? v1
+                                           : (in_zero_x(sh.cc[2], xf) ? 0.0
+                                                                      : eval_fast(sh.cc[2], sh.ch[2], sh.he, x)));
         out[(long long)i * 3 + 0] = (float)v0;
         out[(long long)i * 3 + 1] = (float)v1;
         out[(long long)i * 3 + 2] = (float)v2;
@@ -950,9 +1173,10 @@ extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long
     static bool attr_done = false;
     if (!attr_done) {
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
+        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
         attr_done = true;
     }
-    pp_sort_kernel<<<B, kPPThreads, 0, st>>>(p);
+    pp_sort_kernel<<<B, kPPThreads, sizeof(SortSmem), st>>>(p);
     pp_chain_kernel<<<B, kPPThreads, sizeof(Shared), st>>>(p);
     CY_CUDA_CHECK(cudaGetLastError());
     if (model_in) return cy_letterbox_resize(chain_out, B, Ty, Tx, imgsz, model_in, model_in_f32, stream);
