@@ -42,7 +42,7 @@ def parse():
     ap.add_argument('--step', type=float, default=1.0)
     ap.add_argument('--variant', default='l')
     ap.add_argument('--imgsz', type=int, default=640)
-    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--batch', type=int, default=296)
     ap.add_argument('--cpu-tiles', type=int, default=16, help='tiles in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')

@@ -368,13 +368,47 @@ struct Shared {
     int hist[256];
     int next_hid;
     int fail;                // tile status
+    int sidx;                // block-wide search scratch
 };
+
+// Block-cooperative version of lower_index (all threads call it with the same arguments): every round probes
+// kPPThreads equally spaced elements at once, so 2^18 elements need two rounds of one load each instead of 18
+// dependent loads per thread.
+template <bool STRICT>
+__device__ int lower_index_coop(Shared& sh, const Chan& c, int nops, const float* S, int a, int b, double t) {
+    int lo = a, hi = b;
+    while (hi > lo) {
+        const int len = hi - lo;
+        const int step = (len + kPPThreads - 1) / kPPThreads;
+        const long long mi = (long long)lo + (long long)threadIdx.x * step;
+        bool ok = true;  // probes at or beyond hi count as "true"
+        if (mi < hi) {
+            const double v = eval_ops<false>(c, nops, sh.he, (double)S[mi]);
+            ok = STRICT ? (v > t) : (v >= t);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sh.sidx = kPPThreads;
+        __syncthreads();
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && bal) atomicMin(&sh.sidx, (int)(threadIdx.x & ~31u) + __ffs(bal) - 1);
+        __syncthreads();
+        const int T = sh.sidx;  // first probing thread whose predicate holds (kPPThreads: none)
+        const long long mT = (long long)lo + (long long)T * step;
+        const int nhi = (int)(mT < hi ? mT : hi);
+        const int nlo = T == 0 ? lo : (int)(mT - step + 1 < hi ? mT - step + 1 : hi);
+        if (step == 1 || T == 0) return nhi;
+        lo = nlo;
+        hi = nhi;
+    }
+    return lo;
+}
 
 // Pivoted moment sums of the live values f(S[i]), i in [a,b) U [a2,b2):  n, sum(v-p), sum((v-p)^2)   (fp64).
 // Values come from the compiled op list; masked elements are the zero index ranges of the channel.
 __device__ void range_sums(const Chan& c, const Comp& cc, const HistEq& he, const float* S, int a, int b, int a2,
                            int b2, double p, double* red, double& s0, double& s1, double& s2) {
     double n = 0.0, u = 0.0, q = 0.0;
+#pragma unroll 4
     for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
         if (!in_zero_idx(c, i)) {
             const double d = eval_fast(cc, c, he, (double)S[i]) - p;
@@ -431,8 +465,8 @@ __device__ bool sigma_clip(Shared& sh, const Chan& c, const Comp& cc, const floa
         const double med = live_median(c, sh.he, S, a, cnt);
         lo = med - sd * sig_lo;
         hi = med + sd * sig_hi;
-        const int na = lower_index<false>(c, c.nops, sh.he, S, a, b, lo);   // first f >= lo
-        const int nb = lower_index<true>(c, c.nops, sh.he, S, na, b, hi);   // first f > hi
+        const int na = lower_index_coop<false>(sh, c, c.nops, S, a, b, lo);   // first f >= lo
+        const int nb = lower_index_coop<true>(sh, c, c.nops, S, na, b, hi);   // first f > hi
         const int ncnt = live_count(c, na, nb);
         if (ncnt == cnt) break;
         if (ncnt <= 0) return false;
@@ -467,8 +501,8 @@ __device__ void push_op(Shared& sh, int ci, const float* S, int n, int kind, dou
     }
     __syncthreads();
     // zero set of the plain composition is a contiguous index range (monotone): [first >= 0, first > 0)
-    const int h0 = lower_index<false>(c, c.nops, sh.he, S, 0, n, 0.0);
-    const int h1 = lower_index<true>(c, c.nops, sh.he, S, h0, n, 0.0);
+    const int h0 = lower_index_coop<false>(sh, c, c.nops, S, 0, n, 0.0);
+    const int h1 = lower_index_coop<true>(sh, c, c.nops, S, h0, n, 0.0);
     __syncthreads();
     if (threadIdx.x == 0) {
         add_zero_range(c, h0, h1);
@@ -1029,6 +1063,7 @@ __global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_const
     }
     const bool same01 = sh.ch[0].hid == sh.ch[1].hid, same02 = sh.ch[0].hid == sh.ch[2].hid,
                same12 = sh.ch[1].hid == sh.ch[2].hid;
+#pragma unroll 4
     for (int i = threadIdx.x; i < N; i += kPPThreads) {
         const float xf = tile[i];
         const double x = (double)xf;

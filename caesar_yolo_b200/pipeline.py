@@ -56,7 +56,7 @@ class Engine(object):
     all tiles of a rank at once (the reference runs them one by one, batch 1)."""
 
     def __init__(self, weights, pp_cfg, imgsz=640, score_thr=0.7, iou_thr=0.5, thr_soft=0.3, thr_hard=0.8,
-                 device=None, batch_tiles=32, pp_tiles=296):
+                 device=None, batch_tiles=296, pp_tiles=296):
         if not torch.cuda.is_available():
             raise CaesarB200Error("no CUDA device: the B200 path has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
