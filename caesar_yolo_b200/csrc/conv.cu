@@ -104,7 +104,7 @@ __device__ __forceinline__ void epi_cols32(const uint32_t (&v)[32], const float4
     }
 }
 
-template <int HALVES, int KSTEPS>
+template <int HALVES, int KSTEPS, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,6 +113,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int lane = threadIdx.x & 31;
     const uint32_t row_bytes = p.kc * 2;
     const int a_stages = p.a_stages, b_stages = p.b_stages;
+    // PAIR: two CTAs of a cluster (one TPC) work on one unit with tcgen05 cta_group::2: every MMA covers 128 rows
+    // from each CTA (own A boxes) and block_n/2 weight rows from each CTA's shared memory, so each SM reads half of
+    // B per flop.  The rank-0 CTA issues the MMAs; barriers "full" live in the leader, "empty" are multicast to both.
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int kCtasPerUnit = PAIR ? 2 : 1;
 
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + (size_t)a_stages * p.a_stage_bytes;
@@ -140,17 +147,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kNumEpiWarps);
+            mbar_init(&acc_empty[s], kNumEpiWarps * kCtasPerUnit);
         }
         for (int s = 0; s < 2 * kNumEpiWarps; ++s) mbar_init(&res_bar[s], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync();   // barrier inits + TMEM allocation of both CTAs visible before any remote signal
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr int halves = HALVES;
@@ -162,21 +175,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // ------------------------------------------------------------ A-box producer
         int s = 0;
         uint32_t ph = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        for (int u = worker; u < p.n_units; u += n_workers) {
             const int mu = u / p.n_tiles_n;
-            const HalfCoord hc0 = half_coord(p, mu * HALVES);
-            const HalfCoord hc1 = half_coord(p, mu * HALVES + 1);
+            const HalfCoord hc0 = half_coord(p, (mu * kCtasPerUnit + (int)rank) * HALVES);
+            const HalfCoord hc1 = half_coord(p, (mu * kCtasPerUnit + (int)rank) * HALVES + 1);
             for (int ck = 0; ck < p.cchunks; ++ck) {
                 for (int al = 0; al < p.n_aloads; ++al) {
                     const ConvALoad L = p.aload[al];
                     mbar_wait(&a_empty[s], ph ^ 1);
                     if (elect_one()) {
                         uint8_t* dst = a_ring + (size_t)s * p.a_stage_bytes;
-                        mbar_arrive_expect_tx(&a_full[s], p.a_box_bytes * HALVES);
-                        tma_load_4d(dst, &p.tmA[L.map], &a_full[s], ck * p.kc, hc0.w0 + L.dw, hc0.h0 + L.dh, hc0.n0);
-                        if (HALVES == 2)
-                            tma_load_4d(dst + p.a_half_stride, &p.tmA[L.map], &a_full[s], ck * p.kc, hc1.w0 + L.dw,
-                                        hc1.h0 + L.dh, hc1.n0);
+                        if (rank == 0) mbar_arrive_expect_tx(&a_full[s], p.a_box_bytes * HALVES * kCtasPerUnit);
+                        if (PAIR) {
+                            const uint32_t bar = mapa_u32(smem_u32(&a_full[s]), 0);
+                            tma_load_4d_pair(dst, &p.tmA[L.map], bar, ck * p.kc, hc0.w0 + L.dw, hc0.h0 + L.dh, hc0.n0);
+                            if (HALVES == 2)
+                                tma_load_4d_pair(dst + p.a_half_stride, &p.tmA[L.map], bar, ck * p.kc, hc1.w0 + L.dw,
+                                                 hc1.h0 + L.dh, hc1.n0);
+                        } else {
+                            tma_load_4d(dst, &p.tmA[L.map], &a_full[s], ck * p.kc, hc0.w0 + L.dw, hc0.h0 + L.dh,
+                                        hc0.n0);
+                            if (HALVES == 2)
+                                tma_load_4d(dst + p.a_half_stride, &p.tmA[L.map], &a_full[s], ck * p.kc,
+                                            hc1.w0 + L.dw, hc1.h0 + L.dh, hc1.n0);
+                        }
                     }
                     __syncwarp();
                     if (++s == a_stages) {
@@ -190,7 +212,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         // ------------------------------------------------------------ weight-tile producer
         int s = 0;
         uint32_t ph = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int b_rows = p.block_n / kCtasPerUnit;   // weight rows this CTA stages per tile
+        for (int u = worker; u < p.n_units; u += n_workers) {
             const int n_tile = u % p.n_tiles_n;
             for (int ck = 0; ck < p.cchunks; ++ck) {
                 for (int al = 0; al < p.n_aloads; ++al) {
@@ -199,9 +222,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         const int wtap = p.tap[L.tap0 + t].wtap;
                         mbar_wait(&b_empty[s], ph ^ 1);
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(&b_full[s], p.b_tile_bytes);
-                            tma_load_2d(b_ring + (size_t)s * p.b_stage_bytes, &p.tmB, &b_full[s],
-                                        wtap * p.cin + ck * p.kc, n_tile * p.block_n);
+                            if (rank == 0) mbar_arrive_expect_tx(&b_full[s], p.b_tile_bytes * kCtasPerUnit);
+                            if (PAIR)
+                                tma_load_2d_pair(b_ring + (size_t)s * p.b_stage_bytes, &p.tmB,
+                                                 mapa_u32(smem_u32(&b_full[s]), 0), wtap * p.cin + ck * p.kc,
+                                                 n_tile * p.block_n + (int)rank * b_rows);
+                            else
+                                tma_load_2d(b_ring + (size_t)s * p.b_stage_bytes, &p.tmB, &b_full[s],
+                                            wtap * p.cin + ck * p.kc, n_tile * p.block_n);
                         }
                         __syncwarp();
                         if (++s == b_stages) {
@@ -213,18 +241,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one elected thread)
-        const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n);
+      if (rank == 0) {
+        // ------------------------------------------------------------ MMA issuer (one elected thread of the leader)
+        const uint32_t idesc = make_idesc_bf16(kBlockM * kCtasPerUnit, p.block_n);
         const uint32_t a_ring_addr = smem_u32(a_ring);
         const uint32_t b_ring_addr = smem_u32(b_ring);
         int sa = 0, sb = 0;
         uint32_t pha = 0, phb = 0;
         int i = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        for (int u = worker; u < p.n_units; u += n_workers, ++i) {
             const int buf = p.acc_bufs == 2 ? (i & 1) : 0;
             const uint32_t use = p.acc_bufs == 2 ? (uint32_t)(i >> 1) : (uint32_t)i;
             unsigned long long* dbg =
-                (p.dbg && i < p.dbg_units) ? p.dbg + ((size_t)blockIdx.x * p.dbg_units + i) * 8 : nullptr;
+                (p.dbg && i < p.dbg_units) ? p.dbg + ((size_t)worker * p.dbg_units + i) * 8 : nullptr;
             long long wait_a = 0, wait_b = 0;
             if (dbg && lane == 0) dbg[0] = clock64();
             mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
@@ -254,11 +283,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                 const uint64_t da = da0 + (uint64_t)((h * p.a_half_stride) >> 4);
                                 const uint32_t td = tacc + (uint32_t)(h * p.acc_stride);
 #pragma unroll
-                                for (int k = 0; k < KSTEPS; ++k)
+                                for (int k = 0; k < KSTEPS; ++k) {
                                     // advancing 16 bf16 (=32 B) along K inside the swizzle row = +2 in the 16 B field
-                                    umma_bf16(td, da + 2u * k, db + 2u * k, idesc, accum | (uint32_t)k);
+                                    if (PAIR) umma_bf16_pair(td, da + 2u * k, db + 2u * k, idesc, accum | (uint32_t)k);
+                                    else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, accum | (uint32_t)k);
+                                }
                             }
-                            umma_commit(&b_empty[sb]);
+                            if (PAIR) umma_commit_pair(&b_empty[sb]);
+                            else umma_commit(&b_empty[sb]);
                         }
                         __syncwarp();
                         accum = 1;
@@ -267,7 +299,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                             phb ^= 1;
                         }
                     }
-                    if (elect_one()) umma_commit(&a_empty[sa]);
+                    if (elect_one()) {
+                        if (PAIR) umma_commit_pair(&a_empty[sa]);
+                        else umma_commit(&a_empty[sa]);
+                    }
                     __syncwarp();
                     if (++sa == a_stages) {
                         sa = 0;
@@ -275,7 +310,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     }
                 }
             }
-            if (elect_one()) umma_commit(&acc_full[buf]);
+            if (elect_one()) {
+                if (PAIR) umma_commit_pair(&acc_full[buf]);
+                else umma_commit(&acc_full[buf]);
+            }
             __syncwarp();
             if (dbg && lane == 0) {
                 dbg[2] = clock64();
@@ -283,6 +321,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 dbg[4] = (unsigned long long)wait_a;
             }
         }
+      }
     } else {
         // ------------------------------------------------------------ epilogue
         // TMEM -> registers -> bias + SiLU -> swizzled staging buffer (+ residual, TMA-loaded into the same buffer,
@@ -308,16 +347,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         int bufsel = 0;
         uint32_t rphase0 = 0, rphase1 = 0;
         int i = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        for (int u = worker; u < p.n_units; u += n_workers, ++i) {
             const int buf = p.acc_bufs == 2 ? (i & 1) : 0;
             const uint32_t use = p.acc_bufs == 2 ? (uint32_t)(i >> 1) : (uint32_t)i;
             const int n_tile = u % p.n_tiles_n;
             const int mu = u / p.n_tiles_n;
-            const HalfCoord hc = half_coord(p, mu * halves + h);
+            const HalfCoord hc = half_coord(p, (mu * kCtasPerUnit + (int)rank) * halves + h);
             const bool valid_half = hc.n0 < p.B;
             const int bw0 = hc.w0 + sub_w, bh0 = hc.h0 + sub_h, bn0 = hc.n0 + sub_n;
-            unsigned long long* dbg = (p.dbg && e == 0 && lane == 0 && i < p.dbg_units)
-                                          ? p.dbg + ((size_t)blockIdx.x * p.dbg_units + i) * 8
+            unsigned long long* dbg = (p.dbg && e == 0 && lane == 0 && rank == 0 && i < p.dbg_units)
+                                          ? p.dbg + ((size_t)worker * p.dbg_units + i) * 8
                                           : nullptr;
             if (dbg) dbg[5] = clock64();
             mbar_wait(&acc_full[buf], use & 1);
@@ -385,7 +424,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) {
+                if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+                else mbar_arrive(&acc_empty[buf]);
+            }
             if (dbg) dbg[7] = clock64();
         }
         if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores that read it
@@ -393,10 +435,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync();   // the peer's shared memory / TMEM stay valid until the leader's last MMA retired
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+        else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -473,35 +517,47 @@ void conv_set_debug(unsigned long long* dev_buf, int units_per_cta) {
     g_dbg_units = units_per_cta;
 }
 
-template <int HALVES, int KSTEPS>
+template <int HALVES, int KSTEPS, bool PAIR>
 static int launch_t(const ConvPlan& pl, cudaStream_t st) {
     static bool attr_done = false;
+    auto kern = conv_igemm_kernel<HALVES, KSTEPS, PAIR>;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<HALVES, KSTEPS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
+    ConvKParams kp = pl.kp;
     if (g_dbg) {
-        ConvKParams kp = pl.kp;
         kp.dbg = g_dbg;
         kp.dbg_units = g_dbg_units;
-        conv_igemm_kernel<HALVES, KSTEPS><<<pl.grid, kConvThreads, pl.smem, st>>>(kp);
-    } else {
-        conv_igemm_kernel<HALVES, KSTEPS><<<pl.grid, kConvThreads, pl.smem, st>>>(pl.kp);
     }
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pl.grid;
+    cfg.blockDim = dim3(kConvThreads, 1, 1);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, kp);
 }
 
 int conv_launch(const ConvPlan& pl, cudaStream_t st) {
-    const int key = pl.kp.halves * 10 + (pl.kp.kc >> 4);
+    const int key = pl.kp.pair * 100 + pl.kp.halves * 10 + (pl.kp.kc >> 4);
     switch (key) {
-        case 11: return launch_t<1, 1>(pl, st);
-        case 12: return launch_t<1, 2>(pl, st);
-        case 14: return launch_t<1, 4>(pl, st);
-        case 21: return launch_t<2, 1>(pl, st);
-        case 22: return launch_t<2, 2>(pl, st);
-        case 24: return launch_t<2, 4>(pl, st);
+        case 11: return launch_t<1, 1, false>(pl, st);
+        case 12: return launch_t<1, 2, false>(pl, st);
+        case 14: return launch_t<1, 4, false>(pl, st);
+        case 21: return launch_t<2, 1, false>(pl, st);
+        case 22: return launch_t<2, 2, false>(pl, st);
+        case 24: return launch_t<2, 4, false>(pl, st);
+        case 114: return launch_t<1, 4, true>(pl, st);
+        case 124: return launch_t<2, 4, true>(pl, st);
     }
     return (int)cudaErrorInvalidValue;
 }
@@ -578,8 +634,22 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     int halves = ((kp.n_half_tiles + 1) / 2) * kp.n_tiles_n >= num_sms() ? 2 : 1;
     const int force_halves = env_int("CY_CONV_HALVES", 0);
     if (force_halves == 1 || force_halves == 2) halves = force_halves;
+    // CTA pairs: 128-byte channel chunks, a weight tile that splits into two halves of >= 32 rows, and enough units
+    // to give every pair of SMs work
+    // Measured per layer (profiles/): pairs win once the K loop is long enough to amortise the cluster hand-shakes
+    // (K = taps * cin >= 768); short-K layers are epilogue-bound and run better as independent CTAs.
+    int pair = 0;
+    const bool pair_ok = kc == 64 && bn_ >= 64;
+    if (pair_ok && ntaps * d.cin >= 768 &&
+        ((kp.n_half_tiles + 2 * halves - 1) / (2 * halves)) * kp.n_tiles_n >= num_sms() / 2)
+        pair = 1;
+    const int force_pair = env_int("CY_CONV_PAIR", -1);   // -1 auto, 0 off, 2 force wherever possible
+    if (force_pair == 0) pair = 0;
+    if (force_pair == 2) pair = pair_ok ? 1 : 0;
+    kp.pair = pair;
     kp.halves = halves;
-    kp.n_units_m = (kp.n_half_tiles + halves - 1) / halves;
+    const int per_unit = halves * (pair ? 2 : 1);
+    kp.n_units_m = (kp.n_half_tiles + per_unit - 1) / per_unit;
     kp.n_units = kp.n_units_m * kp.n_tiles_n;
     kp.acc_stride = bn_ < 32 ? 32 : bn_;
     kp.acc_bufs = 2 * halves * kp.acc_stride <= 512 ? 2 : 1;
@@ -646,7 +716,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     kp.a_box_bytes = (uint32_t)(box_w * box_h * box_n * row_bytes);
     kp.a_half_stride = (kp.a_box_bytes + 1023u) & ~1023u;
     kp.a_stage_bytes = kp.a_half_stride * halves;
-    kp.b_tile_bytes = (uint32_t)(bn_ * row_bytes);
+    kp.b_tile_bytes = (uint32_t)((bn_ / (pair ? 2 : 1)) * row_bytes);   // per CTA
     kp.b_stage_bytes = (kp.b_tile_bytes + 1023u) & ~1023u;
 
     // ---- A tensor maps
@@ -679,7 +749,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     {
         const cuuint64_t dims[2] = {(cuuint64_t)ntaps * d.cin, (cuuint64_t)d.cout_pad};
         const cuuint64_t str[1] = {(cuuint64_t)ntaps * d.cin * 2};
-        const cuuint32_t bbox[2] = {(cuuint32_t)kc, (cuuint32_t)bn_};
+        const cuuint32_t bbox[2] = {(cuuint32_t)kc, (cuuint32_t)(bn_ / (pair ? 2 : 1))};
         const cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d.w, dims, str, bbox, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -741,7 +811,11 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     plan->smem = (size_t)a_stages * kp.a_stage_bytes + (size_t)b_stages * kp.b_stage_bytes + epi_bytes +
                  (size_t)(2 * a_stages + 2 * b_stages + 4 + 2 * kNumEpiWarps) * 8 + 16 + 1024;
     plan->block_n = bn_;
-    const int g = kp.n_units < num_sms() ? kp.n_units : num_sms();
+    int g = kp.n_units < num_sms() ? kp.n_units : num_sms();
+    if (pair) {
+        const int nclusters = kp.n_units < num_sms() / 2 ? kp.n_units : num_sms() / 2;
+        g = 2 * nclusters;
+    }
     plan->grid = dim3(g, 1, 1);
     plan->flops = 2.0 * d.B * Hout * Wout * (double)d.cout * ntaps * d.cin;
     return 0;

@@ -75,6 +75,7 @@ struct ConvKParams {
     int act;                       // 1 = SiLU
     int out_f32;                   // 1 = write fp32
     int mode;
+    int pair;                      // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2), a unit = 2 x halves half tiles
     unsigned long long* dbg;       // optional per-CTA timeline (clock64 stamps), 8 words per unit, see conv_probe
     int dbg_units;
     ConvALoad aload[9];

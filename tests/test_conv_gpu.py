@@ -84,3 +84,29 @@ def test_conv_large_batch_persistent():
     _run_case(B=24, H=80, W=80, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False, seed=11)
     _run_case(B=32, H=40, W=40, cin=256, cout=512, k=1, s=1, act=True, res=False, out_f32=False, seed=12)
     _run_case(B=16, H=160, W=160, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False, seed=13)
+
+
+PAIR_SHAPES = [
+    dict(B=2, H=16, W=16, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False),
+    dict(B=3, H=40, W=40, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=1, H=80, W=40, cin=256, cout=256, k=3, s=1, act=True, res=False, out_f32=False, in_extra=64, out_extra=128),
+    dict(B=7, H=20, W=20, cin=192, cout=256, k=1, s=1, act=True, res=False, out_f32=False),
+    dict(B=3, H=40, W=40, cin=64, cout=128, k=3, s=2, act=True, res=False, out_f32=False),
+    dict(B=2, H=20, W=20, cin=64, cout=64, k=1, s=1, act=False, res=False, out_f32=True, out_extra=16),
+]
+
+
+@pytest.mark.parametrize("halves", [1, 2])
+@pytest.mark.parametrize("shape", range(len(PAIR_SHAPES)))
+def test_conv_cta_pairs(monkeypatch, halves, shape):
+    """tcgen05 cta_group::2 path (cluster of two CTAs per work unit), forced on small shapes."""
+    monkeypatch.setenv("CY_CONV_PAIR", "2")
+    monkeypatch.setenv("CY_CONV_HALVES", str(halves))
+    _run_case(seed=shape + 21, **PAIR_SHAPES[shape])
+
+
+def test_conv_cta_pairs_persistent(monkeypatch):
+    monkeypatch.setenv("CY_CONV_PAIR", "2")
+    _run_case(B=24, H=80, W=80, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False, seed=31)
+    _run_case(B=32, H=40, W=40, cin=256, cout=512, k=1, s=1, act=True, res=False, out_f32=False, seed=32)
+    _run_case(B=16, H=160, W=160, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False, seed=33)
