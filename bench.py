@@ -24,6 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ['NCCL_DEBUG'] = 'WARN'   # NCCL_DEBUG=VERSION/INFO print to stdout; the contract is ONE JSON line there
 
 PP_FLAGS = dict(subtract_bkg=True, clip_data=True, zscale_stretch=True, chan3_preproc=True, normalize_minmax=True,
                 nchannels=3, norm_max=255.)
