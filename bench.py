@@ -310,6 +310,18 @@ def main():
                             "algorithmic_flops_per_launch": conv_fl / len(conv),
                             "conv_share_of_forward": conv_ms / tot_ms,
                             "forward_ms_per_tile": tot_ms / args.batch}
+        # dram traffic per launch from the committed ncu capture (profiles/conv_traffic.json), scaled to this batch;
+        # algorithmic bytes per launch from the plan (input + weights + output + residual, each once)
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_traffic.json')))
+            line["roofline"]["traffic"] = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["conv_launches"] * (
+                args.batch / float(tj["tiles"]))
+            line["roofline"]["traffic_source"] = tj["source"]
+            line["roofline"]["tensor_pipe_active_pct_ncu"] = tj.get("tensor_pipe_active_pct_time_weighted")
+        except Exception:
+            pass
+        ab, nconv = eng.model.conv_bytes(args.batch, Sh, Sw)
+        line["roofline"]["algorithmic_bytes_per_launch"] = ab / max(nconv, 1)
         slow = sorted(prof, key=lambda p: -p[1])[:8]
         line["roofline"]["top_ops"] = [{"op": n_, "ms": round(ms, 4), "tflops": round(fl / (ms * 1e-3) / 1e12, 1) if ms > 0 else 0} for n_, ms, fl in slow]
 

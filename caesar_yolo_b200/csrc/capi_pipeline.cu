@@ -69,6 +69,22 @@ extern "C" int cy_model_profile(void* model, const void* in, int B, int Sh, int 
     return ((Model*)model)->profile(in, B, Sh, Sw, cap, names_host, ms_host, flops_host, nops_host,
                                     (cudaStream_t)stream);
 }
+extern "C" int cy_model_conv_bytes(void* model, int B, int Sh, int Sw, double* bytes_host, int* nconv_host) {
+    if (!model || !bytes_host) return set_error(CY_ERR_INVALID, "null argument");
+    Plan* pl = nullptr;
+    int r = ((Model*)model)->get_plan(B, Sh, Sw, &pl);
+    if (r) return r;
+    double tot = 0;
+    int n = 0;
+    for (const Op& op : pl->ops)
+        if (op.type == Op::CONV) {
+            tot += op.conv.bytes;
+            ++n;
+        }
+    *bytes_host = tot;
+    if (nconv_host) *nconv_host = n;
+    return CY_OK;
+}
 extern "C" int cy_model_destroy(void* model) {
     delete (Model*)model;
     return CY_OK;

@@ -818,6 +818,9 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     }
     plan->grid = dim3(g, 1, 1);
     plan->flops = 2.0 * d.B * Hout * Wout * (double)d.cout * ntaps * d.cin;
+    plan->bytes = (double)d.B * d.Hin * d.Win * d.cin * 2.0 + (double)d.cout_pad * ntaps * d.cin * 2.0 +
+                  (double)d.B * Hout * Wout * kp.cout_store * (d.out_f32 ? 4.0 : 2.0) +
+                  (d.res ? (double)d.B * Hout * Wout * kp.cout_store * 2.0 : 0.0);
     return 0;
 #undef FAIL
 }

@@ -100,6 +100,7 @@ struct ConvPlan {
     int block_n;
     size_t smem;
     double flops;
+    double bytes;   // algorithmic HBM bytes: input slice + weights + output slice (+ residual), each touched once
 };
 
 // returns 0 on success, fills plan (encodes tensor maps).  err gets a message on failure.

@@ -168,6 +168,13 @@ class DeviceModel(object):
         keys = ('nparams', 'flops', 'launches', 'act_bytes', 'c3', 'c4', 'c5', 'nconv')
         return dict(zip(keys, [float(v) for v in a]))
 
+    def conv_bytes(self, B, Sh, Sw):
+        """(algorithmic HBM bytes of all conv launches of one forward, number of conv launches)."""
+        b = c_double(0.0)
+        n = c_int(0)
+        check(lib.cy_model_conv_bytes(self._h, c_int(B), c_int(Sh), c_int(Sw), ctypes.byref(b), ctypes.byref(n)))
+        return float(b.value), int(n.value)
+
     def profile(self, x):
         B, Sh, Sw, _ = x.shape
         cap = 512

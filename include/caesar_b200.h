@@ -125,6 +125,9 @@ int cy_model_info(void* model, int B, int Sh, int Sw, double* info_host);
  * internal strings, ms_host / flops_host the per-op numbers. Returns the number of ops in *nops_host. */
 int cy_model_profile(void* model, const void* in, int B, int Sh, int Sw, int cap, const char** names_host,
                      float* ms_host, double* flops_host, int* nops_host, uintptr_t stream);
+/* Sum over the conv launches of one forward of the algorithmic HBM bytes (input slice + weights + output slice +
+ * residual, each once) -- the denominator for the ncu dram traffic in bench.py's roofline. */
+int cy_model_conv_bytes(void* model, int B, int Sh, int Sw, double* bytes_host, int* nconv_host);
 int cy_model_destroy(void* model);
 
 /* ------------------------------------------------------------------------------------------------ detect / NMS
