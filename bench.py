@@ -182,8 +182,10 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args, n):
-    T = (args.mosaic // int(round(args.tile * args.step))) ** 2 if args.step < 1 else (args.mosaic // args.tile) ** 2
+def workload_config(args, n, T=None):
+    if T is None:
+        from caesar_yolo_b200 import ops
+        T = len(ops.generate_tiles(0, args.mosaic - 1, 0, args.mosaic - 1, args.tile, args.tile, args.step, args.step))
     return {"workload": "synthetic %dx%d f32 mosaic (FITS byte order), %dx%d tiles step %.1f (%d tiles), YOLOv8%s nc=5 "
                         "random-init, imgsz %d, full preprocessing chain, FITS payload -> merged catalog"
                         % (args.mosaic, args.mosaic, args.tile, args.tile, args.step, T, args.variant, args.imgsz),
@@ -284,7 +286,7 @@ def main():
     mpix = T * args.tile * args.tile / 1e6
     line = {"metric": "tiles/s FITS->catalog", "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world, T),
             "mpix_per_s": mpix / (ms_step * 1e-3), "sources": int(len(src)), "records": int(nrec),
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": int(args.mosaic) * int(args.mosaic) * 4,
                     "d2h_bytes_per_step": int(len(src2)) * 32 * world, "ms_per_step": e2e_ms,

@@ -241,6 +241,54 @@ __global__ void uf_flatten_kernel(int* parent, int nv, int* __restrict__ is_root
     atomicAdd(&comp_size[r], 1);
 }
 
+// Per-component statistics without walking the graph: largest member area, how many members reach it, the smallest
+// vertex id among those, and the hull.  When the largest area is unique (the common case) the reference's winner
+// ("first member in DFS preorder with strictly largest area") is that member whatever the DFS order, so giant
+// components (50 % overlap chains thousands of boxes) need no serial walk; ties fall back to the DFS replay.
+__device__ __forceinline__ int f2ord(float f) {
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ unsigned long long rec_area(const cy_det_record& r) {
+    const long long a = ((long long)r.x2 - (long long)r.x1) * ((long long)r.y2 - (long long)r.y1);
+    return (unsigned long long)(a + (1ll << 62));  // order-preserving for negative areas as well
+}
+__global__ void comp_stats_init_kernel(unsigned long long* amax, int* tie, int* bestv, int* hull, int nv) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    amax[v] = 0ull;
+    tie[v] = 0;
+    bestv[v] = 0x7fffffff;
+    hull[v] = 0x7fffffff;
+    hull[nv + v] = 0x7fffffff;
+    hull[2 * nv + v] = (int)0x80000000;
+    hull[3 * nv + v] = (int)0x80000000;
+}
+__global__ void comp_stats_kernel(const cy_det_record* __restrict__ recs, const int* __restrict__ vert_rec, int nv,
+                                  const int* __restrict__ parent, unsigned long long* amax, int* hull) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const cy_det_record r = recs[vert_rec[v]];
+    const int root = parent[v];
+    atomicMax(&amax[root], rec_area(r));
+    atomicMin(&hull[root], f2ord(r.x1));
+    atomicMin(&hull[nv + root], f2ord(r.y1));
+    atomicMax(&hull[2 * nv + root], f2ord(r.x2));
+    atomicMax(&hull[3 * nv + root], f2ord(r.y2));
+}
+__global__ void comp_tie_kernel(const cy_det_record* __restrict__ recs, const int* __restrict__ vert_rec, int nv,
+                                const int* __restrict__ parent, const unsigned long long* __restrict__ amax, int* tie,
+                                int* bestv) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int root = parent[v];
+    if (rec_area(recs[vert_rec[v]]) == amax[root]) {
+        atomicAdd(&tie[root], 1);
+        atomicMin(&bestv[root], v);
+    }
+}
+
 // One thread per component root: recursive-DFS emulation (graph.py:9-23) with per-vertex adjacency cursors.
 // Winner = first member in DFS preorder with strictly largest (x2-x1)*(y2-y1) (inference.py:838-851), hull bbox.
 __global__ void component_kernel(const cy_det_record* __restrict__ recs, const int* __restrict__ vert_rec, int nv,
@@ -248,7 +296,9 @@ __global__ void component_kernel(const cy_det_record* __restrict__ recs, const i
                                  const int* __restrict__ comp_rank, const int* __restrict__ comp_size,
                                  const int* __restrict__ stack_off, const int* __restrict__ adj_off,
                                  const int* __restrict__ adj, int* __restrict__ cursor, unsigned char* __restrict__ visited,
-                                 int* __restrict__ stack, int n_plain, cy_source* __restrict__ out) {
+                                 int* __restrict__ stack, int n_plain, const int* __restrict__ tie,
+                                 const int* __restrict__ bestv, const int* __restrict__ hull,
+                                 cy_source* __restrict__ out) {
     const int v0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (v0 >= nv || !is_root[v0]) return;
     cy_source s;
@@ -257,6 +307,16 @@ __global__ void component_kernel(const cy_det_record* __restrict__ recs, const i
         s.x1 = r0.x1; s.y1 = r0.y1; s.x2 = r0.x2; s.y2 = r0.y2; s.score = r0.score; s.cls = r0.cls;
         s.flags = (r0.flags & 1);  // edge stays as flagged, merged = False
         s.tile_id = r0.tile_id;
+        out[n_plain + comp_rank[v0]] = s;
+        return;
+    }
+    if (tie[v0] == 1) {  // unique largest member: no walk needed
+        const cy_det_record rb = recs[vert_rec[bestv[v0]]];
+        s.x1 = ord2f(hull[v0]); s.y1 = ord2f(hull[nv + v0]); s.x2 = ord2f(hull[2 * nv + v0]);
+        s.y2 = ord2f(hull[3 * nv + v0]);
+        s.score = rb.score; s.cls = rb.cls;
+        s.flags = 3;
+        s.tile_id = -1;
         out[n_plain + comp_rank[v0]] = s;
         return;
     }
@@ -363,7 +423,7 @@ int merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const 
     int *is_edge, *is_plain, *epos, *ppos, *vert_rec, *tile_vcount, *tile_vstart, *deg, *adj_off, *parent, *is_root,
         *comp_size, *comp_rank, *stack_off, *cursor, *stack, *sums, *scalars, *msize;
     unsigned char* visited;
-    size_t ints = (size_t)n * 16 + (size_t)T * 2 + nsums + 64;  // 15 n-sized arrays + adj_off[n+1]
+    size_t ints = (size_t)n * 24 + (size_t)T * 2 + nsums + 64;  // 23 n-sized arrays + adj_off[n+1]
     int* ws;
     if (cudaMallocAsync(&ws, ints * sizeof(int) + (size_t)n + 16, st) != cudaSuccess) return -3;
     int* p = ws;
@@ -382,6 +442,11 @@ int merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const 
     cursor = p; p += n;
     stack = p; p += n;
     msize = p; p += n;
+    int* tie = p; p += n;
+    int* bestv = p; p += n;
+    int* hull = p; p += 4 * (size_t)n;
+    p += ((size_t)(p - ws) & 1);  // 8-byte alignment for the 64-bit area array
+    unsigned long long* amax = (unsigned long long*)p; p += 2 * (size_t)n;
     tile_vcount = p; p += T;
     tile_vstart = p; p += T;
     sums = p; p += nsums;
@@ -426,8 +491,11 @@ int merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const 
         exclusive_scan(msize, stack_off, nv, sums, scalars + 4, st);
         init_cursor_kernel<<<vb, 256, 0, st>>>(cursor, adj_off, nv);
         cudaMemsetAsync(visited, 0, (size_t)nv, st);
+        comp_stats_init_kernel<<<vb, 256, 0, st>>>(amax, tie, bestv, hull, nv);
+        comp_stats_kernel<<<vb, 256, 0, st>>>(recs, vert_rec, nv, parent, amax, hull);
+        comp_tie_kernel<<<vb, 256, 0, st>>>(recs, vert_rec, nv, parent, amax, tie, bestv);
         component_kernel<<<vb, 256, 0, st>>>(recs, vert_rec, nv, parent, is_root, comp_rank, comp_size, stack_off,
-                                             adj_off, adj, cursor, visited, stack, n_plain, out);
+                                             adj_off, adj, cursor, visited, stack, n_plain, tie, bestv, hull, out);
         final_count_kernel<<<1, 1, 0, st>>>(scalars + 1, scalars + 3, nout);
         cudaFreeAsync(adj, st);
     } else {

@@ -207,7 +207,7 @@ class Engine(object):
                               torch.from_numpy(nb_idx if len(nb_idx) else np.zeros(1, np.int32)).to(self.device))
         off_dev, idx_dev = self._buf[key]
         out = self._get('sources', (max(n, 1) * 32,), torch.uint8)
-        self.launches += 30
+        self.launches += 33
         e = self._mark()
         res = ops.merge_global(packed, n, self.tiles_dev, self.T, off_dev, idx_dev, out=out)
         self._stage('merge_global', e)
