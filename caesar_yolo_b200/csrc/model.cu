@@ -342,6 +342,9 @@ struct PlanBuilder {
     }
 };
 
+// Plans (activation buffers + tensor maps) are cached per (batch, extent).  A large batch of YOLOv8l holds 148 MB per
+// tile, so when building a new plan runs out of device memory the other cached plans are dropped and the build is
+// retried once (the caller synchronises: plans of earlier batches are not in use once their results were consumed).
 int Model::get_plan(int B, int Sh, int Sw, Plan** out) {
     if (!finalized) return set_error(CY_ERR_STATE, "model not finalized");
     if (Sh % 32 || Sw % 32 || Sh <= 0 || Sw <= 0) return set_error(CY_ERR_INVALID, "input extent must be a multiple of 32");
@@ -351,6 +354,19 @@ int Model::get_plan(int B, int Sh, int Sw, Plan** out) {
         *out = it->second;
         return CY_OK;
     }
+    int rc = build_plan(B, Sh, Sw, out);
+    if (rc != CY_OK && !plans.empty()) {
+        cudaDeviceSynchronize();
+        for (auto& kv : plans) delete kv.second;
+        plans.clear();
+        cudaGetLastError();
+        rc = build_plan(B, Sh, Sw, out);
+    }
+    return rc;
+}
+
+int Model::build_plan(int B, int Sh, int Sw, Plan** out) {
+    const auto key = std::make_tuple(B, Sh, Sw);
     Plan* pl = new Plan();
     pl->B = B; pl->Sh = Sh; pl->Sw = Sw;
     PlanBuilder pb(*this, *pl, B);

@@ -55,6 +55,7 @@ struct Model {
     int set_tensor(const char* name, const float* data, long long numel);
     int finalize();
     int get_plan(int B, int Sh, int Sw, Plan** out);
+    int build_plan(int B, int Sh, int Sw, Plan** out);
     int forward(const void* in, int B, int Sh, int Sw, cudaStream_t st, Plan** plan_out);
     int launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaStream_t st);
     int profile(const void* in, int B, int Sh, int Sw, int cap, const char** names, float* ms, double* flops, int* nops,

@@ -74,7 +74,7 @@ class SFinder(object):
                                  score_thr=self.config['score_thr'], iou_thr=self.config['iou_thr'],
                                  thr_soft=self.config['merge_overlap_iou_thr_soft'],
                                  thr_hard=self.config['merge_overlap_iou_thr_hard'], device=dev,
-                                 batch_tiles=self.config.get('batch_tiles', 32))
+                                 batch_tiles=self.config.get('batch_tiles', 296))
         return self.engine
 
     def set_img_size_params(self):

@@ -138,6 +138,37 @@ def test_chain_synthetic_512(name, nan_frac):
         assert_close(chain[b], want, '%s tile %d' % (name, b))
 
 
+@pytest.mark.parametrize('name', ['config2', 'bkg_only', 'clip_only'])
+def test_chain_quantised_duplicates_and_odd_sizes(name):
+    """Stress for the order statistics (radix sort + rank searches): heavily duplicated values (16 and 3 distinct
+    levels: constant high digits -> skipped sort passes), negative/positive mix, a live count that is neither a multiple
+    of the sort chunk (8192) nor of the warp size, and a tiny tile."""
+    kw = FLAGSETS[name]
+    rng = np.random.default_rng(7)
+    base = synth_tile(8, T=256)
+    q16 = (np.round(base / np.abs(base).max() * 8) / 8 * 1e-3).astype(np.float32)
+    q16 += (rng.standard_normal(q16.shape) * 1e-9).astype(np.float32) * (rng.random(q16.shape) < 0.02)
+    lv3 = rng.choice(np.array([-2e-4, 1e-4, 5e-3], dtype=np.float32), size=(256, 256), p=[0.45, 0.45, 0.10])
+    lv3[:3] += (rng.standard_normal((3, 256)) * 1e-5).astype(np.float32)   # keep rows 0..2 non-constant
+    odd = synth_tile(9, T=256).copy()
+    odd[200:, :] = np.nan
+    odd[:, 251:] = np.nan                                                    # live = 200 * 251 = 50200
+    tiles = np.stack([q16, lv3, odd])
+    chain, _, _, status = run_gpu(tiles, kw)
+    for b in range(len(tiles)):
+        want = run_oracle(tiles[b], kw)
+        if want is None:
+            assert status[b] == -1
+            continue
+        assert status[b] == oracle_status(want)
+        assert_close(chain[b], want, '%s tile %d' % (name, b))
+    small = synth_tile(10, ny=40, nx=24)
+    chain, _, _, status = run_gpu(small[None], kw)
+    want = run_oracle(small, kw)
+    assert status[0] == oracle_status(want)
+    assert_close(chain[0], want, '%s small tile' % name)
+
+
 def test_nan_top_rows_rejected_like_reference():
     """Reference quirk (evaluation.py:171-176 indexes ROWS 0..2): a tile whose first rows are masked (NaN border of a
     mosaic) is rejected even though the rest of the tile is fine.  The chain output itself still matches."""
