@@ -59,6 +59,8 @@ struct Comp {
 struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per chain: Chan3 channel 2)
     double edges[257];
     double cdf[256];
+    double center[256];   // (edges[k] + edges[k+1]) / 2
+    double slope[256];    // (cdf[k+1] - cdf[k]) / (center[k+1] - center[k]), k < 255: the division np.interp does
 };
 
 struct PPParams {
@@ -215,17 +217,15 @@ __device__ int lower_index(const Chan& c, int nops, const HistEq& he, const floa
 
 // np.interp on the uniform histogram centres with an O(1) bracket (same interpolation arithmetic as histeq_interp).
 __device__ __forceinline__ double histeq_interp_fast(const HistEq& h, double v) {
-    const double c0 = (h.edges[0] + h.edges[1]) / 2.0, c255 = (h.edges[255] + h.edges[256]) / 2.0;
+    const double c0 = h.center[0], c255 = h.center[255];
     if (!(v > c0)) return h.cdf[0];
     if (v >= c255) return h.cdf[255];
     const double step = (c255 - c0) / 255.0;
     int lo = step > 0.0 ? (int)((v - c0) / step) : 0;
     lo = max(0, min(254, lo));
-    while (lo > 0 && (h.edges[lo] + h.edges[lo + 1]) / 2.0 > v) --lo;
-    while (lo < 254 && (h.edges[lo + 1] + h.edges[lo + 2]) / 2.0 <= v) ++lo;
-    const double xl = (h.edges[lo] + h.edges[lo + 1]) / 2.0, xr = (h.edges[lo + 1] + h.edges[lo + 2]) / 2.0;
-    const double slope = __ddiv_rn(__dsub_rn(h.cdf[lo + 1], h.cdf[lo]), __dsub_rn(xr, xl));
-    return __dadd_rn(__dmul_rn(slope, __dsub_rn(v, xl)), h.cdf[lo]);
+    while (lo > 0 && h.center[lo] > v) --lo;
+    while (lo < 254 && h.center[lo + 1] <= v) ++lo;
+    return __dadd_rn(__dmul_rn(h.slope[lo], __dsub_rn(v, h.center[lo])), h.cdf[lo]);
 }
 
 // Value of a NON-masked pixel through the compiled op list (callers decide masking by index / x interval).
@@ -404,25 +404,42 @@ __device__ int lower_index_coop(Shared& sh, const Chan& c, int nops, const float
 }
 
 // Pivoted moment sums of the live values f(S[i]), i in [a,b) U [a2,b2):  n, sum(v-p), sum((v-p)^2)   (fp64).
-// Values come from the compiled op list; masked elements are the zero index ranges of the channel.
+// Values come from the compiled op list; masked elements are the zero index ranges of the channel, so each input
+// range is cut into its live segments once and the element loop carries no mask test.
 __device__ void range_sums(const Chan& c, const Comp& cc, const HistEq& he, const float* S, int a, int b, int a2,
                            int b2, double p, double* red, double& s0, double& s1, double& s2) {
     double n = 0.0, u = 0.0, q = 0.0;
+    const bool simple = cc.ok && !cc.has_he;
+    const double bp = cc.b0 - p, lp = cc.l0 - p, hp = cc.h0 - p;   // clamp(a*x + b, l, h) - p
+    for (int part = 0; part < 2; ++part) {
+        int pos = part ? a2 : a;
+        const int end = part ? b2 : b;
+        int zi = 0;
+        while (pos < end) {
+            // next live segment [pos, seg_end)
+            while (zi < c.nz && c.z1[zi] <= pos) ++zi;
+            if (zi < c.nz && c.z0[zi] <= pos) {
+                pos = c.z1[zi];
+                continue;
+            }
+            const int seg_end = (zi < c.nz && c.z0[zi] < end) ? c.z0[zi] : end;
+            if (threadIdx.x == 0) n += (double)(seg_end - pos);
+            if (simple) {
 #pragma unroll 4
-    for (int i = a + threadIdx.x; i < b; i += kPPThreads) {
-        if (!in_zero_idx(c, i)) {
-            const double d = eval_fast(cc, c, he, (double)S[i]) - p;
-            n += 1.0;
-            u += d;
-            q += d * d;
-        }
-    }
-    for (int i = a2 + threadIdx.x; i < b2; i += kPPThreads) {
-        if (!in_zero_idx(c, i)) {
-            const double d = eval_fast(cc, c, he, (double)S[i]) - p;
-            n += 1.0;
-            u += d;
-            q += d * d;
+                for (int i = pos + threadIdx.x; i < seg_end; i += kPPThreads) {
+                    const double d = fmin(fmax(fma(cc.a0, (double)S[i], bp), lp), hp);
+                    u += d;
+                    q = fma(d, d, q);
+                }
+            } else {
+#pragma unroll 2
+                for (int i = pos + threadIdx.x; i < seg_end; i += kPPThreads) {
+                    const double d = eval_fast(cc, c, he, (double)S[i]) - p;
+                    u += d;
+                    q = fma(d, d, q);
+                }
+            }
+            pos = seg_end;
         }
     }
     block_sum3(n, u, q, red);
@@ -660,6 +677,13 @@ __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const
         const double tot = (double)run;
         for (int i = 0; i < 256; ++i) sh.he.cdf[i] = sh.he.cdf[i] / tot;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.he.center[i] = (sh.he.edges[i] + sh.he.edges[i + 1]) / 2.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += kPPThreads)
+        sh.he.slope[i] = i < 255 ? __ddiv_rn(__dsub_rn(sh.he.cdf[i + 1], sh.he.cdf[i]),
+                                            __dsub_rn(sh.he.center[i + 1], sh.he.center[i]))
+                                 : 0.0;
     __syncthreads();
     push_op(sh, ci, S, n, OP_HISTEQ, 0.0, 0.0, 0.0, 0.0);
 }
