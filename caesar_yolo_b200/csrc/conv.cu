@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     mbar_wait(&a_empty[s], ph ^ 1);
                     if (elect_one()) {
                         uint8_t* dst = a_ring + (size_t)s * p.a_stage_bytes;
-                        if (rank == 0) mbar_arrive_expect_tx(&a_full[s], p.a_box_bytes * HALVES * kCtasPerUnit);
+                        if (rank == 0) mbar_arrive_expect_tx(&a_full[s], L.bytes * HALVES * kCtasPerUnit);
                         if (PAIR) {
                             const uint32_t bar = mapa_u32(smem_u32(&a_full[s]), 0);
                             tma_load_4d_pair(dst, &p.tmA[L.map], bar, ck * p.kc, hc0.w0 + L.dw, hc0.h0 + L.dh, hc0.n0);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         if (elect_one()) {
                             const uint64_t db = make_desc_sbo(b_ring_addr + (uint32_t)sb * p.b_stage_bytes, row_bytes,
                                                               8u * row_bytes);
-                            const uint64_t da0 = make_desc_sbo(a_addr + a_off, row_bytes, p.sbo_a);
+                            const uint64_t da0 = make_desc_sbo(a_addr + a_off, row_bytes, L.sbo);
 #pragma unroll
                             for (int h = 0; h < HALVES; ++h) {
                                 const uint64_t da = da0 + (uint64_t)((h * p.a_half_stride) >> 4);
@@ -595,18 +595,23 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
         const double util = (double)Wout * Hout / ((double)((Wout + 7) / 8 * 8) * ((Hout + 15) / 16 * 16));
         if (util >= 0.8) mode = 2;
     }
-    const int max_mode = env_int("CY_CONV_MODE", 2);
-    if (mode > max_mode) mode = max_mode;
+    if (d.ksize == 3 && d.stride == 2 && kc == 64) {
+        const double util = (double)Wout * Hout / ((double)((Wout + 7) / 8 * 8) * ((Hout + 15) / 16 * 16));
+        if (util >= 0.8) mode = 3;
+    }
+    const int max_mode = env_int("CY_CONV_MODE", 3);
+    if (mode > max_mode) mode = (mode == 3) ? 0 : max_mode;
     kp.mode = mode;
-    int box_w, box_h, box_n;          // TMA box in pixels
+    int box_w, box_h, box_n;          // TMA box in pixels (mode 3: the largest of the four parity boxes)
     if (mode == 0) {
         choose_box(d.B, Hout, Wout, &kp.bw, &kp.bh, &kp.bn);
         box_w = kp.bw; box_h = kp.bh; box_n = kp.bn;
-        kp.sbo_a = 8u * row_bytes;
+    } else if (mode == 3) {
+        kp.bw = 8; kp.bh = 16; kp.bn = 1;
+        box_w = 9; box_h = 17; box_n = 1;
     } else {
         kp.bw = 8; kp.bh = 16; kp.bn = 1;
         box_w = mode == 2 ? 10 : 8; box_h = 18; box_n = 1;
-        kp.sbo_a = (uint32_t)box_w * row_bytes;
     }
     kp.tiles_w = (Wout + kp.bw - 1) / kp.bw;
     kp.tiles_h = (Hout + kp.bh - 1) / kp.bh;
@@ -660,7 +665,39 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     kp.tmem_cols = pow2;
 
     // ---- A-load / tap lists
-    if (mode == 0) {
+    const uint32_t box_bytes_dflt = (uint32_t)(box_w * box_h * box_n * row_bytes);
+    for (int t = 0; t < 9; ++t) {
+        kp.aload[t].bytes = box_bytes_dflt;
+        kp.aload[t].sbo = mode == 0 ? 8u * row_bytes : (uint32_t)box_w * row_bytes;
+    }
+    if (mode == 3) {
+        // parity class (ph, pw): ph = 1 -> odd input rows, taps kh = 0 (row oh-1) and kh = 2 (row oh): box rows
+        // [h0-1, h0+16); ph = 0 -> kh = 1 (row oh): box rows [h0, h0+16).  Same for columns.
+        kp.n_aloads = 4;
+        int t = 0;
+        for (int ph = 1; ph >= 0; --ph)
+            for (int pw = 1; pw >= 0; --pw) {
+                const int al = (1 - ph) * 2 + (1 - pw);
+                const int bwid = pw ? 9 : 8, bhgt = ph ? 17 : 16;
+                kp.aload[al].map = (signed char)(ph * 2 + pw);
+                kp.aload[al].dw = (signed char)(pw ? -1 : 0);
+                kp.aload[al].dh = (signed char)(ph ? -1 : 0);
+                kp.aload[al].tap0 = (signed char)t;
+                kp.aload[al].bytes = (uint32_t)(bwid * bhgt * row_bytes);
+                kp.aload[al].sbo = (uint32_t)(bwid * row_bytes);
+                int nt = 0;
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int kw = 0; kw < 3; ++kw) {
+                        if ((kh != 1) != (ph == 1) || (kw != 1) != (pw == 1)) continue;
+                        const int di = ph ? (kh == 0 ? 0 : 1) : 0, dj = pw ? (kw == 0 ? 0 : 1) : 0;
+                        kp.tap[t].wtap = kh * 3 + kw;
+                        kp.tap[t].a_off = (uint32_t)((di * bwid + dj) * row_bytes);
+                        ++t;
+                        ++nt;
+                    }
+                kp.aload[al].ntaps = (signed char)nt;
+            }
+    } else if (mode == 0) {
         kp.n_aloads = ntaps;
         for (int t = 0; t < ntaps; ++t) {
             kp.aload[t].ntaps = 1;
@@ -713,8 +750,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
                 kp.tap[kh * 3 + kw].a_off = (uint32_t)((kh * box_w + kw) * row_bytes);
             }
     }
-    kp.a_box_bytes = (uint32_t)(box_w * box_h * box_n * row_bytes);
-    kp.a_half_stride = (kp.a_box_bytes + 1023u) & ~1023u;
+    kp.a_half_stride = (box_bytes_dflt + 1023u) & ~1023u;
     kp.a_stage_bytes = kp.a_half_stride * halves;
     kp.b_tile_bytes = (uint32_t)((bn_ / (pair ? 2 : 1)) * row_bytes);   // per CTA
     kp.b_stage_bytes = (kp.b_tile_bytes + 1023u) & ~1023u;
@@ -739,7 +775,9 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
                                             (cuuint64_t)d.B};
                 const cuuint64_t str[3] = {pixb * 2, pixb * d.Win * 2, pixb * d.Win * d.Hin};
                 const char* b2 = base + ((size_t)ph * d.Win + pw) * pixb;
-                CUresult r = enc(&kp.tmA[ph * 2 + pw], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)b2, dims, str, box,
+                const cuuint32_t pbox[4] = {(cuuint32_t)kc, (cuuint32_t)(pw ? 9 : 8), (cuuint32_t)(ph ? 17 : 16), 1u};
+                CUresult r = enc(&kp.tmA[ph * 2 + pw], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)b2, dims, str,
+                                 mode == 3 ? pbox : box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) FAIL("cuTensorMapEncodeTiled(A s2) failed: %d", (int)r);
@@ -799,7 +837,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
         if (a_stages > 8) a_stages = 8;
         b_stages = a_stages;
     } else {
-        a_stages = 2;
+        a_stages = mode == 3 ? 3 : 2;
         b_stages = (int)((budget - (size_t)a_stages * kp.a_stage_bytes) / kp.b_stage_bytes);
         if (b_stages > 12) b_stages = 12;
     }

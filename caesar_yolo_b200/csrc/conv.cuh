@@ -20,6 +20,9 @@
 //      MODE 1: 3x3 stride 1: three A loads per channel chunk (one per horizontal tap), box 8 x 18 pixels; the three
 //              vertical taps are the same box read at +0/+1/+2 image rows (8 px * 128 B = one swizzle atom, so the
 //              shift keeps the 128B-swizzle phase);
+//      MODE 3: 3x3 stride 2: four A loads per channel chunk, one per input parity class (odd/even rows x cols): the
+//              9 taps fall into classes of 4 + 2 + 2 + 1 taps that read the same (17|16) x (9|8) pixel box of their
+//              parity map at +0/+1 row / column offsets -- A traffic drops from 9 to 4.4 boxes per chunk.
 //      MODE 2: 3x3 stride 1: ONE A load per channel chunk, box 10 x 18 pixels (halo on all sides); all nine taps read
 //              it at (kh*10 + kw) * 128 B (the swizzle XOR is a function of the absolute shared-memory address, so a
 //              128 B shift is legal; stride between 8-row groups = 10 px * 128 B).
@@ -34,6 +37,8 @@ namespace cy {
 
 struct ConvALoad {
     signed char map, dw, dh, ntaps, tap0;
+    uint32_t bytes;    // bytes one half-tile box of this load delivers
+    uint32_t sbo;      // byte stride between 8-row groups of the A operand inside this box
 };
 struct ConvTap {
     int wtap;          // tap index in the weight K layout (K = wtap*cin + c)
@@ -62,11 +67,9 @@ struct ConvKParams {
     int cchunks, kc, cin;          // K loop: cchunks chunks of kc channels
     int n_aloads;                  // A loads per channel chunk
     int a_stages, b_stages;
-    uint32_t a_box_bytes;          // bytes one half-tile A load delivers
     uint32_t a_half_stride;        // distance between the halves inside an A stage (multiple of 1024)
     uint32_t a_stage_bytes;
     uint32_t b_tile_bytes, b_stage_bytes;
-    uint32_t sbo_a;                // byte stride between 8-row groups of the A operand
     int cout_store;                // number of valid output columns (multiple of 8)
     int o_gw;                      // output columns per epilogue group (one TMA store box)
     uint32_t o_row_bytes;          // o_gw * element size (32 / 64 / 128)

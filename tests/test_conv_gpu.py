@@ -110,3 +110,20 @@ def test_conv_cta_pairs_persistent(monkeypatch):
     _run_case(B=24, H=80, W=80, cin=128, cout=128, k=3, s=1, act=True, res=True, out_f32=False, seed=31)
     _run_case(B=32, H=40, W=40, cin=256, cout=512, k=1, s=1, act=True, res=False, out_f32=False, seed=32)
     _run_case(B=16, H=160, W=160, cin=64, cout=64, k=3, s=1, act=True, res=False, out_f32=False, seed=33)
+
+
+S2_SHAPES = [
+    dict(B=2, H=64, W=32, cin=64, cout=128, k=3, s=2, act=True, res=False, out_f32=False),
+    dict(B=3, H=80, W=80, cin=128, cout=256, k=3, s=2, act=True, res=False, out_f32=False),
+    dict(B=1, H=96, W=48, cin=192, cout=64, k=3, s=2, act=True, res=False, out_f32=False, in_extra=64, out_extra=64),
+]
+
+
+@pytest.mark.parametrize("pair", [0, 2])
+@pytest.mark.parametrize("halves", [1, 2])
+@pytest.mark.parametrize("shape", range(len(S2_SHAPES)))
+def test_conv_stride2_parity_patch_reuse(monkeypatch, pair, halves, shape):
+    """MODE 3: stride-2 3x3 convs read four parity-class boxes per channel chunk instead of nine tap boxes."""
+    monkeypatch.setenv("CY_CONV_PAIR", str(pair))
+    monkeypatch.setenv("CY_CONV_HALVES", str(halves))
+    _run_case(seed=shape + 41, **S2_SHAPES[shape])
