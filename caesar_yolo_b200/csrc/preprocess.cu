@@ -27,8 +27,11 @@
 
 namespace cy {
 
-static constexpr int kPPThreads = 1024;
+static constexpr int kPPThreads = 512;    // two CTAs (tiles) per SM: the kernels are latency-bound, the second CTA
+                                          // fills the first one's barrier and dependent-load stalls
 static constexpr int kPPWarps = kPPThreads / 32;
+static constexpr int kSortThreads = 1024;  // the sort is instruction-bound: one full-width CTA per SM
+static constexpr int kSortWarps = kSortThreads / 32;
 static constexpr int kMaxOps = 12;
 static constexpr int kMaxZero = 8;
 
@@ -110,7 +113,8 @@ __device__ void block_sum3(double& a, double& b, double& c, double* red) {
     }
     __syncthreads();
     if (w == 0) {
-        double x = red[lane], y = red[32 + lane], z = red[64 + lane];
+        double x = lane < kPPWarps ? red[lane] : 0.0, y = lane < kPPWarps ? red[32 + lane] : 0.0,
+               z = lane < kPPWarps ? red[64 + lane] : 0.0;
         x = warp_sum(x);
         y = warp_sum(y);
         z = warp_sum(z);
@@ -139,7 +143,7 @@ __device__ void block_minmax(double& mn, double& mx, double* red) {
     }
     __syncthreads();
     if (w == 0) {
-        double x = red[lane], y = red[32 + lane];
+        double x = lane < kPPWarps ? red[lane] : INFINITY, y = lane < kPPWarps ? red[32 + lane] : -INFINITY;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
@@ -543,69 +547,120 @@ __device__ void copy_chan(Shared& sh, int dst, int src) {
 __device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const float* S, int n, double contrast) {
     const Chan& c = sh.ch[ci];
     const int t = threadIdx.x;
+    constexpr int kZS = 1024;                     // sample slots (>= the 1000 samples of ZScaleInterval)
+    constexpr int kZE = kZS / kPPThreads;         // slots per thread: e = t + q * kPPThreads
     const int stride = (int)fmax(1.0, (double)N / 1000.0);
     int npix = (N + stride - 1) / stride;
     if (npix > 1000) npix = 1000;
     __syncthreads();
-    sh.zs[t] = (t < npix) ? eval_ops<true>(c, c.nops, sh.he, (double)tile[(long long)t * stride]) : INFINITY;
+#pragma unroll
+    for (int q = 0; q < kZE; ++q) {
+        const int e = t + q * kPPThreads;
+        sh.zs[e] = (e < npix) ? eval_ops<true>(c, c.nops, sh.he, (double)tile[(long long)e * stride]) : INFINITY;
+    }
     __syncthreads();
-    // bitonic sort ascending, 1024 elements, one compare-exchange per thread pair
-    for (int k = 2; k <= 1024; k <<= 1) {
+    // bitonic sort ascending, 1024 elements, one compare-exchange per element pair
+    for (int k = 2; k <= kZS; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const int p = t ^ j;
-            if (p > t) {
-                const double x = sh.zs[t], y = sh.zs[p];
-                const bool asc = ((t & k) == 0);
-                if (asc ? (x > y) : (x < y)) {
-                    sh.zs[t] = y;
-                    sh.zs[p] = x;
+#pragma unroll
+            for (int q = 0; q < kZE; ++q) {
+                const int e = t + q * kPPThreads;
+                const int p = e ^ j;
+                if (p > e) {
+                    const double x = sh.zs[e], y = sh.zs[p];
+                    const bool asc = ((e & k) == 0);
+                    if (asc ? (x > y) : (x < y)) {
+                        sh.zs[e] = y;
+                        sh.zs[p] = x;
+                    }
                 }
             }
             __syncthreads();
         }
     }
-    const double y = t < npix ? sh.zs[t] : 0.0;
-    const double x = (double)t;
+    double y[kZE], x[kZE], flat[kZE];
+#pragma unroll
+    for (int q = 0; q < kZE; ++q) {
+        const int e = t + q * kPPThreads;
+        y[q] = e < npix ? sh.zs[e] : 0.0;
+        x[q] = (double)e;
+        sh.zbad[e] = 0;
+    }
     double vmin = sh.zs[0], vmax = sh.zs[npix - 1];
     const int minpix = max(5, (int)(npix * 0.5));
     int ngood = npix, last = npix + 1;
     const int ngrow = max(1, (int)(npix * 0.01));
-    sh.zbad[t] = 0;
     double slope = 0.0, icpt = 0.0;
     bool fitted = false;
     __syncthreads();
     for (int it = 0; it < 5; ++it) {
         if (ngood >= last || ngood < minpix) break;
-        const bool good = (t < npix) && !sh.zbad[t];
+        bool good[kZE];
         // weighted (0/1) least squares line, centred for stability (== np.polyfit deg 1 up to rounding)
-        double sw = good ? 1.0 : 0.0, sx = good ? x : 0.0, sy = good ? y : 0.0;
+        double sw = 0.0, sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q) {
+            const int e = t + q * kPPThreads;
+            good[q] = (e < npix) && !sh.zbad[e];
+            if (good[q]) {
+                sw += 1.0;
+                sx += x[q];
+                sy += y[q];
+            }
+        }
         block_sum3(sw, sx, sy, sh.red);
         const double xm = sx / sw, ym = sy / sw;
-        double sxx = good ? (x - xm) * (x - xm) : 0.0, sxy = good ? (x - xm) * (y - ym) : 0.0, zz = 0.0;
+        double sxx = 0.0, sxy = 0.0, zz = 0.0;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q)
+            if (good[q]) {
+                sxx += (x[q] - xm) * (x[q] - xm);
+                sxy += (x[q] - xm) * (y[q] - ym);
+            }
         block_sum3(sxx, sxy, zz, sh.red);
         slope = sxy / sxx;
         icpt = ym - slope * xm;
         fitted = true;
-        const double flat = y - (slope * x + icpt);
-        double sf = good ? flat : 0.0, z1 = 0.0, z2 = 0.0;
+        double sf = 0.0, z1 = 0.0, z2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q) {
+            flat[q] = y[q] - (slope * x[q] + icpt);
+            if (good[q]) sf += flat[q];
+        }
         block_sum3(sf, z1, z2, sh.red);
         const double fm = sf / sw;
-        double sq = good ? (flat - fm) * (flat - fm) : 0.0;
+        double sq = 0.0;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q)
+            if (good[q]) sq += (flat[q] - fm) * (flat[q] - fm);
         z1 = z2 = 0.0;
         block_sum3(sq, z1, z2, sh.red);
         const double thr = 2.5 * sqrt(sq / sw);
-        if (t < npix && (flat < -thr || flat > thr)) sh.zbad[t] = 1;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q) {
+            const int e = t + q * kPPThreads;
+            if (e < npix && (flat[q] < -thr || flat[q] > thr)) sh.zbad[e] = 1;
+        }
         __syncthreads();
         // np.convolve(badpix, ones(ngrow), 'same') on bools: out[i] = OR bad[i - ngrow/2 .. i + (ngrow-1)/2]
-        unsigned char nb = 0;
-        if (t < npix) {
-            const int l0 = max(0, t - ngrow / 2), l1 = min(npix - 1, t + (ngrow - 1) / 2);
-            for (int q = l0; q <= l1; ++q) nb |= sh.zbad[q];
+        double g = 0.0;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q) {
+            const int e = t + q * kPPThreads;
+            unsigned char nb = 0;
+            if (e < npix) {
+                const int l0 = max(0, e - ngrow / 2), l1 = min(npix - 1, e + (ngrow - 1) / 2);
+                for (int r = l0; r <= l1; ++r) nb |= sh.zbad[r];
+            }
+            sh.zbad2[e] = nb;
+            if (e < npix && !nb) g += 1.0;
         }
-        sh.zbad2[t] = nb;
         __syncthreads();
-        sh.zbad[t] = sh.zbad2[t];
-        double g = (t < npix && !nb) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < kZE; ++q) {
+            const int e = t + q * kPPThreads;
+            sh.zbad[e] = sh.zbad2[e];
+        }
         z1 = z2 = 0.0;
         block_sum3(g, z1, z2, sh.red);
         last = ngood;
@@ -708,15 +763,15 @@ __device__ __forceinline__ float load_pixel(const PPParams& p, int b, int idx) {
     return isfinite(f) ? f : 0.0f;  // utils.py:219,394
 }
 
-// LSD radix sort (4 x 8 bit) of `n` keys in global memory with one CTA.  Every pass streams the keys in chunks of 8192
+// LSD radix sort (4 x 8 bit) of `n` keys in global memory with one CTA.  Every pass streams the keys in chunks of 8 keys per thread
 // through shared memory: warp-striped loads, stable ranks inside the chunk from __match_any_sync + per-warp digit
 // counters, a counting sort of the chunk in shared memory, then a write-out in which consecutive threads carry
 // consecutive keys of one digit to consecutive addresses (full-sector stores; the direct per-key scatter this replaces
 // wrote 4 bytes per 32-byte sector).  The histogram of the NEXT digit is built during the write-out, so a pass reads
 // and writes every key once; passes whose digit is the same for all keys are skipped.
-static constexpr int kSortChunk = 8192;
+static constexpr int kSortChunk = 8 * kSortThreads;   // 8 keys per thread, warp-striped
 struct SortSmem {
-    int hist[256][kPPWarps + 1];  // [digit][warp] counters -> exclusive warp bases inside the chunk (+1: bank skew)
+    int hist[256][kSortWarps + 1];  // [digit][warp] counters -> exclusive warp bases inside the chunk (+1: bank skew)
     uint32_t sorted[kSortChunk];  // the chunk in digit order
     int dtot[256], dbase[256], gcur[256];
     int nh[2][256];               // digit histograms of the whole array (current / next pass)
@@ -763,18 +818,18 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     uint32_t* src = a;
     uint32_t* dst = b;
-    for (int i = t; i < 512; i += kPPThreads) (&sm.nh[0][0])[i] = 0;
+    for (int i = t; i < 512; i += kSortThreads) (&sm.nh[0][0])[i] = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += 4 * kPPThreads) {
+    for (int i0 = 0; i0 < n; i0 += 4 * kSortThreads) {
         uint32_t k[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int i = i0 + q * kPPThreads + t;
+            const int i = i0 + q * kSortThreads + t;
             k[q] = i < n ? src[i] : 0xffffffffu;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (i0 + q * kPPThreads + t < n) atomicAdd(&sm.nh[0][k[q] & 255u], 1);
+            if (i0 + q * kSortThreads + t < n) atomicAdd(&sm.nh[0][k[q] & 255u], 1);
     }
     __syncthreads();
     int cur = 0;
@@ -788,19 +843,19 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
             one = __any_sync(0xffffffffu, one);
             if (lane == 0) sm.flag = one;
         }
-        for (int i = t; i < 256; i += kPPThreads) nh_next[i] = 0;
+        for (int i = t; i < 256; i += kSortThreads) nh_next[i] = 0;
         __syncthreads();
         const bool trivial = sm.flag != 0;
         const bool more = shift < 24;
         if (trivial) {  // nothing moves; only the next digit's histogram is needed
             if (more)
-                for (int i = t; i < n; i += kPPThreads) atomicAdd(&nh_next[(src[i] >> (shift + 8)) & 255u], 1);
+                for (int i = t; i < n; i += kSortThreads) atomicAdd(&nh_next[(src[i] >> (shift + 8)) & 255u], 1);
             __syncthreads();
             continue;
         }
         for (int c0 = 0; c0 < n; c0 += kSortChunk) {
             const int m = min(kSortChunk, n - c0);
-            for (int i = t; i < 256 * (kPPWarps + 1); i += kPPThreads) (&sm.hist[0][0])[i] = 0;
+            for (int i = t; i < 256 * (kSortWarps + 1); i += kSortThreads) (&sm.hist[0][0])[i] = 0;
             uint32_t key[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // independent loads first
@@ -827,18 +882,18 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 __syncwarp();
             }
             __syncthreads();
-            // per digit: exclusive scan over the 32 warps (one warp per digit, 8 digits per warp)
+            // per digit: exclusive scan over the warps' counters (one warp per digit, 256 / kSortWarps digits per warp)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int d = w * 8 + q;
-                const int v = sm.hist[d][lane];
+            for (int q = 0; q < 256 / kSortWarps; ++q) {
+                const int d = w * (256 / kSortWarps) + q;
+                const int v = lane < kSortWarps ? sm.hist[d][lane] : 0;
                 int inc = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const int y = __shfl_up_sync(0xffffffffu, inc, o);
                     if (lane >= o) inc += y;
                 }
-                sm.hist[d][lane] = inc - v;
+                if (lane < kSortWarps) sm.hist[d][lane] = inc - v;
                 if (lane == 31) sm.dtot[d] = inc;
             }
             __syncthreads();
@@ -852,8 +907,8 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < kSortChunk / kPPThreads; ++q) {
-                const int j = q * kPPThreads + t;
+            for (int q = 0; q < kSortChunk / kSortThreads; ++q) {
+                const int j = q * kSortThreads + t;
                 if (j < m) {
                     const uint32_t k = sm.sorted[j];
                     const uint32_t d = (k >> shift) & 255u;
@@ -872,7 +927,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
     return src;
 }
 
-__global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_constant__ PPParams p) {
+__global__ void __launch_bounds__(kSortThreads) pp_sort_kernel(const __grid_constant__ PPParams p) {
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
     SortSmem& sm = *reinterpret_cast<SortSmem*>(sort_smem_raw);
     __shared__ int s_n, s_nb;
@@ -891,16 +946,16 @@ __global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_consta
     const int xc = p.Tx / 2, yc = p.Ty / 2;
     const int dy = (int)(p.Ty * p.cfg.bkg_box_mask_fract / 2.0), dx = (int)(p.Tx * p.cfg.bkg_box_mask_fract / 2.0);
     const int lane = threadIdx.x & 31;
-    for (int i00 = 0; i00 < N; i00 += 4 * kPPThreads) {
+    for (int i00 = 0; i00 < N; i00 += 4 * kSortThreads) {
         float fq[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {  // four independent loads in flight per thread
-            const int i = i00 + q * kPPThreads + threadIdx.x;
+            const int i = i00 + q * kSortThreads + threadIdx.x;
             fq[q] = i < N ? load_pixel(p, b, i) : 0.f;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int i = i00 + q * kPPThreads + threadIdx.x;
+            const int i = i00 + q * kSortThreads + threadIdx.x;
             const float f = fq[q];
             if (i < N) tile[i] = f;
             const bool live = (i < N) && (f != 0.0f);
@@ -925,12 +980,12 @@ __global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_consta
     const int n = s_n, nb = s_nb;
     {
         const uint32_t* r = block_radix_sort(A, Bk, n, sm);
-        for (int i = threadIdx.x; i < n; i += kPPThreads) A[i] = __float_as_uint(key2f(r[i]));
+        for (int i = threadIdx.x; i < n; i += kSortThreads) A[i] = __float_as_uint(key2f(r[i]));
     }
     if (C) {
         __syncthreads();
         const uint32_t* r = block_radix_sort(C, Bk, nb, sm);
-        for (int i = threadIdx.x; i < nb; i += kPPThreads) C[i] = __float_as_uint(key2f(r[i]));
+        for (int i = threadIdx.x; i < nb; i += kSortThreads) C[i] = __float_as_uint(key2f(r[i]));
     }
     if (threadIdx.x == 0) {
         p.nlive[b] = n;
@@ -942,7 +997,7 @@ __global__ void __launch_bounds__(kPPThreads) pp_sort_kernel(const __grid_consta
 
 __device__ __forceinline__ bool chan_selected(int chid, int c) { return chid == -1 || chid == c; }
 
-__global__ void __launch_bounds__(kPPThreads) pp_chain_kernel(const __grid_constant__ PPParams p) {
+__global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_constant__ PPParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
     const int b = blockIdx.x;
@@ -1235,7 +1290,7 @@ extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
         attr_done = true;
     }
-    pp_sort_kernel<<<B, kPPThreads, sizeof(SortSmem), st>>>(p);
+    pp_sort_kernel<<<B, kSortThreads, sizeof(SortSmem), st>>>(p);
     pp_chain_kernel<<<B, kPPThreads, sizeof(Shared), st>>>(p);
     CY_CUDA_CHECK(cudaGetLastError());
     if (model_in) return cy_letterbox_resize(chain_out, B, Ty, Tx, imgsz, model_in, model_in_f32, stream);
