@@ -813,8 +813,13 @@ __device__ __forceinline__ void scan256_warp0(const int* a, int* out) {
     }
 }
 
+__device__ long long* g_sort_dbg = nullptr;   // optional phase timing (clock64 sums of thread 0 of block 0), tools only
+#define SORT_T(k) do { if (dbg) { const long long _c = clock64(); dbg[k] += _c - tprev; tprev = _c; } } while (0)
+
 // Returns the buffer (a or b) that holds the sorted keys.
 __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem& sm) {
+    long long* dbg = (g_sort_dbg && blockIdx.x == 0 && threadIdx.x == 0) ? g_sort_dbg : nullptr;
+    long long tprev = dbg ? clock64() : 0;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     uint32_t* src = a;
     uint32_t* dst = b;
@@ -832,6 +837,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
             if (i0 + q * kSortThreads + t < n) atomicAdd(&sm.nh[0][k[q] & 255u], 1);
     }
     __syncthreads();
+    SORT_T(0);
     int cur = 0;
     for (int shift = 0; shift < 32; shift += 8, cur ^= 1) {
         int* nh = sm.nh[cur];
@@ -863,6 +869,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 key[j] = li < m ? src[c0 + li] : 0u;
             }
             __syncthreads();
+            SORT_T(1);
             int rnk[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -882,6 +889,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 __syncwarp();
             }
             __syncthreads();
+            SORT_T(2);
             // per digit: exclusive scan over the warps' counters (one warp per digit, 256 / kSortWarps digits per warp)
 #pragma unroll
             for (int q = 0; q < 256 / kSortWarps; ++q) {
@@ -897,8 +905,10 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 if (lane == 31) sm.dtot[d] = inc;
             }
             __syncthreads();
+            SORT_T(3);
             if (t < 32) scan256_warp0(sm.dtot, sm.dbase);
             __syncthreads();
+            SORT_T(4);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (rnk[j] >= 0) {
@@ -906,6 +916,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                     sm.sorted[sm.dbase[d] + sm.hist[d][w] + rnk[j]] = key[j];
                 }
             __syncthreads();
+            SORT_T(5);
 #pragma unroll
             for (int q = 0; q < kSortChunk / kSortThreads; ++q) {
                 const int j = q * kSortThreads + t;
@@ -917,6 +928,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 }
             }
             __syncthreads();
+            SORT_T(6);
             if (t < 256) sm.gcur[t] += sm.dtot[t];
         }
         __syncthreads();
@@ -1237,6 +1249,12 @@ __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
 // ------------------------------------------------------------------------------------------ C ABI
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int cy_sort_set_debug(void* dev_buf) {
+    long long* p = (long long*)dev_buf;
+    CY_CUDA_CHECK(cudaMemcpyToSymbol(cy::g_sort_dbg, &p, sizeof(p)));
+    return CY_OK;
+}
 
 extern "C" size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg, int B, int Ty, int Tx) {
     const size_t N = (size_t)Ty * Tx;

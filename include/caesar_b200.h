@@ -101,6 +101,8 @@ int cy_conv_block_n(int cout);
 /* Diagnostics (tools/conv_probe.py): per-CTA clock64 timeline buffer for the conv kernel (NULL disables); the plan the
  * kernel would use for a shape: info8 = {mode, halves, units, block_n, a_stages, b_stages, acc_bufs, grid}. */
 int cy_conv_set_debug(void* dev_buf, int units_per_cta);
+/* Diagnostics: phase cycle sums (8 x int64) of block 0 of the tile sort kernel; NULL disables. */
+int cy_sort_set_debug(void* dev_buf);
 int cy_conv_plan_info(int B, int Hin, int Win, int cin, int cout, int ksize, int stride, int* info8);
 int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ctot, int in_coff, int cin, const void* w,
                    const float* bias, int cout, int cout_pad, int ksize, int stride, void* out, int out_ctot,
