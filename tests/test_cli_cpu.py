@@ -1,0 +1,67 @@
+"""scripts/run.py keeps the reference's option surface (scripts/run.py:58-155 of the reference), its argument
+validation (:158-190), the fixed stage order (:272-293) and the chan3/nchannels check (:253-256).  No GPU needed."""
+import importlib.util
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run_py():
+    spec = importlib.util.spec_from_file_location("cy_run_cli", os.path.join(ROOT, "scripts", "run.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+REFERENCE_DEFAULTS = dict(imgsize=640, norm_min=0., norm_max=1., sigma_bkg=3, bkg_box_mask_fract=0.7, bkg_chid=-1,
+                          sigma_clip=1, sigma_clip_low=10, sigma_clip_up=10, clip_chid=-1,
+                          zscale_contrasts='0.25,0.25,0.25', sigma_clip_baseline=0, nchannels=1, scoreThr=0.7,
+                          iouThr=0.5, merge_overlap_iou_thr_soft=0.3, merge_overlap_iou_thr_hard=0.8, xmin=-1, xmax=-1,
+                          ymin=-1, ymax=-1, tile_xsize=512, tile_ysize=512, tile_xstep=1.0, tile_ystep=1.0,
+                          max_ntasks_per_worker=100, maxnimgs=-1)
+
+
+def test_defaults_match_reference():
+    run = _run_py()
+    a = run.parse_args(['--weights', 'w.pt'])
+    for k, v in REFERENCE_DEFAULTS.items():
+        assert getattr(a, k) == v, k
+    for flag in ('preprocessing', 'normalize_minmax', 'subtract_bkg', 'use_box_mask_in_bkg', 'clip_shift_data',
+                 'clip_data', 'zscale_stretch', 'chan3_preproc', 'split_img_in_tiles', 'multigpu', 'draw_plots',
+                 'save_plots', 'save_tile_catalog', 'save_tile_region', 'save_tile_img'):
+        assert getattr(a, flag) is False, flag
+
+
+def test_stage_order_and_parameters():
+    run = _run_py()
+    a = run.parse_args(['--weights', 'w.pt', '--preprocessing', '--normalize_minmax', '--norm_max=255',
+                        '--chan3_preproc', '--zscale_stretch', '--clip_data', '--clip_shift_data', '--subtract_bkg',
+                        '--nchannels=3', '--sigma_clip_low=4', '--zscale_contrasts=0.3,0.2,0.1'])
+    st = run.build_stages(a)
+    assert [type(s).__name__ for s in st] == ['BkgSubtractor', 'SigmaClipShifter', 'SigmaClipper', 'ChanResizer',
+                                              'ZScaleTransformer', 'Chan3Trasformer', 'MinMaxNormalizer']
+    from caesar_yolo_b200.preprocessing import DataPreprocessor
+    cfg = DataPreprocessor(st).pp_config
+    assert cfg.subtract_bkg == 1 and cfg.clip_shift_data == 1 and cfg.clip_data == 1 and cfg.zscale_stretch == 1
+    assert cfg.chan3_preproc == 1 and cfg.normalize_minmax == 1 and cfg.nchannels == 3
+    assert cfg.sigma_clip_low == 4.0 and cfg.norm_max == 255.0
+    assert [cfg.zscale_contrasts[i] for i in range(3)] == [0.3, 0.2, 0.1]
+
+
+def test_validation_errors_return_1(tmp_path):
+    run = _run_py()
+    w = tmp_path / "w.pt"
+    w.write_bytes(b"x")
+    img = tmp_path / "a.fits"
+    img.write_bytes(b"SIMPLE")
+    assert run.main(['--weights', str(w)]) == 1                                   # no --image
+    assert run.main(['--weights', str(w), '--image', str(tmp_path / "nope.fits")]) == 1
+    assert run.main(['--weights', str(tmp_path / "nope.pt"), '--image', str(img)]) == 1
+    assert run.main(['--weights', str(w), '--image', str(img), '--maxnimgs=0']) == 1
+    txt = tmp_path / "a.txt"
+    txt.write_bytes(b"x")
+    assert run.main(['--weights', str(w), '--image', str(txt)]) == 1               # extension check
+    # chan3_preproc needs nchannels == 3 (reference scripts/run.py:253-256)
+    assert run.main(['--weights', str(w), '--image', str(img), '--preprocessing', '--chan3_preproc']) == 1
