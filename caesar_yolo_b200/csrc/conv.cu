@@ -57,21 +57,32 @@ __device__ __forceinline__ float silu_f(float y) {
 template <bool F32OUT>
 __device__ __forceinline__ void epi_cols32(const uint32_t (&v)[32], const float4 (&bias4)[8], int act, bool has_res,
                                            uint8_t* sbuf, uint32_t my_row, uint32_t sw_mask, int cc0, int ncols) {
+    // stage 1: bias (+ SiLU) on all 32 columns with the 32 MUFU ops issued back to back (their latency overlaps)
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bias4[j].x;
+        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bias4[j].y;
+        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bias4[j].z;
+        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bias4[j].w;
+    }
+    if (act == 1) {
+        float t[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            y[j] *= 0.5f;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t[j]) : "f"(y[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], t[j], y[j]);
+    } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = __fdividef(y[j], 1.0f + __expf(-y[j]));
+    }
+    // stage 2: (+ residual read in place) and 16-byte chunks into the swizzled staging row
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
         if (g8 * 8 < ncols) {
-            const float4 ba = bias4[2 * g8], bb = bias4[2 * g8 + 1];
-            float y[8] = {__uint_as_float(v[g8 * 8 + 0]) + ba.x, __uint_as_float(v[g8 * 8 + 1]) + ba.y,
-                          __uint_as_float(v[g8 * 8 + 2]) + ba.z, __uint_as_float(v[g8 * 8 + 3]) + ba.w,
-                          __uint_as_float(v[g8 * 8 + 4]) + bb.x, __uint_as_float(v[g8 * 8 + 5]) + bb.y,
-                          __uint_as_float(v[g8 * 8 + 6]) + bb.z, __uint_as_float(v[g8 * 8 + 7]) + bb.w};
-            if (act == 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
-            } else if (act == 2) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = __fdividef(y[j], 1.0f + __expf(-y[j]));
-            }
             const int cc = cc0 + g8 * 8;
             if (!F32OUT) {
                 uint32_t a = my_row + (uint32_t)(cc >> 3) * 16u;
@@ -83,22 +94,24 @@ __device__ __forceinline__ void epi_cols32(const uint32_t (&v)[32], const float4
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float2 f = __bfloat1622float2(r2[j]);
-                        y[2 * j] += f.x;
-                        y[2 * j + 1] += f.y;
+                        y[g8 * 8 + 2 * j] += f.x;
+                        y[g8 * 8 + 2 * j + 1] += f.y;
                     }
                 }
                 uint4 o;
                 __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(y[g8 * 8 + 2 * j], y[g8 * 8 + 2 * j + 1]);
                 *dst = o;
             } else {
                 uint32_t a0 = my_row + (uint32_t)(cc >> 2) * 16u;
                 uint32_t a1 = a0 + 16u;
                 a0 ^= (a0 >> 3) & sw_mask;
                 a1 ^= (a1 >> 3) & sw_mask;
-                *reinterpret_cast<float4*>(sbuf + a0) = make_float4(y[0], y[1], y[2], y[3]);
-                *reinterpret_cast<float4*>(sbuf + a1) = make_float4(y[4], y[5], y[6], y[7]);
+                *reinterpret_cast<float4*>(sbuf + a0) =
+                    make_float4(y[g8 * 8 + 0], y[g8 * 8 + 1], y[g8 * 8 + 2], y[g8 * 8 + 3]);
+                *reinterpret_cast<float4*>(sbuf + a1) =
+                    make_float4(y[g8 * 8 + 4], y[g8 * 8 + 5], y[g8 * 8 + 6], y[g8 * 8 + 7]);
             }
         }
     }
@@ -255,6 +268,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             unsigned long long* dbg =
                 (p.dbg && i < p.dbg_units) ? p.dbg + ((size_t)worker * p.dbg_units + i) * 8 : nullptr;
             long long wait_a = 0, wait_b = 0;
+            if (p.dbg_epi) dbg = nullptr;
             if (dbg && lane == 0) dbg[0] = clock64();
             mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
             tc_fence_after();
@@ -373,52 +387,63 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     bufsel ^= 1;
                     uint8_t* sbuf = stage_base + (size_t)b * kEpiBufBytes;
                     const uint32_t sbuf_a = smem_u32(sbuf);
+                    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
+                    if (dbg) tq0 = clock64();
                     if (lane == 0) bulk_wait_read<1>();  // the store that used this buffer two groups ago has read it
                     __syncwarp();
+                    if (dbg) tq1 = clock64();
                     if (p.res != nullptr && lane == 0) {
                         mbar_arrive_expect_tx(&rbar[b], 32u * p.o_row_bytes);
                         tma_load_4d(sbuf, &p.tmR, &rbar[b], col0, bw0, bh0, bn0);
                     }
                     const bool has_res = p.res != nullptr;
-                    bool res_ready = !has_res;
-#pragma unroll 1
-                    for (int cs = 0; cs < gw; cs += 32) {
-                        const int ncols = gw - cs >= 32 ? 32 : 16;
-                        // bias for these columns first: the loads overlap the TMEM read
-                        float4 bias4[8];
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + cs);
+                    // both 32-column TMEM reads of the group are issued before the wait (and the bias loads overlap
+                    // them), then 64 columns of math run with full instruction-level parallelism
+                    const bool two = gw > 32;
+                    const int ncols0 = gw >= 32 ? 32 : 16;
+                    uint32_t va[32], vb[32];
+                    if (ncols0 == 32) {
+                        tmem_ld_32x32(taddr + c0, va);
+                    } else {
+                        uint32_t v16[16];
+                        tmem_ld_32x16(taddr + c0, v16);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            bias4[j] = (j * 4 < ncols) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        uint32_t v[32];
-                        if (ncols == 32) {
-                            tmem_ld_32x32(taddr + c0 + cs, v);
-                        } else {
-                            uint32_t v16[16];
-                            tmem_ld_32x16(taddr + c0 + cs, v16);
+                        for (int j = 0; j < 16; ++j) va[j] = v16[j];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = v16[j];
+                        for (int j = 16; j < 32; ++j) va[j] = 0;
+                    }
+                    if (two) tmem_ld_32x32(taddr + c0 + 32, vb);
+                    float4 bias_a[8], bias_b[8];
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-                            for (int j = 16; j < 32; ++j) v[j] = 0;
-                        }
-                        tmem_ld_wait();
-                        if (!res_ready) {
-                            mbar_wait(&rbar[b], b ? rphase1 : rphase0);
-                            if (b) rphase1 ^= 1;
-                            else rphase0 ^= 1;
-                            res_ready = true;
-                        }
-                        if (p.o_esz == 2)
-                            epi_cols32<false>(v, bias4, p.act, has_res, sbuf, my_row, p.o_sw_mask, cs, ncols);
-                        else
-                            epi_cols32<true>(v, bias4, p.act, false, sbuf, my_row, p.o_sw_mask, cs, ncols);
+                    for (int j = 0; j < 8; ++j) {
+                        bias_a[j] = (j * 4 < ncols0) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        bias_b[j] = two ? __ldg(b4 + 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tmem_ld_wait();
+                    if (dbg) tq2 = clock64();
+                    if (has_res) {
+                        mbar_wait(&rbar[b], b ? rphase1 : rphase0);
+                        if (b) rphase1 ^= 1;
+                        else rphase0 ^= 1;
+                    }
+                    if (p.o_esz == 2) {
+                        epi_cols32<false>(va, bias_a, p.act, has_res, sbuf, my_row, p.o_sw_mask, 0, ncols0);
+                        if (two) epi_cols32<false>(vb, bias_b, p.act, has_res, sbuf, my_row, p.o_sw_mask, 32, 32);
+                    } else {
+                        epi_cols32<true>(va, bias_a, p.act, false, sbuf, my_row, p.o_sw_mask, 0, ncols0);
                     }
                     (void)sbuf_a;
+                    if (dbg) tq3 = clock64();
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         tma_store_4d(&p.tmO, sbuf, col0, bw0, bh0, bn0);
                         bulk_commit();
+                    }
+                    if (dbg && p.dbg_epi) {
+                        const long long tq4 = clock64();
+                        dbg[0] += tq1 - tq0; dbg[1] += tq2 - tq1; dbg[2] += tq3 - tq2; dbg[3] += tq4 - tq3;
                     }
                 }
             }
@@ -529,7 +554,8 @@ static int launch_t(const ConvPlan& pl, cudaStream_t st) {
     ConvKParams kp = pl.kp;
     if (g_dbg) {
         kp.dbg = g_dbg;
-        kp.dbg_units = g_dbg_units;
+        kp.dbg_units = g_dbg_units & 0xffff;
+        kp.dbg_epi = (g_dbg_units >> 30) & 1;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -81,6 +81,7 @@ struct ConvKParams {
     int pair;                      // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2), a unit = 2 x halves half tiles
     unsigned long long* dbg;       // optional per-CTA timeline (clock64 stamps), 8 words per unit, see conv_probe
     int dbg_units;
+    int dbg_epi;                   // timeline slots 0..3 = epilogue phase sums instead of the MMA stamps
     ConvALoad aload[9];
     ConvTap tap[9];
 };

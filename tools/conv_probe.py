@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 SHAPES = {
     # name: (B, H, W, cin, cout, k, s, res)
+    'stem_1x1_320_32_64': (32, 320, 320, 32, 64, 1, 1, False),
     'm2.cv1_1x1_160_128_128': (32, 160, 160, 128, 128, 1, 1, False),
     'm2.m_3x3_160_64_64': (32, 160, 160, 64, 64, 3, 1, False),
     'm2.m_3x3_160_64_64_res': (32, 160, 160, 64, 64, 3, 1, True),
@@ -32,6 +33,7 @@ def main():
     ap.add_argument('--timeline', action='store_true')
     ap.add_argument('--shapes', default='')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--epi', action='store_true', help='epilogue phase sums instead of the MMA timeline')
     a = ap.parse_args()
     import torch
     from caesar_yolo_b200 import ops
@@ -72,11 +74,17 @@ def main():
             U = 64
             grid = info[7]
             buf = torch.zeros(grid * U * 8, dtype=torch.int64, device=dev)
-            check(lib.cy_conv_set_debug(ctypes.c_void_p(buf.data_ptr()), U))
+            check(lib.cy_conv_set_debug(ctypes.c_void_p(buf.data_ptr()), U | ((1 << 30) if a.epi else 0)))
             ops.conv2d_nhwc(x, 0, cin, wp, bp, cout, k, s, out, 0, act=True, res=r)
             torch.cuda.synchronize()
             check(lib.cy_conv_set_debug(ctypes.c_void_p(0), 0))
             t = buf.cpu().numpy().reshape(grid, U, 8)
+            if a.epi:
+                nu0 = min((info[2] + grid - 1) // grid, U)
+                d = t[0, 1:nu0 - 1].astype(float)
+                print("   CTA0 epilogue warp 0, clk per unit: wait staging buffer %.0f | TMEM load %.0f | math + st.shared %.0f | fence + TMA store %.0f | acc wait %.0f | total %.0f"
+                      % (d[:, 0].mean(), d[:, 1].mean(), d[:, 2].mean(), d[:, 3].mean(), (d[:, 6] - d[:, 5]).mean(), (d[:, 7] - d[:, 6]).mean()))
+                continue
             nu = [(info[2] - c + grid - 1) // grid for c in range(grid)]
             c = 0
             t0 = t[c, 0, 0]
