@@ -386,7 +386,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     const int b = bufsel;
                     bufsel ^= 1;
                     uint8_t* sbuf = stage_base + (size_t)b * kEpiBufBytes;
-                    const uint32_t sbuf_a = smem_u32(sbuf);
                     long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
                     if (dbg) tq0 = clock64();
                     if (lane == 0) bulk_wait_read<1>();  // the store that used this buffer two groups ago has read it
@@ -433,7 +432,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     } else {
                         epi_cols32<true>(va, bias_a, p.act, false, sbuf, my_row, p.o_sw_mask, 0, ncols0);
                     }
-                    (void)sbuf_a;
                     if (dbg) tq3 = clock64();
                     fence_proxy_async_smem();
                     __syncwarp();

@@ -9,24 +9,29 @@
 // by TMA = the conv padding).  Stride-2 convs use four parity-shifted tensor maps (even/odd rows x even/odd cols) so
 // that every tap is again a dense box.
 //
-// What bounds this kernel is L2->SMEM traffic (LTS cap ~42 B/clk/SM against ~8192 flop/clk/SM of tensor pipe), so the
-// design is about bytes per flop:
+// What bounds a tcgen05 conv (measured): operand delivery.  An SS-mode MMA of 128 x 128 x 16 reads 8 KB of
+// shared memory per 64 clk of math (the whole 128 B/clk port), TMA writes fill the same memory, and L2 delivers about
+// 42 B/clk to an SM.  So the design is about operand bytes per flop:
 //  * persistent CTAs (one per SM), a work unit = up to two 128-row "half tiles" (two TMEM accumulators) that share
 //    every weight tile, x one BLOCK_N column tile; accumulators are double-buffered in TMEM so the epilogue of unit i
 //    overlaps the main loop of unit i+1;
+//  * PAIR: two CTAs of a cluster run one unit with tcgen05 cta_group::2 (M = 256 per instruction): each CTA stages its
+//    own A boxes and half of every weight tile, the leader issues the MMAs, commits are multicast to both CTAs;
 //  * the K loop is a list of "A loads" (one TMA box per half tile) each serving a list of taps; a tap = one weight
-//    tile + the MMAs that read the A box at a byte offset through the UMMA descriptor start address:
-//      MODE 0: one A load per tap (any box shape bw x bh x bn = 128 rows), 1x1 and stride-2 convs, odd map sizes;
-//      MODE 1: 3x3 stride 1: three A loads per channel chunk (one per horizontal tap), box 8 x 18 pixels; the three
-//              vertical taps are the same box read at +0/+1/+2 image rows (8 px * 128 B = one swizzle atom, so the
-//              shift keeps the 128B-swizzle phase);
+//    tile + the MMAs that read the A box at a byte offset through the UMMA descriptor start address (the 128B-swizzle
+//    XOR is a function of the absolute shared-memory address, so a shift by whole 128 B pixel rows is legal):
+//      MODE 0: one A load per tap (any box shape bw x bh x bn = 128 rows): 1x1 convs, maps that 8 x 16 tiles cover badly;
+//      MODE 1: 3x3 stride 1, conservative variant: three A loads per channel chunk (one per horizontal tap), box
+//              8 x 18 pixels; the three vertical taps are the same box read at +0/+1/+2 image rows;
+//      MODE 2: 3x3 stride 1: ONE A load per channel chunk, box 10 x 18 pixels (halo on all sides); all nine taps read
+//              it at (kh*10 + kw) * 128 B, stride between 8-row groups = 10 px * 128 B;
 //      MODE 3: 3x3 stride 2: four A loads per channel chunk, one per input parity class (odd/even rows x cols): the
 //              9 taps fall into classes of 4 + 2 + 2 + 1 taps that read the same (17|16) x (9|8) pixel box of their
-//              parity map at +0/+1 row / column offsets -- A traffic drops from 9 to 4.4 boxes per chunk.
-//      MODE 2: 3x3 stride 1: ONE A load per channel chunk, box 10 x 18 pixels (halo on all sides); all nine taps read
-//              it at (kh*10 + kw) * 128 B (the swizzle XOR is a function of the absolute shared-memory address, so a
-//              128 B shift is legal; stride between 8-row groups = 10 px * 128 B).
-//  * separate shared-memory rings for A boxes and weight tiles, each with its own TMA producer thread.
+//              parity map at +0/+1 row / column offsets -- A traffic drops from 9 to 4.4 boxes per chunk;
+//  * separate shared-memory rings for A boxes and weight tiles, each with its own TMA producer warp; all single-issuer
+//    loops are warp-uniform with elect.sync around the issuing instruction (uniform-register UTCHMMA / UTMALDG);
+//  * epilogue: TMEM -> bias + SiLU (tanh form) -> swizzled staging buffer (+ TMA-loaded residual, in place) -> one TMA
+//    store per warp and 64-column group (TMA clips image borders and channel padding).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -1,5 +1,5 @@
 // YOLOv8 detection model runtime for B200: graph builder, BN folding, weight packing, activation buffers,
-// per-shape execution plans (tensor maps cached), and the non-GEMM layer kernels (stem conv, max-pool,
+// per-shape execution plans (tensor maps cached), and the non-GEMM layer kernels (stem im2col gather, max-pool,
 // nearest upsample).  All dense contractions go through the tcgen05 implicit-GEMM kernel in conv.cu.
 //
 // Replaces the `model(image, ...)` call of the reference (caesar_yolo/evaluation.py:181-193), i.e. ultralytics
