@@ -247,3 +247,23 @@ def test_tiled_subimage_matches_oracle(tmp_path):
     m = match_fraction(got, emu)
     print("sub-image: ours %d, oracle(bf16-emulated) %d sources, matched@IoU0.9 %.4f" % (len(got), len(emu), m))
     assert m >= 0.90 - (0.05 + 2.0 / len(emu))
+
+
+def test_catalog_independent_of_batching(tmp_path):
+    """Size-independent property at a larger scale (4096^2 mosaic, 64 tiles, YOLOv8n): the catalog must not depend on
+    how tiles are batched through the conv stack (batch 7 -> single-CTA kernels, ragged last batch; batch 64 -> CTA
+    pairs and two-half units): per output element the K loop order is the same in every variant."""
+    from caesar_yolo_b200 import synth, weights as W
+    mosaic = synth.make_mosaic(4096, 4096, seed=91, nan_border_frac=0.0)
+    mosaic[:, -60:] = np.nan
+    path = str(tmp_path / "big.fits")
+    synth.write_fits(path, mosaic)
+    w = W.make_random_weights('n', 5, seed=0, cls_bias=-12.0)
+    cats = []
+    for bt in (7, 64):
+        out = tmp_path / ("b%d" % bt)
+        out.mkdir()
+        _run_ours(w, path, str(out), True, batch_tiles=bt)
+        cats.append(json.load(open(str(out / "catalog_big.json")))['sources'])
+    assert len(cats[0]) > 300
+    assert cats[0] == cats[1]
