@@ -75,3 +75,29 @@ class FitsImage(object):
         if self.bscale != 1 or self.bzero != 0:
             out = out * np.float32(self.bscale) + np.float32(self.bzero)
         return out
+
+
+def write_fits(data, path):
+    """Minimal primary-HDU writer (utils.write_fits, caesar_yolo/utils.py:126-134: `fits.PrimaryHDU(data)` with no
+    header): 2-D float32 / float64 array -> big-endian payload padded to 2880-byte blocks."""
+    a = np.asarray(data)
+    if a.ndim != 2 or a.dtype.kind != 'f':
+        raise ValueError("write_fits: 2-D floating-point array expected")
+    bitpix = -32 if a.dtype.itemsize == 4 else -64
+
+    def card(key, val, comment=""):
+        v = ("%20s" % val) if not isinstance(val, str) else val
+        c = "%-8s= %s" % (key, v)
+        if comment:
+            c += " / " + comment
+        return ("%-80s" % c)[:80]
+    cards = [card("SIMPLE", "T", "conforms to FITS standard"), card("BITPIX", bitpix, "array data type"),
+             card("NAXIS", 2, "number of array dimensions"), card("NAXIS1", a.shape[1]), card("NAXIS2", a.shape[0]),
+             card("EXTEND", "T"), "%-80s" % "END"]
+    hdr = "".join(cards)
+    hdr += " " * (-len(hdr) % 2880)
+    payload = np.ascontiguousarray(a, dtype='>f4' if bitpix == -32 else '>f8').tobytes()
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        f.write(payload)
+        f.write(b"\0" * (-len(payload) % 2880))

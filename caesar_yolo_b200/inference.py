@@ -41,6 +41,9 @@ class SFinder(object):
         self.write_to_json = config.get('save_catalog', True)
         self.write_to_ds9 = config.get('save_region', True)
         self.outdir = config.get('outdir', '.')
+        self.save_tile_json = config.get('save_tile_catalog', False)
+        self.save_tile_regions = config.get('save_tile_region', False)
+        self.save_tile_img = config.get('save_tile_img', False)
         self.procId, self.nproc = _dist_info()
         self.timing = {}
         self.engine = None
@@ -151,7 +154,25 @@ class SFinder(object):
             return -1
         eng = self._engine()
         img = self.fits.raw if self.fits.is_raw_f32 else self.fits.rows(0, self.fits.ny)
-        src, n = run_image(eng, img, self.fits.is_raw_f32, tiles, rank=self.procId, world=self.nproc)
+        # per-tile debug files (inference.py:218-229): every rank writes the files of its own tiles
+        hook = None
+        eng.collect_tile_status = bool(self.save_tile_json or self.save_tile_regions)
+        eng.tile_img_sink = None
+        if self.save_tile_img:
+            from .fits import write_fits
+
+            def sink(tid, ch0):  # evaluation.py:550-554: image[:,:,0] (float64 in the reference)
+                write_fits(ch0.astype(np.float64),
+                           os.path.join(self.outdir, 'timg_' + str(self.image_id) + '_tid' + str(tid) + '.fits'))
+            eng.tile_img_sink = sink
+        if eng.collect_tile_status:
+            def hook(packed, n, a, b):
+                recs = packed[:n * 32].cpu().numpy().view(ops.REC_DTYPE)
+                st = eng.tile_status[a:b].cpu().numpy()
+                catalog.write_tile_outputs(recs, tiles, np.arange(a, b), st, self.class_names, self.image_id,
+                                           self.outdir, self.save_tile_json, self.save_tile_regions)
+        src, n = run_image(eng, img, self.fits.is_raw_f32, tiles, rank=self.procId, world=self.nproc,
+                           on_local_records=hook)
         self.timing['run_s'] = time.time() - t0
         if self.procId == 0:
             self.sources = {"sources": catalog.sources_to_dicts(src, self.class_names)}

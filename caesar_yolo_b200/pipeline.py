@@ -75,6 +75,9 @@ class Engine(object):
         self.launches = 0      # kernels launched by this engine (bench.py's gpu_launches)
         self.stage_events = None   # set to [] to collect (stage, start_event, end_event) triples (bench breakdown)
         self._fwd_launches = {}
+        # per-tile debug outputs (--save_tile_catalog / --save_tile_region / --save_tile_img, inference.py:218-229):
+        self.collect_tile_status = False   # keep the per-tile status (0 ok, <0 rejected) in self.tile_status
+        self.tile_img_sink = None          # callable(tile_id, ndarray[Ty,Tx] float32): channel 0 after the chain
 
     def _mark(self):
         if self.stage_events is None:
@@ -113,6 +116,9 @@ class Engine(object):
         self.nrec = self._get('nrec', (self.T,), torch.int32)
         self.nrec.zero_()
         self.launches += 1
+        self.tile_status = None
+        if self.collect_tile_status:
+            self.tile_status = torch.full((self.T,), -3, dtype=torch.int32, device=self.device)  # -3: not processed
 
     def process_tiles(self, img_dev, row_stride, big_endian, origin_x, origin_y, tile_ids):
         """img_dev covers mosaic rows/cols starting at (origin_x, origin_y); tile_ids: global ids of the tiles to
@@ -150,6 +156,12 @@ class Engine(object):
                        chain_out=chain, model_in=model_in, status=status)
         self._stage('preprocess', e)
         self.launches += 3
+        if self.tile_img_sink is not None:   # Analyzer.write_fits: channel 0 of the preprocessed image, accepted tiles
+            ok = status.cpu().numpy()
+            ch0 = chain[:, :, :, 0].cpu().numpy()
+            for k in range(G):
+                if ok[k] == 0:
+                    self.tile_img_sink(int(ids[k]), ch0[k])
         for s in range(0, G, self.batch_tiles):
             e = min(G, s + self.batch_tiles)
             self._run_batch(model_in[s:e], status[s:e], ids_dev[s:e], Ty, Tx, Sh, Sw, lb)
@@ -181,6 +193,8 @@ class Engine(object):
                        status=mstat, pre_status=status)
         ops.make_records(dets, keep, nkeep, mstat, self.tiles_dev, ids_dev, self.rec_slots, self.nrec)
         self._stage('merge_tile_records', e)
+        if self.tile_status is not None:
+            self.tile_status.index_copy_(0, ids_dev.long(), mstat)
         fl = self._fwd_launches.get((B, Sh, Sw))
         if fl is None:
             fl = int(self.model.info(B, Sh, Sw)['launches'])
@@ -258,11 +272,13 @@ def allgather_records(packed, n, world_size):
     return torch.cat(parts), sum(counts)
 
 
-def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, max_chunk_bytes=1 << 29, on_rank0_only=True):
+def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, max_chunk_bytes=1 << 29, on_rank0_only=True,
+              on_local_records=None):
     """FITS payload in HOST memory -> catalog.  img_host: 2-D array [ny,nx] of 4-byte pixels (numpy array / memmap, or
     a pinned torch tensor for zero-copy staging); big_endian: raw FITS byte order.  Tiles of this rank (contiguous
     band of tile rows) are uploaded in row chunks on a copy stream and processed as they arrive.
-    Returns (sources structured array or None on ranks != 0, n_records_total)."""
+    on_local_records(packed, n, first_tile_id, last_tile_id_excl): called with this rank's records before the exchange
+    (per-tile output files).  Returns (sources structured array or None on ranks != 0, n_records_total)."""
     engine.begin(tiles)
     a, b = split_tile_rows(tiles, world)[rank]
     ids = np.arange(a, b, dtype=np.int32)
@@ -296,18 +312,32 @@ def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, max_chunk_by
                 if is_torch:
                     src = img_host[y0c:y1c]
                 else:
-                    stage = torch.empty(((y1c - y0c), nx), dtype=torch.int32, pin_memory=True)
+                    # two reusable pinned staging buffers (file/memmap rows -> pinned -> HBM): the host copy of chunk
+                    # i+1 overlaps the DMA of chunk i; a buffer is rewritten only after its last DMA completed
+                    nwords = (y1c - y0c) * nx
+                    slot = ('pin', ci & 1)
+                    pin, pin_ev = engine._buf.get(slot, (None, None))
+                    if pin is None or pin.numel() < nwords:
+                        pin = torch.empty((nwords,), dtype=torch.int32, pin_memory=True)
+                        pin_ev = None
+                    if pin_ev is not None:
+                        pin_ev.synchronize()
+                    stage = pin[:nwords].view(y1c - y0c, nx)
                     np.copyto(stage.numpy().view(np.uint8).reshape(y1c - y0c, nx * 4),
                               np.ascontiguousarray(img_host[y0c:y1c]).view(np.uint8).reshape(y1c - y0c, nx * 4))
                     src = stage
                 slab_dev.copy_(src.view(torch.int32) if src.dtype != torch.int32 else src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
+                if not is_torch:
+                    engine._buf[slot] = (pin, ev)
             compute.wait_event(ev)
             slab_dev.record_stream(compute)
             engine.process_tiles(slab_dev, nx, big_endian, 0, y0c, sel)
             slabs.append(slab_dev)
     packed, n = engine.finish()
+    if on_local_records is not None:
+        on_local_records(packed, n, a, b)
     if world > 1:
         packed, n = allgather_records(packed, n, world)
     if rank == 0 or not on_rank0_only:

@@ -65,3 +65,43 @@ def test_validation_errors_return_1(tmp_path):
     assert run.main(['--weights', str(w), '--image', str(txt)]) == 1               # extension check
     # chan3_preproc needs nchannels == 3 (reference scripts/run.py:253-256)
     assert run.main(['--weights', str(w), '--image', str(img), '--preprocessing', '--chan3_preproc']) == 1
+
+
+def test_writers_formats(tmp_path):
+    """catalog.py writers: key set / order of the json files, DS9 text with the SFinder vs Analyzer colour maps
+    (inference.py:334-342 vs evaluation.py:108-115), per-tile files; fits.write_fits round trip."""
+    import json
+    import numpy as np
+    from caesar_yolo_b200 import catalog, fits, ops
+    names = {0: 'spurious', 1: 'compact', 2: 'extended', 3: 'extended-multisland', 4: 'flagged'}
+    recs = np.zeros(4, dtype=ops.REC_DTYPE)
+    recs['x1'], recs['y1'], recs['x2'], recs['y2'] = [10, 600, 700, 20], [5, 40, 90, 30], [30, 640, 760, 25], [25, 80, 99, 44]
+    recs['score'] = [0.9, 0.8, 0.7, 0.6]
+    recs['cls'] = [1, 3, 4, 2]
+    recs['tile_id'] = [0, 1, 1, 0]
+    recs['flags'] = [0, 1, 0, 0]
+    tiles = np.zeros(3, dtype=ops.TILE_DTYPE)
+    written = catalog.write_tile_outputs(recs, tiles, [0, 1, 2], np.array([0, 0, -1]), names, 'img', str(tmp_path),
+                                         True, True)
+    assert sorted(os.path.basename(p) for p in written) == ['catalog_img_tid0.json', 'catalog_img_tid0.reg',
+                                                            'catalog_img_tid1.json', 'catalog_img_tid1.reg']
+    t0 = json.load(open(str(tmp_path / 'catalog_img_tid0.json')))
+    assert [o['name'] for o in t0['objs']] == ['S1_t0', 'S2_t0'] and t0['image_id'] == 'img'
+    assert [o['x1'] for o in t0['objs']] == [10.0, 20.0]
+    text = open(str(tmp_path / 'catalog_img_tid0.json')).read()
+    assert text.index('"class_id"') < text.index('"class_name"') < text.index('"edge"') < text.index('"name"')
+    reg = open(str(tmp_path / 'catalog_img_tid1.reg')).read().splitlines()
+    assert reg[0] == '# Region file format: DS9 astropy/regions' and reg[1] == 'image'
+    assert reg[2] == 'box(621,61,40,40,0) # text={S1_t1} tag={extended-multisland} tag={BORDER} color=orange'
+    assert reg[3].endswith('tag={flagged} color=magenta')
+    src = catalog.sources_to_dicts(np.array([(600, 40, 640, 80, .8, 3, 3, -1), (700, 90, 760, 99, .7, 4, 0, 1)],
+                                            dtype=ops.SRC_DTYPE), names)
+    catalog.write_ds9(src, str(tmp_path / 'ds9.reg'))
+    reg = open(str(tmp_path / 'ds9.reg')).read().splitlines()
+    assert reg[2] == 'box(621,61,40,40,0) # text={S1} tag={extended-multisland} tag={BORDER} tag={MERGED} color=yellow'
+    assert reg[3] == 'box(731,95.5,60,9,0) # text={S2} tag={flagged} color=black'
+    a = np.random.default_rng(0).normal(size=(37, 53))
+    fits.write_fits(a, str(tmp_path / 'x.fits'))
+    f = fits.FitsImage(str(tmp_path / 'x.fits'))
+    assert (f.nx, f.ny, f.bitpix) == (53, 37, -64) and np.array_equal(np.asarray(f.raw).astype('f8'), a)
+    assert os.path.getsize(str(tmp_path / 'x.fits')) % 2880 == 0

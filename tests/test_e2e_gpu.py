@@ -267,3 +267,38 @@ def test_catalog_independent_of_batching(tmp_path):
         cats.append(json.load(open(str(out / "catalog_big.json")))['sources'])
     assert len(cats[0]) > 300
     assert cats[0] == cats[1]
+
+
+def test_per_tile_outputs(tmp_path):
+    """--save_tile_catalog / --save_tile_region / --save_tile_img (inference.py:218-229, evaluation.py:216-241): one
+    catalog_<id>_tid<N>.json per accepted tile with tile-tagged names and tile-local edge flags, a .reg per tile with
+    detections, timg_<id>_tid<N>.fits = channel 0 of the preprocessed tile; their union equals the records the
+    mosaic catalog was merged from."""
+    from caesar_yolo_b200 import synth, weights as W
+    from caesar_yolo_b200.fits import FitsImage
+    mosaic = synth.make_mosaic(1024, 1536, seed=12, nan_border_frac=0.0)
+    mosaic[:512, :512] = np.nan      # tile 0: all masked -> rejected by the reference (no files)
+    path = str(tmp_path / "m.fits")
+    synth.write_fits(path, mosaic)
+    w = W.make_random_weights('n', 5, seed=0, cls_bias=-12.0)
+    _run_ours(w, path, str(tmp_path), True, save_tile_catalog=True, save_tile_region=True, save_tile_img=True)
+    cat = json.load(open(str(tmp_path / "catalog_m.json")))['sources']
+    assert not os.path.exists(str(tmp_path / "catalog_m_tid0.json"))
+    assert not os.path.exists(str(tmp_path / "timg_m_tid0.fits"))
+    n_obj = 0
+    for tid in range(1, 6):
+        t = json.load(open(str(tmp_path / ("catalog_m_tid%d.json" % tid))))
+        assert t['image_id'] == 'm'
+        objs = t['objs']
+        n_obj += len(objs)
+        assert [o['name'] for o in objs] == ['S%d_t%d' % (i + 1, tid) for i in range(len(objs))]
+        x0, y0 = (tid % 3) * 512, (tid // 3) * 512
+        for o in objs:
+            assert x0 <= o['x1'] <= o['x2'] <= x0 + 512 and y0 <= o['y1'] <= o['y2'] <= y0 + 512
+            assert o['edge'] in (0, 1) and 'merged' not in o
+        assert os.path.exists(str(tmp_path / ("catalog_m_tid%d.reg" % tid))) == (len(objs) > 0)
+        f = FitsImage(str(tmp_path / ("timg_m_tid%d.fits" % tid)))
+        assert (f.ny, f.nx, f.bitpix) == (512, 512, -64)
+        img = np.asarray(f.raw)
+        assert 0.0 <= img.min() and img.max() <= 255.0 and img.max() > 1.0
+    assert n_obj >= len(cat) > 10      # merging only removes sources
