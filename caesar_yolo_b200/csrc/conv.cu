@@ -602,7 +602,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     if (d.stride == 2 && ((d.Hin | d.Win) & 1)) FAIL("stride-2 conv needs even input extent");
     const int kc = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
     const int row_bytes = kc * 2;
-    const int bn_ = conv_block_n(d.cout);
+    int bn_ = conv_block_n(d.cout);
     if (d.cout_pad % bn_) FAIL("cout_pad %d not a multiple of BLOCK_N %d", d.cout_pad, bn_);
     ConvKParams& kp = plan->kp;
     memset(&kp, 0, sizeof(kp));
@@ -675,6 +675,21 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     const int force_pair = env_int("CY_CONV_PAIR", -1);   // -1 auto, 0 off, 2 force wherever possible
     if (force_pair == 0) pair = 0;
     if (force_pair == 2) pair = pair_ok ? 1 : 0;
+    // Wide pair tiles: one 256 x 256 unit per CTA pair (cta_group::2, M = 256, N = 256; each CTA stages its own 128 A
+    // rows and 128 of the 256 weight rows) instead of two 128-row halves x N = 128.  Operand rows fetched per K step and
+    // CTA: 128 A + 128 B = 256 instead of 256 A + 64 B = 320, and per MMA and SM the shared-memory operand reads drop
+    // from 6 KB / 64 clk to 8 KB / 128 clk; the two accumulator buffers are the full 512 TMEM columns.  Used where
+    // every tap loads its own A box (1x1 convs, mode 0): with 3x3 halo reuse (mode 2/3) A is nearly free and the
+    // weight rows dominate, so the two-half unit (64 weight rows per CTA) stays better there (measured per layer,
+    // profiles/r01h_layers_wide_ab.txt).
+    const int wide_env = env_int("CY_CONV_WIDE", 1);   // 0 off, 1 auto, 2 force wherever possible (tests)
+    if (pair && bn_ == 128 && d.cout_pad % 256 == 0 && !d.out_f32 && wide_env &&
+        (wide_env == 2 || (mode == 0 && ((kp.n_half_tiles + 1) / 2) * (d.cout_pad / 256) >= num_sms() / 2))) {
+        bn_ = 256;
+        halves = 1;
+        kp.block_n = bn_;
+        kp.n_tiles_n = d.cout_pad / bn_;
+    }
     kp.pair = pair;
     kp.halves = halves;
     const int per_unit = halves * (pair ? 2 : 1);

@@ -412,7 +412,8 @@ def build_reference_stages(pp, subtract_bkg=False, sigma_bkg=3, use_box_mask_in_
 
 
 def synth_tile():
-    """96 x 80 tile with point sources, a NaN->0 border band and a block of exact zeros (mosaic edge)."""
+    """96 x 80 tile with point sources, a NaN->0 border band and a block of exact zeros (mosaic edge).  Rows 0..2 keep
+    live pixels: Analyzer.predict rejects images whose first rows are constant (evaluation.py:171-176)."""
     rng = np.random.default_rng(77)
     ny, nx = 80, 96
     img = rng.normal(2e-5, 1e-4, (ny, nx))
@@ -421,8 +422,8 @@ def synth_tile():
         cx, cy, a, s = rng.uniform(5, nx - 5), rng.uniform(5, ny - 5), rng.uniform(5e-4, 2e-2), rng.uniform(1, 3)
         img += a * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
     img = img.astype(np.float32)
-    img[:7, :] = 0
-    img[60:, 80:] = 0
+    img[-7:, :] = 0
+    img[:30, 80:] = 0
     return img
 
 

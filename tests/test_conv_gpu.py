@@ -127,3 +127,40 @@ def test_conv_stride2_parity_patch_reuse(monkeypatch, pair, halves, shape):
     monkeypatch.setenv("CY_CONV_PAIR", str(pair))
     monkeypatch.setenv("CY_CONV_HALVES", str(halves))
     _run_case(seed=shape + 41, **S2_SHAPES[shape])
+
+
+WIDE_SHAPES = [
+    dict(B=1, H=80, W=40, cin=256, cout=256, k=3, s=1, act=True, res=False, out_f32=False, in_extra=64, out_extra=128),
+    dict(B=7, H=20, W=20, cin=192, cout=256, k=1, s=1, act=True, res=False, out_f32=False),
+    dict(B=3, H=40, W=40, cin=128, cout=512, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=3, H=80, W=80, cin=128, cout=256, k=3, s=2, act=True, res=False, out_f32=False),
+    dict(B=5, H=20, W=10, cin=320, cout=512, k=1, s=1, act=False, res=False, out_f32=False, out_extra=8),
+]
+
+
+@pytest.mark.parametrize("shape", range(len(WIDE_SHAPES)))
+def test_conv_wide_pair_tiles(monkeypatch, shape):
+    """256 x 256 pair units (cta_group::2, N = 256, one 128-row half per CTA, two 256-column accumulators in TMEM),
+    forced on small shapes; the planner picks them for Cout % 256 == 0 pair layers."""
+    from caesar_yolo_b200 import ops
+    import ctypes
+    monkeypatch.setenv("CY_CONV_PAIR", "2")
+    monkeypatch.setenv("CY_CONV_WIDE", "2")
+    c = WIDE_SHAPES[shape]
+    info = (ctypes.c_int * 8)()
+    ops.check(ops.lib.cy_conv_plan_info(c['B'], c['H'], c['W'], c['cin'], c['cout'], c['k'], c['s'], info))
+    assert info[0] >= 10 and info[1] == 1 and info[3] == 256 and info[6] == 2   # pair, one half, N 256, 2 acc buffers
+    _run_case(seed=shape + 51, **c)
+
+
+def test_conv_wide_pair_tiles_persistent():
+    """Planner-selected wide tiles with several units per CTA pair (ring phases, both TMEM buffers in use)."""
+    from caesar_yolo_b200 import ops
+    import ctypes
+    info = (ctypes.c_int * 8)()
+    ops.check(ops.lib.cy_conv_plan_info(32, 40, 40, 1024, 512, 1, 1, info))
+    assert info[3] == 256 and info[0] >= 10
+    _run_case(B=32, H=40, W=40, cin=1024, cout=512, k=1, s=1, act=True, res=False, out_f32=False, seed=61)
+    ops.check(ops.lib.cy_conv_plan_info(64, 20, 20, 256, 256, 3, 1, info))
+    assert info[3] == 256 and info[0] == 10     # 20x20 maps: one box per tap (mode 0), pair, wide
+    _run_case(B=64, H=20, W=20, cin=256, cout=256, k=3, s=1, act=True, res=True, out_f32=False, seed=62)
