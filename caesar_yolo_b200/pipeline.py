@@ -120,11 +120,13 @@ class Engine(object):
         if self.collect_tile_status:
             self.tile_status = torch.full((self.T,), -3, dtype=torch.int32, device=self.device)  # -3: not processed
 
-    def process_tiles(self, img_dev, row_stride, big_endian, origin_x, origin_y, tile_ids):
+    def process_tiles(self, img_dev, row_stride, big_endian, origin_x, origin_y, tile_ids, ready=None):
         """img_dev covers mosaic rows/cols starting at (origin_x, origin_y); tile_ids: global ids of the tiles to
         process (all must lie inside img_dev).  Groups by tile shape (edge tiles are smaller).
         Preprocessing runs in groups of `pp_tiles` tiles (one CTA per tile: a multiple of the SM count keeps all 148
-        SMs busy); the conv stack and the detect/merge kernels run in batches of `batch_tiles`."""
+        SMs busy); the conv stack and the detect/merge kernels run in batches of `batch_tiles`.
+        ready(y): optional callback invoked before a group is launched, y = last mosaic row (exclusive) the group
+        reads (run_image uses it to wait for / issue the upload of those rows)."""
         tile_ids = np.asarray(tile_ids, dtype=np.int32)
         if tile_ids.size == 0:
             return
@@ -135,7 +137,10 @@ class Engine(object):
         for (Ty, Tx) in shapes:
             ids = tile_ids[(h == Ty) & (w == Tx)]
             for s in range(0, len(ids), self.pp_tiles):
-                self._run_group(img_dev, row_stride, big_endian, origin_x, origin_y, ids[s:s + self.pp_tiles], Ty, Tx)
+                g = ids[s:s + self.pp_tiles]
+                if ready is not None:
+                    ready(int(self.tiles['ymax'][g].max()))
+                self._run_group(img_dev, row_stride, big_endian, origin_x, origin_y, g, Ty, Tx)
 
     def _run_group(self, img_dev, row_stride, big_endian, ox, oy, ids, Ty, Tx):
         G = len(ids)
@@ -272,11 +277,12 @@ def allgather_records(packed, n, world_size):
     return torch.cat(parts), sum(counts)
 
 
-def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, max_chunk_bytes=1 << 29, on_rank0_only=True,
+def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, piece_bytes=1 << 26, on_rank0_only=True,
               on_local_records=None):
     """FITS payload in HOST memory -> catalog.  img_host: 2-D array [ny,nx] of 4-byte pixels (numpy array / memmap, or
-    a pinned torch tensor for zero-copy staging); big_endian: raw FITS byte order.  Tiles of this rank (contiguous
-    band of tile rows) are uploaded in row chunks on a copy stream and processed as they arrive.
+    a pinned torch tensor for zero-copy staging); big_endian: raw FITS byte order.  The rows of this rank's tiles
+    (contiguous band of tile rows) are uploaded in pieces of ~piece_bytes on a copy stream; every tile group waits
+    only for the rows it needs, so all but the first group's upload overlaps the compute of earlier groups.
     on_local_records(packed, n, first_tile_id, last_tile_id_excl): called with this rank's records before the exchange
     (per-tile output files).  Returns (sources structured array or None on ranks != 0, n_records_total)."""
     engine.begin(tiles)
@@ -285,56 +291,57 @@ def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, max_chunk_by
     is_torch = isinstance(img_host, torch.Tensor)
     ny, nx = (img_host.shape[0], img_host.shape[1])
     if len(ids):
-        ymin = tiles['ymin'][ids]
-        row_keys = np.unique(ymin)
+        Y0, Y1 = int(tiles['ymin'][ids].min()), int(tiles['ymax'][ids].max())
         copy_stream = engine._buf.get('copy_stream')
         if copy_stream is None:
             copy_stream = torch.cuda.Stream(device=engine.device)
             engine._buf['copy_stream'] = copy_stream
         compute = torch.cuda.current_stream()
-        # chunks of whole tile rows
-        chunks, cur = [], []
-        for rk in row_keys:
-            cur.append(rk)
-            sel = ids[np.isin(ymin, cur)]
-            y0c, y1c = int(tiles['ymin'][sel].min()), int(tiles['ymax'][sel].max())
-            if (y1c - y0c) * nx * 4 >= max_chunk_bytes:
-                chunks.append(cur)
-                cur = []
-        if cur:
-            chunks.append(cur)
-        slabs = []
-        for ci, ch in enumerate(chunks):
-            sel = ids[np.isin(ymin, ch)]
-            y0c, y1c = int(tiles['ymin'][sel].min()), int(tiles['ymax'][sel].max())
-            slab_dev = torch.empty(((y1c - y0c), nx), dtype=torch.int32, device=engine.device)
+        band = engine._get('band', (Y1 - Y0, nx), torch.int32)   # reused across calls: no allocation per image
+        copy_stream.wait_stream(compute)                          # earlier work may still read the band buffer
+        rows_per_piece = max(1, int(piece_bytes) // (nx * 4))
+        state = {'row': Y0, 'events': []}                         # events[i] = (last_row_excl, event)
+
+        def upload_piece():
+            r0 = state['row']
+            r1 = min(Y1, r0 + rows_per_piece)
+            k = len(state['events'])
             with torch.cuda.stream(copy_stream):
                 if is_torch:
-                    src = img_host[y0c:y1c]
+                    src = img_host[r0:r1]
                 else:
-                    # two reusable pinned staging buffers (file/memmap rows -> pinned -> HBM): the host copy of chunk
-                    # i+1 overlaps the DMA of chunk i; a buffer is rewritten only after its last DMA completed
-                    nwords = (y1c - y0c) * nx
-                    slot = ('pin', ci & 1)
+                    # two reusable pinned staging buffers (file/memmap rows -> pinned -> HBM): the host copy of piece
+                    # k+1 overlaps the DMA of piece k; a buffer is rewritten only after its last DMA completed
+                    nwords = (r1 - r0) * nx
+                    slot = ('pin', k & 1)
                     pin, pin_ev = engine._buf.get(slot, (None, None))
                     if pin is None or pin.numel() < nwords:
-                        pin = torch.empty((nwords,), dtype=torch.int32, pin_memory=True)
+                        pin = torch.empty((rows_per_piece * nx,), dtype=torch.int32, pin_memory=True)
                         pin_ev = None
                     if pin_ev is not None:
                         pin_ev.synchronize()
-                    stage = pin[:nwords].view(y1c - y0c, nx)
-                    np.copyto(stage.numpy().view(np.uint8).reshape(y1c - y0c, nx * 4),
-                              np.ascontiguousarray(img_host[y0c:y1c]).view(np.uint8).reshape(y1c - y0c, nx * 4))
-                    src = stage
-                slab_dev.copy_(src.view(torch.int32) if src.dtype != torch.int32 else src, non_blocking=True)
+                    src = pin[:nwords].view(r1 - r0, nx)
+                    np.copyto(src.numpy().view(np.uint8).reshape(r1 - r0, nx * 4),
+                              np.ascontiguousarray(img_host[r0:r1]).view(np.uint8).reshape(r1 - r0, nx * 4))
+                band[r0 - Y0:r1 - Y0].copy_(src.view(torch.int32) if src.dtype != torch.int32 else src,
+                                            non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 if not is_torch:
                     engine._buf[slot] = (pin, ev)
-            compute.wait_event(ev)
-            slab_dev.record_stream(compute)
-            engine.process_tiles(slab_dev, nx, big_endian, 0, y0c, sel)
-            slabs.append(slab_dev)
+            state['events'].append((r1, ev))
+            state['row'] = r1
+
+        def ready(y_needed):
+            """Called before a tile group is launched: rows [Y0, y_needed) must be in HBM."""
+            while state['row'] < min(y_needed, Y1):
+                upload_piece()
+            for r1, ev in state['events']:
+                if r1 >= min(y_needed, Y1):
+                    compute.wait_event(ev)
+                    break
+
+        engine.process_tiles(band, nx, big_endian, 0, Y0, ids, ready=ready)
     packed, n = engine.finish()
     if on_local_records is not None:
         on_local_records(packed, n, a, b)
