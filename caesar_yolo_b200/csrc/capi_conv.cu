@@ -4,7 +4,11 @@
 #include "common.h"
 #include <string.h>
 
-namespace cy { int conv_block_n(int cout); }
+namespace cy {
+int conv_block_n(int cout);
+int stem_conv_run(const void* in, int B, int H, int W, const float* w_host, const float* bias_host, int cout, int act,
+                  void* out, cudaStream_t st);
+}
 
 extern "C" int cy_conv_block_n(int cout) { return cy::conv_block_n(cout); }
 
@@ -45,4 +49,10 @@ extern "C" int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ct
     int r = cy::conv_launch(plan, (cudaStream_t)stream);
     if (r != 0) return cy::set_error(CY_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)r));
     return CY_OK;
+}
+
+extern "C" int cy_stem_conv_nhwc4(const void* in, int B, int H, int W, const float* w_host, const float* bias_host,
+                                  int cout, int act, void* out, uintptr_t stream) {
+    if (!in || !w_host || !bias_host || !out || B <= 0) return cy::set_error(CY_ERR_INVALID, "cy_stem_conv_nhwc4: null argument");
+    return cy::stem_conv_run(in, B, H, W, w_host, bias_host, cout, act, out, (cudaStream_t)stream);
 }

@@ -52,7 +52,7 @@ extern "C" int cy_model_info(void* model, int B, int Sh, int Sw, double* info_ho
     int r = m->get_plan(B, Sh, Sw, &pl);
     if (r) return r;
     int nconv = 0;
-    for (const Op& op : pl->ops) nconv += (op.type == Op::CONV);
+    for (const Op& op : pl->ops) nconv += (op.type == Op::CONV || op.type == Op::STEM);
     info_host[0] = (double)m->nparams;
     info_host[1] = pl->flops;
     info_host[2] = (double)pl->ops.size();

@@ -8,6 +8,7 @@
 #include "model.h"
 #include "common.h"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 
@@ -17,47 +18,151 @@ int conv_block_n(int cout);
 
 // ------------------------------------------------------------------------------------------ small kernels
 
-// Stem (3x3 stride-2 pad-1 conv, Cin=3) runs on the tensor pipe as a 1x1 conv with K = 32 over an im2col tensor:
-// one thread = one output pixel gathers its 3x3x3 patch (input NHWC with 4 channels, 4th ignored) into 32 bf16
-// (k = (kh*3+kw)*3 + c, k >= 27 zero) = 64 contiguous bytes.  HBM-bound: reads 8 B/input pixel, writes 64 B/output pixel.
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const __nv_bfloat16* __restrict__ in,  // [B,H,W,4]
-                                                          __nv_bfloat16* __restrict__ col,       // [B,H/2,W/2,32]
-                                                          int B, int H, int W) {
-    const int Ho = H / 2, Wo = W / 2;
-    const long long npix = (long long)B * Ho * Wo;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const int ow = (int)(pix % Wo);
-    const int oh = (int)((pix / Wo) % Ho);
-    const int b = (int)(pix / ((long long)Wo * Ho));
-    unsigned short v[32];
+// Stem (model.0: 3x3 stride-2 pad-1 conv, Cin = 3, + bias + SiLU), one fused kernel: no im2col tensor in HBM.
+// Bytes are the bound (read 8 B per input pixel once, write 2*cout B per output pixel once), and K = 27 is too thin
+// for a tcgen05 tile pipeline (one K-step per 32 KB of output), so the contraction runs on warp-level mma.sync
+// m16n8k16 bf16 with the weights resident in registers as B fragments:
+//   * K layout: k = ky*16 + kx*4 + c (c < 4 input channels of the NHWC-4 model input, 4th channel and kx = 3 carry
+//     zero weights) -> three K-steps, one per filter row; an A fragment register is then ONE aligned 32-bit shared
+//     memory load (two channels of one input pixel) and a warp's 32 loads are 128 contiguous bytes (no conflicts);
+//   * CTA = 8 warps = 8 output rows x 64 output columns; the 17 x 130 pixel input patch is staged in shared memory
+//     once (halo overhead 7 %), warp w owns output row w as four 16-pixel M tiles;
+//   * epilogue: bias + SiLU (same tanh form as the conv kernel) -> bf16 -> per-warp staging rows (padded, conflict
+//     free) -> 16-byte stores; the 16 pixels of an M tile are 16*cout*2 contiguous bytes of the NHWC output.
+template <int NT>  // cout = 8 * NT
+__global__ void __launch_bounds__(256, (NT <= 8 ? 2 : 1))
+stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
+                 const uint32_t* __restrict__ wfrag,     // [3][NT][32][2] B fragments (see pack_stem_weights)
+                 const float* __restrict__ bias,         // [8*NT]
+                 __nv_bfloat16* __restrict__ out,        // [B,H/2,W/2,8*NT]
+                 int H, int W, int act) {
+    constexpr int kRows = 17, kCols = 130, kCout = 8 * NT, kStageW = kCout / 2 + 4;  // staging row stride in words
+    __shared__ __align__(16) uint2 patch[kRows][kCols];
+    __shared__ __align__(16) uint32_t stage[8][16 * kStageW];
+    __shared__ float sbias[kCout];
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int ox0 = blockIdx.x * 64, oy0 = blockIdx.y * 8, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    uint32_t wb[3][NT][2];
 #pragma unroll
-    for (int i = 27; i < 32; ++i) v[i] = 0;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int ih = 2 * oh + kh - 1;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int iw = 2 * ow + kw - 1;
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(wfrag) + (ky * NT + nt) * 32 + lane);
+            wb[ky][nt][0] = q.x;
+            wb[ky][nt][1] = q.y;
+        }
+    if (tid < kCout) sbias[tid] = bias[tid];
+    {
+        const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+        const uint2* src = reinterpret_cast<const uint2*>(in) + (long long)b * H * W;
+        for (int i = tid; i < kRows * kCols; i += 256) {
+            const int r = i / kCols, c = i - r * kCols;
+            const int iy = iy0 + r, ix = ix0 + c;
             uint2 q = make_uint2(0u, 0u);
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-                q = __ldg(reinterpret_cast<const uint2*>(in + (((long long)b * H + ih) * W + iw) * 4));
-            const int t = (kh * 3 + kw) * 3;
-            v[t + 0] = (unsigned short)(q.x & 0xFFFFu);
-            v[t + 1] = (unsigned short)(q.x >> 16);
-            v[t + 2] = (unsigned short)(q.y & 0xFFFFu);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) q = __ldg(src + (long long)iy * W + ix);
+            patch[r][c] = q;
         }
     }
-    uint4* o = reinterpret_cast<uint4*>(col + pix * 32);
+    __syncthreads();
+    const int oy = oy0 + warp;
+    if (oy >= Ho) return;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t* st = stage[warp];
+    for (int mx = 0; mx < 4; ++mx) {
+        const int ox = ox0 + 16 * mx;
+        if (ox >= Wo) break;
+        float acc[NT][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 w;
-        w.x = (uint32_t)v[8 * j + 0] | ((uint32_t)v[8 * j + 1] << 16);
-        w.y = (uint32_t)v[8 * j + 2] | ((uint32_t)v[8 * j + 3] << 16);
-        w.z = (uint32_t)v[8 * j + 4] | ((uint32_t)v[8 * j + 5] << 16);
-        w.w = (uint32_t)v[8 * j + 6] | ((uint32_t)v[8 * j + 7] << 16);
-        o[j] = w;
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            // input row 2*oy - 1 + ky = patch row 2*warp + ky; output pixel p of the tile, tap kx: patch pixel
+            // 2*(16*mx + p) + kx; word index inside the row = 2 * pixel + channel pair
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(&patch[2 * warp + ky][0]) + 64 * mx + lane;
+            const uint32_t a0 = row[0], a1 = row[32], a2 = row[4], a3 = row[36];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                asm volatile(
+                    "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                    "{%0,%1,%2,%3};"
+                    : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wb[ky][nt][0]), "r"(wb[ky][nt][1]));
+        }
+        // epilogue: thread holds pixels g, g+8 x channels nt*8 + 2t, +1
+        float y[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float2 bb = *reinterpret_cast<const float2*>(&sbias[nt * 8 + 2 * t]);
+            y[nt][0] = acc[nt][0] + bb.x; y[nt][1] = acc[nt][1] + bb.y;
+            y[nt][2] = acc[nt][2] + bb.x; y[nt][3] = acc[nt][3] + bb.y;
+        }
+        if (act == 1) {
+            float th[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    y[nt][j] *= 0.5f;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th[nt][j]) : "f"(y[nt][j]));
+                }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[nt][j] = fmaf(y[nt][j], th[nt][j], y[nt][j]);
+        } else if (act == 2) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[nt][j] = __fdividef(y[nt][j], 1.0f + __expf(-y[nt][j]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(y[nt][0], y[nt][1]);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(y[nt][2], y[nt][3]);
+            st[g * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&lo);
+            st[(g + 8) * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        __syncwarp();
+        uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * Ho + oy) * Wo + ox) * kCout);
+#pragma unroll
+        for (int v = lane; v < 16 * NT; v += 32) {
+            const int p = v / NT, ch = v - p * NT;
+            dst[v] = *reinterpret_cast<const uint4*>(&st[p * kStageW + ch * 4]);
+        }
     }
+}
+
+// B fragments of the stem weights for mma.m16n8k16 (col operand): lane (g = lane / 4, t = lane % 4) of n-tile nt and
+// K-step ky holds {B[2t][g], B[2t+1][g]} and {B[2t+8][g], B[2t+9][g]} with B[k][n] = w[n][c][ky][kx] * bn_scale[n],
+// k = kx*4 + c (zero for c = 3 and kx = 3).
+static void pack_stem_weights(const std::vector<float>& w, const std::vector<float>& scale, int cout,
+                              std::vector<uint32_t>& frag) {
+    const int NT = cout / 8;
+    frag.assign((size_t)3 * NT * 32 * 2, 0u);
+    auto wt = [&](int n, int ky, int k) -> uint32_t {
+        const int kx = k >> 2, c = k & 3;
+        if (kx > 2 || c > 2) return 0u;
+        const __nv_bfloat16 h = __float2bfloat16(w[((n * 3 + c) * 3 + ky) * 3 + kx] * scale[n]);
+        return (uint32_t)*reinterpret_cast<const unsigned short*>(&h);
+    };
+    for (int ky = 0; ky < 3; ++ky)
+        for (int nt = 0; nt < NT; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+                uint32_t* f = &frag[((size_t)(ky * NT + nt) * 32 + lane) * 2];
+                f[0] = wt(n, ky, 2 * t) | (wt(n, ky, 2 * t + 1) << 16);
+                f[1] = wt(n, ky, 2 * t + 8) | (wt(n, ky, 2 * t + 9) << 16);
+            }
+}
+
+template <int NT>
+static void launch_stem(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, cudaStream_t st) {
+    dim3 grid((unsigned)((W / 2 + 63) / 64), (unsigned)((H / 2 + 7) / 8), (unsigned)B);
+    stem_conv_kernel<NT><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (const uint32_t*)w.w, w.b,
+                                               (__nv_bfloat16*)out, H, W, act);
 }
 
 // MaxPool2d(5, stride 1, pad 2) on a channel slice; thread = (pixel, 8-channel group).
@@ -117,6 +222,36 @@ __global__ void upsample2_kernel(const __nv_bfloat16* __restrict__ in, int in_ct
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(
         in + (((long long)b * H + (h >> 1)) * W + (w >> 1)) * in_ctot + in_coff + g * 8));
     *reinterpret_cast<uint4*>(out + pix * out_ctot + out_coff + g * 8) = v;
+}
+
+// Stand-alone stem launch for the parity tests (cy_stem_conv_nhwc4): w fp32 [cout,3,3,3] (OIHW), bias fp32 [cout].
+int stem_conv_run(const void* in, int B, int H, int W, const float* w_host, const float* bias_host, int cout, int act,
+                  void* out, cudaStream_t st) {
+    if (cout % 8 != 0 || cout < 16 || cout > 80 || (cout / 8) % 2 != 0)
+        return set_error(CY_ERR_INVALID, "stem: cout must be 16, 32, 48, 64 or 80 (got %d)", cout);
+    if (H % 2 != 0 || W % 32 != 0) return set_error(CY_ERR_INVALID, "stem: H must be even and W a multiple of 32");
+    std::vector<float> w(w_host, w_host + (size_t)cout * 27), scale(cout, 1.f);
+    std::vector<uint32_t> frag;
+    pack_stem_weights(w, scale, cout, frag);
+    ConvW cw;
+    cw.cout = cw.cout_pad = cout;
+    CY_CUDA_CHECK(cudaMalloc(&cw.w, frag.size() * sizeof(uint32_t)));
+    CY_CUDA_CHECK(cudaMalloc(&cw.b, cout * sizeof(float)));
+    CY_CUDA_CHECK(cudaMemcpyAsync(cw.w, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CY_CUDA_CHECK(cudaMemcpyAsync(cw.b, bias_host, cout * sizeof(float), cudaMemcpyHostToDevice, st));
+    switch (cout / 8) {
+        case 2: launch_stem<2>(in, cw, out, B, H, W, act, st); break;
+        case 4: launch_stem<4>(in, cw, out, B, H, W, act, st); break;
+        case 6: launch_stem<6>(in, cw, out, B, H, W, act, st); break;
+        case 8: launch_stem<8>(in, cw, out, B, H, W, act, st); break;
+        default: launch_stem<10>(in, cw, out, B, H, W, act, st); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(st);
+    cudaFree(cw.w);
+    cudaFree(cw.b);
+    if (e != cudaSuccess) return set_error(CY_ERR_CUDA, "stem launch failed: %s", cudaGetErrorString(e));
+    return CY_OK;
 }
 
 // ------------------------------------------------------------------------------------------ model
@@ -182,20 +317,14 @@ int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn) {
     }
     ConvW cw;
     cw.cin = cin; cw.cout = cout; cw.k = k;
-    if (cin == 3) {  // stem: packed bf16 [cout_pad][32], k = (kh*3+kw)*3 + c, zero for k >= 27 (1x1 conv over im2col)
-        const int bn_ = conv_block_n(cout);
-        cw.cout_pad = (cout + bn_ - 1) / bn_ * bn_;
-        std::vector<__nv_bfloat16> hw((size_t)cw.cout_pad * 32, __float2bfloat16(0.f));
-        for (int o = 0; o < cout; ++o)
-            for (int i = 0; i < 3; ++i)
-                for (int kh = 0; kh < 3; ++kh)
-                    for (int kw = 0; kw < 3; ++kw)
-                        hw[(size_t)o * 32 + (kh * 3 + kw) * 3 + i] =
-                            __float2bfloat16((*w)[((o * 3 + i) * 3 + kh) * 3 + kw] * scale[o]);
-        CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(__nv_bfloat16)));
-        CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
-        cw.cin = 32;
-        cw.k = 1;
+    if (cin == 3) {  // stem: mma.sync B fragments (pack_stem_weights), consumed by stem_conv_kernel
+        if (k != 3 || cout % 8 != 0 || cout > 80)
+            return set_error(CY_ERR_INVALID, "stem %s: expected a 3x3 conv with cout %% 8 == 0, cout <= 80", p.c_str());
+        cw.cout_pad = cout;
+        std::vector<uint32_t> frag;
+        pack_stem_weights(*w, scale, cout, frag);
+        CY_CUDA_CHECK(cudaMalloc(&cw.w, frag.size() * sizeof(uint32_t)));
+        CY_CUDA_CHECK(cudaMemcpy(cw.w, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     } else {
         const int bn_ = conv_block_n(cout);
         cw.cout_pad = (cout + bn_ - 1) / bn_ * bn_;
@@ -395,17 +524,16 @@ int Model::build_plan(int B, int Sh, int Sw, Plan** out) {
     Buf x21 = pb.alloc(H32, W32, c5);
     PB(!x0.p || !x1.p || !x2.p || !x3.p || !cat14.p || !x5.p || !cat11.p || !x7.p || !x8.p || !sp.p || !cat20.p ||
        !cat17.p || !x15.p || !x18.p || !x21.p);
-    {   // model.0 stem = im2col gather + 1x1 conv (K = 32) on the tensor pipe
-        Buf col = pb.alloc(H2, W2, 32);
-        PB(!col.p);
+    {   // model.0 stem: fused 3x3 stride-2 conv + bias + SiLU straight from the model input (stem_conv_kernel)
+        auto it0 = convs.find("model.0");
+        if (it0 == convs.end() || it0->second.cout != c1) snprintf(pb.err, sizeof(pb.err), "stem model.0 not loaded");
+        PB(it0 == convs.end() || it0->second.cout != c1);
         Op op;
-        op.type = Op::IM2COL; op.name = "model.0.im2col";
-        op.out = col;
+        op.type = Op::STEM; op.name = "model.0";
+        op.out = x0;
+        op.conv.flops = 2.0 * B * H2 * W2 * c1 * 27;
+        pl->flops += op.conv.flops;
         pl->ops.push_back(op);
-        PB(pb.conv("model.0", col, 0, x0, 0, 1));
-        const double f27 = 2.0 * B * H2 * W2 * c1 * 27;   // count the real 27 taps, not the zero padding
-        pl->flops += f27 - pl->ops.back().conv.flops;
-        pl->ops.back().conv.flops = f27;
     }
     Buf inb; inb.p = nullptr;
     PB(pb.conv("model.1", x0, 0, x1, 0, 2));
@@ -471,10 +599,18 @@ int Model::build_plan(int B, int Sh, int Sw, Plan** out) {
 
 int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaStream_t st) {
     switch (op.type) {
-        case Op::IM2COL: {
-            const long long npix = (long long)B * (Sh / 2) * (Sw / 2);
-            stem_im2col_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(
-                (const __nv_bfloat16*)in, (__nv_bfloat16*)op.out.p, B, Sh, Sw);
+        case Op::STEM: {
+            const ConvW& w = convs.at("model.0");
+            const char* ex = getenv("CY_CONV_SILU_EXACT");   // same switch as the conv kernel (1: tanh form, 2: ex2 + rcp)
+            const int act = (ex && atoi(ex)) ? 2 : 1;
+            switch (w.cout / 8) {
+                case 2: launch_stem<2>(in, w, op.out.p, B, Sh, Sw, act, st); break;
+                case 4: launch_stem<4>(in, w, op.out.p, B, Sh, Sw, act, st); break;
+                case 6: launch_stem<6>(in, w, op.out.p, B, Sh, Sw, act, st); break;
+                case 8: launch_stem<8>(in, w, op.out.p, B, Sh, Sw, act, st); break;
+                case 10: launch_stem<10>(in, w, op.out.p, B, Sh, Sw, act, st); break;
+                default: return set_error(CY_ERR_INVALID, "stem: unsupported cout %d", w.cout);
+            }
             break;
         }
         case Op::CONV: {
@@ -534,7 +670,7 @@ int Model::profile(const void* in, int B, int Sh, int Sw, int cap, const char** 
         cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
         if (ms) ms[i] = t;
         if (names) names[i] = pl->ops[i].name.c_str();
-        if (flops) flops[i] = pl->ops[i].type == Op::CONV ? pl->ops[i].conv.flops : 0.0;
+        if (flops) flops[i] = (pl->ops[i].type == Op::CONV || pl->ops[i].type == Op::STEM) ? pl->ops[i].conv.flops : 0.0;
     }
     for (auto& e : ev) cudaEventDestroy(e);
     if (nops) *nops = n;

@@ -18,13 +18,13 @@ struct Buf {
 };
 
 struct ConvW {
-    void* w = nullptr;   // packed bf16 [cout_pad, k*k*cin]  (stem: fp32 [27][cout])
+    void* w = nullptr;   // packed bf16 [cout_pad, k*k*cin]  (stem: mma.sync B fragments)
     float* b = nullptr;  // fp32 [cout_pad]
     int cin = 0, cout = 0, cout_pad = 0, k = 0;
 };
 
 struct Op {
-    enum Type { IM2COL, CONV, MAXPOOL, UPSAMPLE } type;
+    enum Type { STEM, CONV, MAXPOOL, UPSAMPLE } type;
     std::string name;
     ConvPlan conv;
     Buf in, out;

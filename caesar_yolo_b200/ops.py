@@ -123,6 +123,20 @@ def conv2d_nhwc(x, in_coff, cin, wp, bp, cout, k, s, out, out_coff, act=True, re
                              c_int(1 if act else 0), cur_stream()))
 
 
+def stem_conv(x, w_oihw, bias, act=1):
+    """Fused stem (cy_stem_conv_nhwc4): x [B,H,W,4] bf16 on the device, w [cout,3,3,3] / bias [cout] host fp32 (BN folded)
+    -> [B,H/2,W/2,cout] bf16."""
+    B, H, W, C = x.shape
+    assert C == 4 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    cout = int(w_oihw.shape[0])
+    w = np.ascontiguousarray(w_oihw.detach().cpu().float().numpy())
+    b = np.ascontiguousarray(bias.detach().cpu().float().numpy())
+    out = torch.empty((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=x.device)
+    check(lib.cy_stem_conv_nhwc4(ptr(x), c_int(B), c_int(H), c_int(W), _np_ptr(w), _np_ptr(b), c_int(cout),
+                                 c_int(int(act)), ptr(out), cur_stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ model
 
 class DeviceModel(object):

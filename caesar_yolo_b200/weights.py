@@ -1,14 +1,19 @@
 """YOLOv8 architecture table, seeded random-init weights (ultralytics state-dict key names) and the weight
 file format accepted by `--weights`.
 
-ultralytics is not installed in this environment, so real `.pt` checkpoints (which unpickle ultralytics classes)
-cannot be loaded; the `--weights` file of this build is a plain torch-saved dict
-{'format': 'caesar_yolo_b200-weights-v1', 'variant', 'nc', 'names', 'state_dict'} whose state_dict uses the
-ultralytics key names (model.0.conv.weight, model.0.bn.running_mean, ..., model.22.cv3.2.2.bias).
+`--weights` (scripts/run.py:347, `YOLO(weights_path)`) accepts
+  * an ultralytics YOLOv8 detection checkpoint (`.pt`: a pickled `{'model': DetectionModel, 'ema': ..., ...}`).  The
+    ultralytics package is NOT needed: `load_ultralytics_checkpoint` unpickles with stand-in classes for every module
+    that cannot be imported and reads the tensors out of the module tree (variant from the stem width, nc from the
+    class branch, names from `model.names`); Conv+BN already fused (`model.fuse()`) checkpoints are accepted too;
+  * this build's own file: a plain torch-saved dict
+    {'format': 'caesar_yolo_b200-weights-v1', 'variant', 'nc', 'names', 'state_dict'} whose state_dict uses the
+    ultralytics key names (model.0.conv.weight, model.0.bn.running_mean, ..., model.22.cv3.2.2.bias).
 """
 import json
 import math
 import os
+import pickle
 
 import torch
 
@@ -112,9 +117,111 @@ def save_weights(weights, path):
     torch.save(weights, path)
 
 
+class _StubPickle(object):
+    """`pickle_module` for torch.load: classes / functions whose module cannot be imported here (ultralytics.*, and
+    whatever a training environment left inside the checkpoint) become stand-in torch.nn.Module subclasses, so the
+    module tree — `_modules`, `_parameters`, `_buffers` live in the pickled `__dict__` — is rebuilt without their code."""
+    __name__ = 'caesar_yolo_b200._stub_pickle'
+    _cache = {}
+
+    @classmethod
+    def _stub(cls, module, name):
+        key = (module, name)
+        if key not in cls._cache:
+            def __init__(self, *args, **kwargs):
+                torch.nn.Module.__init__(self)
+            cls._cache[key] = type(name, (torch.nn.Module,), {'__module__': module, '__init__': __init__,
+                                                             '_caesar_stub': True})
+        return cls._cache[key]
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                return _StubPickle._stub(module, name)
+
+    load = staticmethod(pickle.load)
+    dump = staticmethod(pickle.dump)
+    Pickler = pickle.Pickler
+
+
+_STEM_WIDTH_TO_VARIANT = {16: 'n', 32: 's', 48: 'm', 64: 'l', 80: 'x'}
+
+
+def weights_from_state_dict(sd, names=None):
+    """ultralytics-keyed YOLOv8 detection state dict -> this build's weight dict.  Infers the variant from the stem
+    width and nc from the class branch, checks every tensor the device model needs (name and shape) and rewrites
+    fused Conv modules (conv.weight + conv.bias, no bn.*) as Conv + identity BN."""
+    sd = {k: v.detach().float().cpu() for k, v in sd.items() if torch.is_tensor(v)}
+    w0 = sd.get('model.0.conv.weight')
+    if w0 is None or w0.dim() != 4 or tuple(w0.shape[1:]) != (3, 3, 3) or int(w0.shape[0]) not in _STEM_WIDTH_TO_VARIANT:
+        raise ValueError("not a YOLOv8 detection checkpoint: model.0.conv.weight should be [16|32|48|64|80, 3, 3, 3]")
+    variant = _STEM_WIDTH_TO_VARIANT[int(w0.shape[0])]
+    head = sd.get('model.22.cv3.0.2.weight')
+    if head is None:
+        raise ValueError("not a YOLOv8 detection checkpoint: no Detect head at model.22 (yolo11 / segmentation / pose "
+                         "models are not supported by this build)")
+    nc = int(head.shape[0])
+    layers, cb, cc = conv_bn_layers(variant, nc)
+    out = {}
+
+    def need(key, shape):
+        t = sd.get(key)
+        if t is None:
+            raise ValueError("checkpoint does not match yolov8%s (nc=%d): missing tensor %s" % (variant, nc, key))
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("checkpoint does not match yolov8%s (nc=%d): %s has shape %s, expected %s"
+                             % (variant, nc, key, tuple(t.shape), tuple(shape)))
+        return t
+    for (p, cin, cout, k) in layers:
+        out[p + '.conv.weight'] = need(p + '.conv.weight', (cout, cin, k, k))
+        if p + '.bn.weight' in sd:
+            for f in ('weight', 'bias', 'running_mean', 'running_var'):
+                out['%s.bn.%s' % (p, f)] = need('%s.bn.%s' % (p, f), (cout,))
+        else:   # fused: y = conv(x) + bias.  Identity BN under eps = 1e-3: gamma / sqrt(var + eps) = 1
+            out[p + '.bn.weight'] = torch.ones(cout)
+            out[p + '.bn.bias'] = need(p + '.conv.bias', (cout,))
+            out[p + '.bn.running_mean'] = torch.zeros(cout)
+            out[p + '.bn.running_var'] = torch.full((cout,), 1.0 - 1e-3)
+    for l in range(3):
+        out['model.22.cv2.%d.2.weight' % l] = need('model.22.cv2.%d.2.weight' % l, (64, cb, 1, 1))
+        out['model.22.cv2.%d.2.bias' % l] = need('model.22.cv2.%d.2.bias' % l, (64,))
+        out['model.22.cv3.%d.2.weight' % l] = need('model.22.cv3.%d.2.weight' % l, (nc, cc, 1, 1))
+        out['model.22.cv3.%d.2.bias' % l] = need('model.22.cv3.%d.2.bias' % l, (nc,))
+    dfl = sd.get('model.22.dfl.conv.weight')
+    if dfl is not None and not torch.equal(dfl.flatten(), torch.arange(16, dtype=torch.float32)):
+        raise ValueError("model.22.dfl.conv.weight is not arange(16): unsupported DFL")
+    out['model.22.dfl.conv.weight'] = torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)
+    if names is None:
+        names = dict(CLASS_NAMES) if nc == len(CLASS_NAMES) else {i: 'class%d' % i for i in range(nc)}
+    elif not isinstance(names, dict):
+        names = {i: n for i, n in enumerate(names)}
+    names = {int(k): str(v) for k, v in names.items()}
+    if sorted(names) != list(range(nc)):
+        raise ValueError("checkpoint names %r do not cover nc=%d classes" % (names, nc))
+    return {'format': FORMAT, 'variant': variant, 'nc': nc, 'names': names, 'state_dict': out}
+
+
+def load_ultralytics_checkpoint(path):
+    """Reads an ultralytics YOLOv8 detection `.pt` without the ultralytics package (see _StubPickle).  Follows
+    ultralytics' own loader: the EMA model when present, else 'model'; weights converted to fp32 (they are stored as
+    fp16).  Also accepts a bare module or a bare state dict."""
+    ck = torch.load(path, map_location='cpu', weights_only=False, pickle_module=_StubPickle)
+    if isinstance(ck, dict) and ck.get('format') == FORMAT:
+        return ck
+    obj = ck
+    if isinstance(ck, dict) and ('model' in ck or 'ema' in ck):
+        obj = ck.get('ema') if ck.get('ema') is not None else ck.get('model')
+    if isinstance(obj, torch.nn.Module):
+        names = getattr(obj, 'names', None)
+        return weights_from_state_dict(obj.state_dict(), names)
+    if isinstance(obj, dict):
+        sd = obj.get('state_dict', obj)
+        return weights_from_state_dict(sd, obj.get('names') if isinstance(obj.get('names'), (dict, list)) else None)
+    raise ValueError("%s: unsupported checkpoint layout (%s)" % (path, type(obj).__name__))
+
+
 def load_weights(path):
-    w = torch.load(path, map_location='cpu', weights_only=False)
-    if not isinstance(w, dict) or w.get('format') != FORMAT:
-        raise ValueError("%s is not a %s file (ultralytics .pt checkpoints need the ultralytics package, "
-                         "which is not available in this environment)" % (path, FORMAT))
-    return w
+    """`--weights`: this build's weight file or an ultralytics YOLOv8 detection checkpoint."""
+    return load_ultralytics_checkpoint(path)

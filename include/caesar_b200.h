@@ -109,6 +109,14 @@ int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ctot, int in_
                    int out_coff, int out_f32, const void* res, int res_ctot, int res_coff, int act,
                    uintptr_t stream);
 
+/* Stem layer primitive (model.0 of yolov8.yaml: Conv(3, c1, k=3, s=2) + BN + SiLU; same reference call site): the
+ * model input [B,H,W,4] bf16 NHWC (4th channel ignored) -> [B,H/2,W/2,cout] bf16 in one fused kernel.  w_host is the
+ * HOST fp32 OIHW weight [cout,3,3,3] with BN folded, bias_host HOST fp32 [cout]; cout in {16,32,48,64,80}; act: 0 none,
+ * 1 SiLU (tanh form), 2 SiLU (ex2 + rcp).  Synchronises the stream (parity-test entry; the model plan keeps the
+ * packed weights resident). */
+int cy_stem_conv_nhwc4(const void* in, int B, int H, int W, const float* w_host, const float* bias_host, int cout,
+                       int act, void* out, uintptr_t stream);
+
 /* ------------------------------------------------------------------------------------------------ model
  * Replaces `YOLO(weights)` (scripts/run.py:347) and `model(image, ...)` (caesar_yolo/evaluation.py:181-193):
  * YOLOv8 n/s/m/l/x DetectionModel.forward with Conv+BN folded.  Tensors are given under their

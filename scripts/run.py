@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """CLI with the option surface of the reference's scripts/run.py (same flags, defaults, stage order, exit codes;
-scripts/run.py:58-155, 253-256, 272-302, 311-338), driving the B200 engine.  `--weights` takes a
-caesar_yolo_b200 weight file (see caesar_yolo_b200/weights.py).  Multi-GPU: launch with torchrun (one rank per GPU)
+scripts/run.py:58-155, 253-256, 272-302, 311-338), driving the B200 engine.  `--weights` takes an
+ultralytics YOLOv8 detection checkpoint (read without the ultralytics package) or a caesar_yolo_b200 weight file
+(caesar_yolo_b200/weights.py).  Multi-GPU: launch with torchrun (one rank per GPU)
 instead of mpirun; `--devices` defaults to cuda:0 here because this build has no CPU path."""
 import argparse
 import logging

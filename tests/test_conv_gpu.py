@@ -164,3 +164,31 @@ def test_conv_wide_pair_tiles_persistent():
     ops.check(ops.lib.cy_conv_plan_info(64, 20, 20, 256, 256, 3, 1, info))
     assert info[3] == 256 and info[0] == 10     # 20x20 maps: one box per tap (mode 0), pair, wide
     _run_case(B=64, H=20, W=20, cin=256, cout=256, k=3, s=1, act=True, res=True, out_f32=False, seed=62)
+
+
+@pytest.mark.parametrize("B,H,W,cout,act", [
+    (2, 64, 64, 16, 1),       # v8n stem, one partly filled 64-column block
+    (1, 640, 320, 64, 1),     # v8l stem on a 512 x 256 edge tile (Wo = 160: 2.5 column blocks)
+    (3, 96, 160, 32, 1),
+    (2, 32, 96, 48, 2),       # ex2 + rcp SiLU
+    (2, 64, 32, 80, 0),       # v8x width, no activation
+    (5, 320, 320, 64, 1),
+])
+def test_stem_conv_matches_torch(B, H, W, cout, act):
+    """Fused mma.sync stem (model.0: 3x3 stride-2 pad-1 conv on the NHWC-4 model input + bias + SiLU) vs torch fp32 on
+    the same bf16-rounded operands.  The 4th input channel must be ignored whatever it holds."""
+    from caesar_yolo_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + cout)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, H, W, 4, generator=g).to(torch.bfloat16)
+    x[..., 3] = 3.0   # garbage in the padding channel: its weights are zero
+    w = (torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn(cout, generator=g) * 0.1
+    got = ops.stem_conv(x.to(dev).contiguous(), w, b, act=act).float().cpu()
+    y = torch.nn.functional.conv2d(x[..., :3].float().permute(0, 3, 1, 2), w, b, stride=2, padding=1)
+    if act:
+        y = torch.nn.functional.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    assert got.shape == y.shape
+    err = (got - y).abs().max().item()
+    assert err < 2e-2 * max(1.0, y.abs().max().item()), (err, y.abs().max().item())
