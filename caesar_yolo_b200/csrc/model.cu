@@ -25,23 +25,36 @@ int conv_block_n(int cout);
 //   * K layout: k = ky*16 + kx*4 + c (c < 4 input channels of the NHWC-4 model input, 4th channel and kx = 3 carry
 //     zero weights) -> three K-steps, one per filter row; an A fragment register is then ONE aligned 32-bit shared
 //     memory load (two channels of one input pixel) and a warp's 32 loads are 128 contiguous bytes (no conflicts);
-//   * CTA = 8 warps = 8 output rows x 64 output columns; the 17 x 130 pixel input patch is staged in shared memory
+//   * CTA = 8 warps = 8 output rows x 64 output columns; the 17 x 132 pixel input patch is staged in shared memory
 //     once (halo overhead 7 %), warp w owns output row w as four 16-pixel M tiles;
 //   * epilogue: bias + SiLU (same tanh form as the conv kernel) -> bf16 -> per-warp staging rows (padded, conflict
 //     free) -> 16-byte stores; the 16 pixels of an M tile are 16*cout*2 contiguous bytes of the NHWC output.
+//   * persistent CTAs (two per SM) walk the (image, row block, column block) tiles; the patch of the NEXT tile is
+//     fetched with cp.async (8 bytes per pixel, zero fill outside the image = the conv padding) into the second
+//     patch buffer while the current one is being multiplied, so the global-load latency never stalls the warps and
+//     the weight fragments are read once per CTA.
+template <int NT>
+struct StemSmem {
+    static constexpr int kRows = 17, kCols = 132, kCout = 8 * NT, kStageW = kCout / 2 + 4;  // staging stride in words
+    uint2 patch[2][kRows][kCols];   // columns 2*ox0-2 .. 2*ox0+129: starts on an even pixel = 16-byte aligned chunks
+    uint32_t stage[8][16 * kStageW];
+    float bias[kCout];
+};
+
 template <int NT>  // cout = 8 * NT
 __global__ void __launch_bounds__(256, (NT <= 8 ? 2 : 1))
 stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
                  const uint32_t* __restrict__ wfrag,     // [3][NT][32][2] B fragments (see pack_stem_weights)
                  const float* __restrict__ bias,         // [8*NT]
                  __nv_bfloat16* __restrict__ out,        // [B,H/2,W/2,8*NT]
-                 int H, int W, int act) {
-    constexpr int kRows = 17, kCols = 130, kCout = 8 * NT, kStageW = kCout / 2 + 4;  // staging row stride in words
-    __shared__ __align__(16) uint2 patch[kRows][kCols];
-    __shared__ __align__(16) uint32_t stage[8][16 * kStageW];
-    __shared__ float sbias[kCout];
+                 int B, int H, int W, int act) {
+    using S = StemSmem<NT>;
+    constexpr int kRows = S::kRows, kCols = S::kCols, kCout = S::kCout, kStageW = S::kStageW;
+    extern __shared__ __align__(16) unsigned char stem_smem_raw[];
+    S& sm = *reinterpret_cast<S*>(stem_smem_raw);
     const int Ho = H >> 1, Wo = W >> 1;
-    const int ox0 = blockIdx.x * 64, oy0 = blockIdx.y * 8, b = blockIdx.z;
+    const int nbx = (Wo + 63) >> 6, nby = (Ho + 7) >> 3;
+    const long long ntiles = (long long)B * nby * nbx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     uint32_t wb[3][NT][2];
@@ -53,85 +66,109 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
             wb[ky][nt][0] = q.x;
             wb[ky][nt][1] = q.y;
         }
-    if (tid < kCout) sbias[tid] = bias[tid];
-    {
-        const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+    if (tid < kCout) sm.bias[tid] = bias[tid];
+
+    // asynchronous fetch of one tile's input patch (rows 2*oy0-1 .. +16, columns 2*ox0-2 .. +129) in 16-byte chunks
+    // (two pixels; W is even and chunks start on even columns, so a chunk is entirely inside or outside the image)
+    auto fetch = [&](long long tile, int buf) {
+        const int bx = (int)(tile % nbx), by = (int)((tile / nbx) % nby), b = (int)(tile / ((long long)nbx * nby));
+        const int iy0 = 16 * by - 1, ix0 = 128 * bx - 2;
         const uint2* src = reinterpret_cast<const uint2*>(in) + (long long)b * H * W;
-        for (int i = tid; i < kRows * kCols; i += 256) {
-            const int r = i / kCols, c = i - r * kCols;
+        constexpr int kChunks = kCols / 2;
+        for (int i = tid; i < kRows * kChunks; i += 256) {
+            const int r = i / kChunks, c = 2 * (i - r * kChunks);
             const int iy = iy0 + r, ix = ix0 + c;
-            uint2 q = make_uint2(0u, 0u);
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) q = __ldg(src + (long long)iy * W + ix);
-            patch[r][c] = q;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+            const uint2* g = ok ? src + (long long)iy * W + ix : src;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.patch[buf][r][c]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(ok ? 16 : 0) : "memory");
         }
-    }
-    __syncthreads();
-    const int oy = oy0 + warp;
-    if (oy >= Ho) return;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     const int g = lane >> 2, t = lane & 3;
-    uint32_t* st = stage[warp];
-    for (int mx = 0; mx < 4; ++mx) {
-        const int ox = ox0 + 16 * mx;
-        if (ox >= Wo) break;
-        float acc[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            // input row 2*oy - 1 + ky = patch row 2*warp + ky; output pixel p of the tile, tap kx: patch pixel
-            // 2*(16*mx + p) + kx; word index inside the row = 2 * pixel + channel pair
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(&patch[2 * warp + ky][0]) + 64 * mx + lane;
-            const uint32_t a0 = row[0], a1 = row[32], a2 = row[4], a3 = row[36];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-                asm volatile(
-                    "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-                    "{%0,%1,%2,%3};"
-                    : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
-                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wb[ky][nt][0]), "r"(wb[ky][nt][1]));
+    uint32_t* st = sm.stage[warp];
+    long long tile = blockIdx.x;
+    int buf = 0;
+    if (tile < ntiles) fetch(tile, 0);
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+            fetch(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        // epilogue: thread holds pixels g, g+8 x channels nt*8 + 2t, +1
-        float y[NT][4];
+        __syncthreads();   // patch[buf] (and, first time round, the bias) visible to every warp
+        const int bx = (int)(tile % nbx), by = (int)((tile / nbx) % nby), b = (int)(tile / ((long long)nbx * nby));
+        const int ox0 = 64 * bx, oy = 8 * by + warp;
+        if (oy < Ho) {
+            for (int mx = 0; mx < 4; ++mx) {
+                const int ox = ox0 + 16 * mx;
+                if (ox >= Wo) break;
+                float acc[NT][4];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const float2 bb = *reinterpret_cast<const float2*>(&sbias[nt * 8 + 2 * t]);
-            y[nt][0] = acc[nt][0] + bb.x; y[nt][1] = acc[nt][1] + bb.y;
-            y[nt][2] = acc[nt][2] + bb.x; y[nt][3] = acc[nt][3] + bb.y;
-        }
-        if (act == 1) {
-            float th[NT][4];
+                for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                for (int ky = 0; ky < 3; ++ky) {
+                    // input row 2*oy - 1 + ky = patch row 2*warp + ky; output pixel p of the M tile, tap kx: patch
+                    // pixel 2*(16*mx + p) + kx + 1; word index inside the row = 2 * pixel + channel pair
+                    const uint32_t* row = reinterpret_cast<const uint32_t*>(&sm.patch[buf][2 * warp + ky][0]) + 64 * mx + lane + 2;
+                    const uint32_t a0 = row[0], a1 = row[32], a2 = row[4], a3 = row[36];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    y[nt][j] *= 0.5f;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(th[nt][j]) : "f"(y[nt][j]));
+                    for (int nt = 0; nt < NT; ++nt)
+                        asm volatile(
+                            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+                            "{%8,%9}, {%0,%1,%2,%3};"
+                            : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wb[ky][nt][0]), "r"(wb[ky][nt][1]));
                 }
+                // epilogue: thread holds pixels g, g+8 x channels nt*8 + 2t, +1
+                // (SiLU tanh form: h = (acc + bias) / 2 exactly as the conv kernel computes it — the halving is exact)
+                float y[NT][4];
+                const float sc = act == 1 ? 0.5f : 1.0f;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NT; ++nt) {
+                    const float2 bb = *reinterpret_cast<const float2*>(&sm.bias[nt * 8 + 2 * t]);
+                    const float b0 = bb.x * sc, b1 = bb.y * sc;   // sc is a power of two: fma(acc, sc, b*sc) == (acc + b) * sc
+                    y[nt][0] = fmaf(acc[nt][0], sc, b0); y[nt][1] = fmaf(acc[nt][1], sc, b1);
+                    y[nt][2] = fmaf(acc[nt][2], sc, b0); y[nt][3] = fmaf(acc[nt][3], sc, b1);
+                }
+                if (act == 1) {
+                    float th[NT][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) y[nt][j] = fmaf(y[nt][j], th[nt][j], y[nt][j]);
-        } else if (act == 2) {
+                    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                        for (int j = 0; j < 4; ++j)
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(th[nt][j]) : "f"(y[nt][j]));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) y[nt][j] = __fdividef(y[nt][j], 1.0f + __expf(-y[nt][j]));
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) y[nt][j] = fmaf(y[nt][j], th[nt][j], y[nt][j]);
+                } else if (act == 2) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) y[nt][j] = __fdividef(y[nt][j], 1.0f + __expf(-y[nt][j]));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(y[nt][0], y[nt][1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(y[nt][2], y[nt][3]);
+                    st[g * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&lo);
+                    st[(g + 8) * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&hi);
+                }
+                __syncwarp();
+                uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * Ho + oy) * Wo + ox) * kCout);
+#pragma unroll
+                for (int v = lane; v < 16 * NT; v += 32) {
+                    const int p = v / NT, ch = v - p * NT;
+                    dst[v] = *reinterpret_cast<const uint4*>(&st[p * kStageW + ch * 4]);
+                }
+            }
         }
-        __syncwarp();
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(y[nt][0], y[nt][1]);
-            __nv_bfloat162 hi = __floats2bfloat162_rn(y[nt][2], y[nt][3]);
-            st[g * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&lo);
-            st[(g + 8) * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&hi);
-        }
-        __syncwarp();
-        uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * Ho + oy) * Wo + ox) * kCout);
-#pragma unroll
-        for (int v = lane; v < 16 * NT; v += 32) {
-            const int p = v / NT, ch = v - p * NT;
-            dst[v] = *reinterpret_cast<const uint4*>(&st[p * kStageW + ch * 4]);
-        }
+        __syncthreads();   // every warp is done with patch[buf] before the fetch of the tile after next refills it
     }
 }
 
@@ -159,10 +196,35 @@ static void pack_stem_weights(const std::vector<float>& w, const std::vector<flo
 }
 
 template <int NT>
-static void launch_stem(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, cudaStream_t st) {
-    dim3 grid((unsigned)((W / 2 + 63) / 64), (unsigned)((H / 2 + 7) / 8), (unsigned)B);
-    stem_conv_kernel<NT><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (const uint32_t*)w.w, w.b,
-                                               (__nv_bfloat16*)out, H, W, act);
+static int launch_stem(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, cudaStream_t st) {
+    static int ctas = 0;   // persistent grid: resident CTAs per SM x SMs of the current device
+    const int smem = (int)sizeof(StemSmem<NT>);
+    if (!ctas) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<NT>, 256, smem);
+        if (e != cudaSuccess || per_sm < 1 || sms < 1) return (int)(e != cudaSuccess ? e : cudaErrorLaunchOutOfResources);
+        ctas = per_sm * sms;
+    }
+    const long long ntiles = (long long)B * ((H / 2 + 7) / 8) * ((W / 2 + 63) / 64);
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, ctas);
+    stem_conv_kernel<NT><<<grid, 256, smem, st>>>((const __nv_bfloat16*)in, (const uint32_t*)w.w, w.b,
+                                                  (__nv_bfloat16*)out, B, H, W, act);
+    return 0;
+}
+
+static int launch_stem_any(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, cudaStream_t st) {
+    switch (w.cout / 8) {
+        case 2: return launch_stem<2>(in, w, out, B, H, W, act, st);
+        case 4: return launch_stem<4>(in, w, out, B, H, W, act, st);
+        case 6: return launch_stem<6>(in, w, out, B, H, W, act, st);
+        case 8: return launch_stem<8>(in, w, out, B, H, W, act, st);
+        case 10: return launch_stem<10>(in, w, out, B, H, W, act, st);
+        default: return (int)cudaErrorInvalidValue;
+    }
 }
 
 // MaxPool2d(5, stride 1, pad 2) on a channel slice; thread = (pixel, 8-channel group).
@@ -205,23 +267,73 @@ __global__ void maxpool5_kernel(const __nv_bfloat16* __restrict__ in, int in_cto
     *reinterpret_cast<uint4*>(out + pix * out_ctot + out_coff + g * 8) = o;
 }
 
-// nn.Upsample(scale_factor=2, mode='nearest') into a channel slice; thread = (output pixel, 8-channel group).
-__global__ void upsample2_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_coff,
-                                 __nv_bfloat16* __restrict__ out, int out_ctot, int out_coff, int B, int H, int W,
-                                 int C) {  // H, W = input extent
+// SPPF pooling chain in one kernel: y1 = m(x), y2 = m(y1), y3 = m(y2) with m = MaxPool2d(5, 1, 2), x = channel slice 0
+// of the SPPF concat buffer, y_k = slice k.  CTA = (image, 32 channels): the whole H x W map of those channels lives in
+// shared memory and every m is done separably (5-tap row max, then 5-tap column max; out-of-range taps are skipped =
+// the -inf padding), so x is read once from HBM and each y_k written once — instead of three 25-tap gathers through
+// L1.  bf16 max is exact: results are bit-identical to the per-stage kernel.
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, const uint4 b) {
+    __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pa[q] = __hmax2(pa[q], pb[q]);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) sppf_pool3_kernel(__nv_bfloat16* __restrict__ buf, int ctot, int C, int H, int W) {
+    extern __shared__ __align__(16) uint4 sppf_smem[];
+    const int n = H * W * 4;   // 16-byte vectors per buffer: (pixel, group of 8 channels), 4 groups = 32 channels
+    uint4 *cur = sppf_smem, *tmp = sppf_smem + n, *nxt = sppf_smem + 2 * n;
+    __nv_bfloat16* base = buf + (long long)blockIdx.y * H * W * ctot + blockIdx.x * 32;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        cur[i] = __ldg(reinterpret_cast<const uint4*>(base + (long long)(i >> 2) * ctot + (i & 3) * 8));
+    __syncthreads();
+    for (int stage = 1; stage <= 3; ++stage) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int pix = i >> 2, x = pix % W;
+            uint4 m = cur[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && x + d >= 0 && x + d < W) m = bf16x8_max(m, cur[i + 4 * d]);
+            tmp[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int pix = i >> 2, y = pix / W;
+            uint4 m = tmp[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && y + d >= 0 && y + d < H) m = bf16x8_max(m, tmp[i + 4 * d * W]);
+            nxt[i] = m;
+            *reinterpret_cast<uint4*>(base + (long long)pix * ctot + stage * C + (i & 3) * 8) = m;
+        }
+        __syncthreads();
+        uint4* t = cur; cur = nxt; nxt = t;
+    }
+}
+static constexpr int kSppfMaxSmem = 200 * 1024;
+
+// nn.Upsample(scale_factor=2, mode='nearest') into a channel slice; thread = (INPUT pixel, 8-channel group): one
+// 16-byte load, four 16-byte stores (the 2x2 output block), so the source is read exactly once.
+__global__ void __launch_bounds__(256) upsample2_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_coff,
+                                                        __nv_bfloat16* __restrict__ out, int out_ctot, int out_coff,
+                                                        int B, int H, int W, int C) {  // H, W = input extent
     const int groups = C / 8;
-    const int Ho = 2 * H, Wo = 2 * W;
-    const long long total = (long long)B * Ho * Wo * groups;
+    const long long total = (long long)B * H * W * groups;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int g = (int)(idx % groups);
-    long long pix = idx / groups;
-    const int w = (int)(pix % Wo);
-    const int h = (int)((pix / Wo) % Ho);
-    const int b = (int)(pix / ((long long)Wo * Ho));
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-        in + (((long long)b * H + (h >> 1)) * W + (w >> 1)) * in_ctot + in_coff + g * 8));
-    *reinterpret_cast<uint4*>(out + pix * out_ctot + out_coff + g * 8) = v;
+    const long long pix = idx / groups;           // (b*H + h)*W + w
+    const int w = (int)(pix % W);
+    const long long bh = pix / W;                 // b*H + h
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + pix * in_ctot + in_coff + g * 8));
+    const int Wo = 2 * W;
+    __nv_bfloat16* o = out + ((2 * bh) * Wo + 2 * w) * (long long)out_ctot + out_coff + g * 8;
+    const long long row = (long long)Wo * out_ctot;
+    *reinterpret_cast<uint4*>(o) = v;
+    *reinterpret_cast<uint4*>(o + out_ctot) = v;
+    *reinterpret_cast<uint4*>(o + row) = v;
+    *reinterpret_cast<uint4*>(o + row + out_ctot) = v;
 }
 
 // Stand-alone stem launch for the parity tests (cy_stem_conv_nhwc4): w fp32 [cout,3,3,3] (OIHW), bias fp32 [cout].
@@ -239,17 +351,12 @@ int stem_conv_run(const void* in, int B, int H, int W, const float* w_host, cons
     CY_CUDA_CHECK(cudaMalloc(&cw.b, cout * sizeof(float)));
     CY_CUDA_CHECK(cudaMemcpyAsync(cw.w, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CY_CUDA_CHECK(cudaMemcpyAsync(cw.b, bias_host, cout * sizeof(float), cudaMemcpyHostToDevice, st));
-    switch (cout / 8) {
-        case 2: launch_stem<2>(in, cw, out, B, H, W, act, st); break;
-        case 4: launch_stem<4>(in, cw, out, B, H, W, act, st); break;
-        case 6: launch_stem<6>(in, cw, out, B, H, W, act, st); break;
-        case 8: launch_stem<8>(in, cw, out, B, H, W, act, st); break;
-        default: launch_stem<10>(in, cw, out, B, H, W, act, st); break;
-    }
+    const int lrc = launch_stem_any(in, cw, out, B, H, W, act, st);
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(st);
     cudaFree(cw.w);
     cudaFree(cw.b);
+    if (lrc) e = (cudaError_t)lrc;
     if (e != cudaSuccess) return set_error(CY_ERR_CUDA, "stem launch failed: %s", cudaGetErrorString(e));
     return CY_OK;
 }
@@ -549,11 +656,18 @@ int Model::build_plan(int B, int Sh, int Sw, Plan** out) {
     PB(pb.c2f("model.8", x7, c5, n8, true, x8, 0));
     // SPPF
     PB(pb.conv("model.9.cv1", x8, 0, sp, 0, 1));
-    for (int i = 0; i < 3; ++i) {
-        Op op;
-        op.type = Op::MAXPOOL; op.name = "model.9.m";
-        op.in = sp; op.in_off = i * (c5 / 2); op.out = sp; op.out_off = (i + 1) * (c5 / 2); op.C = c5 / 2;
+    if ((size_t)3 * H32 * W32 * 64 <= (size_t)kSppfMaxSmem && (c5 / 2) % 32 == 0) {
+        Op op;   // the three max-pools of SPPF in one kernel (map resident in shared memory)
+        op.type = Op::SPPF_POOL; op.name = "model.9.m";
+        op.in = sp; op.out = sp; op.C = c5 / 2;
         pl->ops.push_back(op);
+    } else {
+        for (int i = 0; i < 3; ++i) {
+            Op op;
+            op.type = Op::MAXPOOL; op.name = "model.9.m";
+            op.in = sp; op.in_off = i * (c5 / 2); op.out = sp; op.out_off = (i + 1) * (c5 / 2); op.C = c5 / 2;
+            pl->ops.push_back(op);
+        }
     }
     PB(pb.conv("model.9.cv2", sp, 0, cat20, c4, 1));  // x9 -> cat20[:, c4:]
     {   // upsample x9 -> cat11[:, :c5]
@@ -603,14 +717,8 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
             const ConvW& w = convs.at("model.0");
             const char* ex = getenv("CY_CONV_SILU_EXACT");   // same switch as the conv kernel (1: tanh form, 2: ex2 + rcp)
             const int act = (ex && atoi(ex)) ? 2 : 1;
-            switch (w.cout / 8) {
-                case 2: launch_stem<2>(in, w, op.out.p, B, Sh, Sw, act, st); break;
-                case 4: launch_stem<4>(in, w, op.out.p, B, Sh, Sw, act, st); break;
-                case 6: launch_stem<6>(in, w, op.out.p, B, Sh, Sw, act, st); break;
-                case 8: launch_stem<8>(in, w, op.out.p, B, Sh, Sw, act, st); break;
-                case 10: launch_stem<10>(in, w, op.out.p, B, Sh, Sw, act, st); break;
-                default: return set_error(CY_ERR_INVALID, "stem: unsupported cout %d", w.cout);
-            }
+            const int e = launch_stem_any(in, w, op.out.p, B, Sh, Sw, act, st);
+            if (e) return set_error(CY_ERR_CUDA, "stem launch failed: %s", cudaGetErrorString((cudaError_t)e));
             break;
         }
         case Op::CONV: {
@@ -626,8 +734,20 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
                 op.in.H, op.in.W, op.C);
             break;
         }
+        case Op::SPPF_POOL: {
+            const int smem = 3 * op.in.H * op.in.W * 64;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(sppf_pool3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSppfMaxSmem);
+                if (e != cudaSuccess) return set_error(CY_ERR_CUDA, "sppf_pool3 attribute: %s", cudaGetErrorString(e));
+                attr_done = true;
+            }
+            sppf_pool3_kernel<<<dim3((unsigned)(op.C / 32), (unsigned)B), 256, smem, st>>>(
+                (__nv_bfloat16*)op.in.p, op.in.C, op.C, op.in.H, op.in.W);
+            break;
+        }
         case Op::UPSAMPLE: {
-            const long long total = (long long)B * op.in.H * 2 * op.in.W * 2 * (op.C / 8);
+            const long long total = (long long)B * op.in.H * op.in.W * (op.C / 8);
             upsample2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
                 (const __nv_bfloat16*)op.in.p, op.in.C, op.in_off, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, B,
                 op.in.H, op.in.W, op.C);

@@ -24,7 +24,7 @@ struct ConvW {
 };
 
 struct Op {
-    enum Type { STEM, CONV, MAXPOOL, UPSAMPLE } type;
+    enum Type { STEM, CONV, MAXPOOL, SPPF_POOL, UPSAMPLE } type;
     std::string name;
     ConvPlan conv;
     Buf in, out;

@@ -195,3 +195,43 @@ def test_merge_global_long_chain_and_area_ties():
     out, want = _run_global(tiles, per)
     _assert_catalog_equal(out, want)
     assert any(w['merged'] for w in want)
+
+
+def test_config5_dense_batch_matches_oracle():
+    """BASELINE.json configs[4]: a batch of imgsz-1024 tiles at scoreThr 0.05 with ~10k candidates per tile (21 504
+    anchors) through Detect decode -> NMS -> un-letterbox -> per-tile IoU merge.  The whole batch runs in one call;
+    sampled tiles (first, middle, last) must equal the oracle bit for bit (kept set, order, scores, classes; boxes up
+    to the expf rounding of the decode) and the merge keep lists must equal Analyzer.process_detections."""
+    from caesar_yolo_b200 import ops
+    from oracle import yolo as oy
+    B, S, nc, conf, iou = 64, 1024, 5, 0.05, 0.5
+    g = torch.Generator(device=DEV).manual_seed(42)
+    heads = []
+    for s in (8, 16, 32):
+        h = torch.zeros(B, S // s, S // s, 80, device=DEV)
+        h[..., :64] = torch.randn(B, S // s, S // s, 64, generator=g, device=DEV) * 2.0
+        h[..., 64:64 + nc] = torch.randn(B, S // s, S // s, nc, generator=g, device=DEV) * 1.5 - 4.7
+        heads.append(h)
+    _, _, lb = ops.letterbox_shape(512, 512, S)
+    lbd = ops.letterbox_array([lb] * B, DEV)
+    dets, nd = ops.postprocess(heads, B, S, S, nc, conf, iou, lbd, DEV)
+    keep, nkeep, status = ops.merge_tile(dets, nd, conf, 0.3, 0.8)
+    torch.cuda.synchronize()
+    ncand = sum(int((torch.sigmoid(h[..., 64:64 + nc]).amax(-1) > conf).sum()) for h in heads) / B
+    assert 8000 < ncand < 14000, ncand
+    assert int(nd.min()) == 300            # max_det reached on every tile
+    for b in (0, B // 2, B - 1):
+        pred = ops.decode_pred([h[b:b + 1].contiguous() for h in heads], 1, S, S, nc, DEV).cpu()[0]
+        want = oy.nms_single(pred, conf, iou)
+        want[:, :4] = oy.scale_boxes((S, S), want[:, :4], (512, 512))
+        got = dets[b, :int(nd[b])].cpu()
+        assert got.shape == want.shape
+        assert torch.equal(got[:, 4], want[:, 4]) and torch.equal(got[:, 5], want[:, 5])
+        assert torch.allclose(got[:, :4], want[:, :4], rtol=0, atol=2e-3)
+        try:
+            wk, _ = oracle_merge_tile(got.numpy(), conf, 0.3, 0.8)
+        except AssertionError:     # utils.get_iou asserts on a box clipped to zero extent: the tile fails (status -2)
+            assert int(status[b]) == -2
+            continue
+        assert int(status[b]) == 0
+        assert keep[b, :int(nkeep[b])].cpu().tolist() == list(wk)
