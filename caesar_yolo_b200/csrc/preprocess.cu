@@ -939,7 +939,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
     return src;
 }
 
-__global__ void __launch_bounds__(kSortThreads) pp_sort_kernel(const __grid_constant__ PPParams p) {
+__global__ void __launch_bounds__(kSortThreads, 2) pp_sort_kernel(const __grid_constant__ PPParams p) {
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
     SortSmem& sm = *reinterpret_cast<SortSmem*>(sort_smem_raw);
     __shared__ int s_n, s_nb;

@@ -101,3 +101,28 @@ def write_fits(data, path):
         f.write(hdr.encode("ascii"))
         f.write(payload)
         f.write(b"\0" * (-len(payload) % 2880))
+
+
+def read_raster(path):
+    """`matplotlib.pyplot.imread` restated over PIL (matplotlib is not a dependency of this build) for the PNG / JPG
+    branch of SFinder.run (caesar_yolo/inference.py:511-520).  PNG: float32 in [0, 1] — 8-bit samples / 255, 16-bit
+    grey / 65535, palette and grey+alpha images expanded to RGBA first (matplotlib.image._pil_png_to_float_array);
+    anything else (JPG): the uint8 array PIL decodes (matplotlib.image.pil_to_array)."""
+    from PIL import Image
+    with Image.open(path) as im:
+        im.load()
+        if im.format == 'PNG':
+            mode = im.mode
+            if mode == '1':
+                return np.asarray(im.convert('L'), dtype=np.float32) / np.float32(255)   # bool -> 0 / 1
+            if mode == 'L':
+                return np.divide(np.asarray(im), 2 ** 8 - 1, dtype=np.float32)
+            if mode.startswith('I;16') or mode == 'I':
+                a = np.asarray(im)
+                return np.divide(a, 2 ** 16 - 1, dtype=np.float32)
+            if mode == 'RGB':
+                return np.divide(np.asarray(im), 2 ** 8 - 1, dtype=np.float32)
+            return np.divide(np.asarray(im.convert('RGBA')), 2 ** 8 - 1, dtype=np.float32)   # P, LA, RGBA, ...
+        if im.mode in ('RGBA', 'RGBX', 'RGB', 'L'):
+            return np.asarray(im).copy()
+        return np.asarray(im.convert('RGBA')).copy()

@@ -82,12 +82,24 @@ class SFinder(object):
 
     def set_img_size_params(self):
         """inference.py:354-477 (pixel geometry only; WCS/beam metadata are not used by the catalog)."""
+        c = self.config
+        self.image_id = os.path.splitext(os.path.basename(os.path.abspath(c['image_path'])))[0]
+        if os.path.splitext(c['image_path'])[1] in ('.png', '.jpg'):   # inference.py:396-404: size from PIL
+            try:
+                from PIL import Image
+                with Image.open(c['image_path'], mode='r') as im:
+                    self.nx, self.ny = im.size
+            except Exception as e:
+                logger.error("Failed to read image size (err=%s)", e)
+                return -1
+            self.fits = None
+            self.xmin, self.xmax, self.ymin, self.ymax = 0, self.nx - 1, 0, self.ny - 1
+            return 0
         try:
             self.fits = FitsImage(self.config['image_path'])
         except Exception as e:
             logger.error("Failed to read image header (err=%s)", e)
             return -1
-        c = self.config
         xmin, xmax, ymin, ymax = c['image_xmin'], c['image_xmax'], c['image_ymin'], c['image_ymax']
         if xmin >= 0 and xmax >= 0 and ymin >= 0 and ymax >= 0 and not (xmin == xmax == ymin == ymax == 0):
             self.xmin, self.xmax, self.ymin, self.ymax = xmin, xmax, ymin, ymax
@@ -95,7 +107,6 @@ class SFinder(object):
         else:
             self.nx, self.ny = self.fits.nx, self.fits.ny
             self.xmin, self.xmax, self.ymin, self.ymax = 0, self.nx - 1, 0, self.ny - 1
-        self.image_id = os.path.splitext(os.path.basename(os.path.abspath(c['image_path'])))[0]
         return 0
 
     # ------------------------------------------------------------------------------------------------------
@@ -105,6 +116,12 @@ class SFinder(object):
         if self.set_img_size_params() < 0:
             return -1
         c = self.config
+        ext = os.path.splitext(c['image_path'])[1]
+        if ext in ('.png', '.jpg'):
+            return self._run_raster()
+        if ext != '.fits':
+            logger.error("Unsupported image format (%s) given!", ext)
+            return -1
         full = all(v in (0, -1) for v in (c['image_xmin'], c['image_xmax'], c['image_ymin'], c['image_ymax']))
         if full:
             x0, x1, y0, y1 = 0, self.fits.nx, 0, self.fits.ny
@@ -118,7 +135,7 @@ class SFinder(object):
         img = self.fits.rows(y0, y1)
         t0 = time.time()
         eng.begin(tiles)
-        dev_img = torch.from_numpy(np.ascontiguousarray(img).view(np.int32)).to(eng.device)
+        dev_img = torch.from_numpy(np.array(img, copy=True).view(np.int32)).to(eng.device)   # memmap rows are read-only
         eng.process_tiles(dev_img, self.fits.nx, self.fits.is_raw_f32, 0, y0, [0])
         packed, n = eng.finish()
         recs = packed.cpu().numpy().view(ops.REC_DTYPE)
@@ -127,6 +144,9 @@ class SFinder(object):
         recs = recs.copy()
         recs['x1'] -= x0; recs['x2'] -= x0; recs['y1'] -= y0; recs['y2'] -= y0
         self.timing['run_s'] = time.time() - t0
+        return self._save_serial(recs, status)
+
+    def _save_serial(self, recs, status):
         self.results = {"image_id": self.image_id, "objs": catalog.records_to_objs(recs, self.class_names)}
         if self.write_to_json:
             catalog.write_json(self.results, os.path.join(self.outdir, 'out_' + str(self.image_id) + '.json'))
@@ -135,10 +155,60 @@ class SFinder(object):
                               merged_key=False)
         return status
 
+    def _run_raster(self):
+        """PNG / JPG input of the serial path (inference.py:511-520): `plt.imread` semantics (read_raster), alpha
+        channel dropped.  A 2-D image, or one whose three channels are equal, takes the same batched tile path as a
+        FITS image (Analyzer.predict replicates a 2-D image into 3 channels, evaluation.py:146-154).  A colour image
+        goes straight to the letterbox + model stages; the CUDA preprocessing chain works on one plane, so colour
+        input together with --preprocessing is refused (-1) instead of being approximated."""
+        from .fits import read_raster
+        c = self.config
+        try:
+            a = read_raster(c['image_path'])
+        except Exception as e:
+            logger.error("Failed to read image %s (err=%s)", c['image_path'], e)
+            return -1
+        if a.ndim == 3 and a.shape[2] == 4:
+            a = a[:, :, :3]
+        if a.ndim == 3 and a.shape[2] != 3:
+            logger.error("Unsupported channel count %d in %s", a.shape[2], c['image_path'])
+            return -1
+        gray = a.ndim == 2 or (np.array_equal(a[:, :, 0], a[:, :, 1]) and np.array_equal(a[:, :, 0], a[:, :, 2]))
+        eng = self._engine()
+        H, W = a.shape[:2]
+        tiles = np.zeros(1, dtype=ops.TILE_DTYPE)
+        tiles[0] = (0, W, 0, H)
+        t0 = time.time()
+        eng.begin(tiles)
+        if gray:
+            plane = np.ascontiguousarray(a if a.ndim == 2 else a[:, :, 0], dtype=np.float32)
+            plane[~np.isfinite(plane)] = 0
+            eng.process_tiles(torch.from_numpy(plane).to(eng.device), W, False, 0, 0, [0])
+        else:
+            if eng.pp_cfg.enabled:
+                logger.error("Colour image with --preprocessing: the preprocessing chain of this build takes "
+                             "single-plane images (FITS, grey PNG/JPG)")
+                return -1
+            cube = np.ascontiguousarray(a, dtype=np.float32)
+            status = torch.zeros(1, dtype=torch.int32, device=eng.device)
+            # evaluation.py:171-176 (bug-compatible: image[i] is ROW i): a constant row 0..2 rejects the image
+            if any(cube[i].min() == cube[i].max() for i in range(min(3, H))):
+                status[0] = -1
+            x, _ = ops.letterbox_resize(torch.from_numpy(cube).to(eng.device).unsqueeze(0), eng.imgsz)
+            Sh, Sw, lb = ops.letterbox_shape(H, W, eng.imgsz)
+            eng._run_batch(x, status, torch.zeros(1, dtype=torch.int32, device=eng.device), H, W, Sh, Sw, lb)
+        packed, n = eng.finish()
+        recs = packed.cpu().numpy().view(ops.REC_DTYPE).copy()
+        self.timing['run_s'] = time.time() - t0
+        return self._save_serial(recs, 0)
+
     def run_parallel(self):
         """Tiled path (inference.py:578-658)."""
         t0 = time.time()
         if self.set_img_size_params() < 0:
+            return -1
+        if self.fits is None:   # tiles are cut with read_fits_crop in the reference (inference.py:190-195): FITS only
+            logger.error("Tiled runs need a FITS image")
             return -1
         c = self.config
         tiles = ops.generate_tiles(self.xmin, self.xmax, self.ymin, self.ymax, c['tile_xsize'], c['tile_ysize'],

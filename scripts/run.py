@@ -81,8 +81,8 @@ def validate_args(args):
     if not args.image.endswith(('.fits', '.png', '.jpg')):
         logger.error("Image must have .fits/.png/.jpg extension!")
         return -1
-    if not args.image.endswith('.fits'):
-        logger.error("Only FITS input is supported by the B200 path")
+    if not args.image.endswith('.fits') and args.split_img_in_tiles:
+        logger.error("Tiled runs need a FITS image (the reference reads tiles with read_fits_crop only)")
         return -1
     if args.maxnimgs == 0 or (args.maxnimgs < 0 and args.maxnimgs != -1):
         logger.error("Invalid maxnimgs given (hint: give -1 or >0)!")

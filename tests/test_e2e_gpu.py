@@ -302,3 +302,50 @@ def test_per_tile_outputs(tmp_path):
         img = np.asarray(f.raw)
         assert 0.0 <= img.min() and img.max() <= 255.0 and img.max() > 1.0
     assert n_obj >= len(cat) > 10      # merging only removes sources
+
+
+def test_png_input_serial_path(tmp_path):
+    """PNG / JPG input of SFinder.run (inference.py:511-520).  (1) a grey PNG and a FITS image holding the same float32
+    pixels give identical objects (same tile pipeline, plt.imread scaling v / 255); (2) a colour PNG without
+    preprocessing goes letterbox -> model -> process_detections like Analyzer.predict on the H x W x 3 array."""
+    from PIL import Image
+    from caesar_yolo_b200 import synth, weights as W
+    from caesar_yolo_b200.inference import SFinder
+    from caesar_yolo_b200.model import YOLO
+    from caesar_yolo_b200.preprocessing import ZScaleTransformer, MinMaxNormalizer, DataPreprocessor
+    from oracle import evaluation as oev
+    w = W.make_random_weights('n', 5, seed=0, cls_bias=-8.0)   # ~15-25 / ~10 detections (oracle) on these images
+    tile = synth.make_mosaic(256, 384, seed=11, nan_border_frac=0.0)
+    lo, hi = np.percentile(tile, 1), np.percentile(tile, 99.5)
+    g8 = np.clip((tile - lo) / (hi - lo) * 255, 0, 255).astype(np.uint8)
+    Image.fromarray(g8, 'L').save(str(tmp_path / 'img.png'))
+    synth.write_fits(str(tmp_path / 'imgf.fits'), (g8 / 255.0).astype(np.float32))
+    mk = lambda: DataPreprocessor([ZScaleTransformer(contrasts=[.25, .25, .25]), MinMaxNormalizer(norm_min=0, norm_max=255.)])
+    objs = {}
+    for name in ('img.png', 'imgf.fits'):
+        sf = SFinder(YOLO(w), _config(str(tmp_path / name), str(tmp_path), mk(), False))
+        assert sf.run() == 0
+        objs[name] = json.load(open(str(tmp_path / ('out_%s.json' % name.split('.')[0]))))['objs']
+    assert len(objs['img.png']) > 0
+    strip = lambda L: [{k: v for k, v in o.items()} for o in L]
+    assert strip(objs['img.png']) == strip(objs['imgf.fits'])
+    # (2) colour image, no preprocessing: values scaled so the network sees a 0..255 image
+    rgb = np.stack([g8, np.roll(g8, 5, 0), np.roll(g8, -7, 1)], -1)
+    Image.fromarray(rgb, 'RGB').save(str(tmp_path / 'col.jpg'), quality=100, subsampling=0)
+    from caesar_yolo_b200.fits import read_raster
+    cube = read_raster(str(tmp_path / 'col.jpg'))
+    assert cube.dtype == np.uint8 and cube.shape == (256, 384, 3)
+    wc = W.make_random_weights('n', 5, seed=0, cls_bias=-4.0)    # ~9 merged objects (oracle) on the colour image
+    sf = SFinder(YOLO(wc), _config(str(tmp_path / 'col.jpg'), str(tmp_path), None, False))
+    assert sf.run() == 0
+    got = json.load(open(str(tmp_path / 'out_col.json')))['objs']
+    an = oev.Analyzer(oy.OracleModel(wc, emulate_bf16=True), _config('col.jpg', str(tmp_path), None, False, devices=['cpu']))
+    assert an.predict(image=cube.astype(np.float32), image_id='col') == 0
+    want = an.results['objs']
+    print("colour jpg: ours %d objs, oracle %d" % (len(got), len(want)))
+    assert len(want) > 5
+    assert abs(len(got) - len(want)) <= max(2, len(want) // 4)
+    assert match_fraction(got, want) >= 0.6
+    # colour + preprocessing is refused rather than approximated
+    sf = SFinder(YOLO(w), _config(str(tmp_path / 'col.jpg'), str(tmp_path), mk(), False))
+    assert sf.run() == -1

@@ -119,3 +119,37 @@ def test_letterbox_shape_matches_oracle(shape):
     gain = min(Sh / Ty, Sw / Tx)
     assert info.gain == np.float32(gain)
     assert info.pad_x == round((Sw - Tx * gain) / 2 - 0.1) and info.pad_y == round((Sh - Ty * gain) / 2 - 0.1)
+
+
+def test_read_raster_follows_plt_imread(tmp_path):
+    """fits.read_raster restates matplotlib.pyplot.imread (inference.py:511-512): PNG -> float32 in [0,1] (8-bit / 255,
+    16-bit / 65535, palette / grey+alpha expanded to RGBA), JPG -> the decoded uint8 array."""
+    from PIL import Image
+    from caesar_yolo_b200.fits import read_raster
+    rng = np.random.default_rng(0)
+    g8 = rng.integers(0, 256, (7, 9), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (7, 9, 3), dtype=np.uint8)
+    rgba = rng.integers(0, 256, (7, 9, 4), dtype=np.uint8)
+    g16 = rng.integers(0, 65536, (7, 9), dtype=np.uint16)
+    p = lambda n: str(tmp_path / n)
+    Image.fromarray(g8, 'L').save(p('g8.png'))
+    Image.fromarray(rgb, 'RGB').save(p('rgb.png'))
+    Image.fromarray(rgba, 'RGBA').save(p('rgba.png'))
+    Image.fromarray(g16).save(p('g16.png'))
+    Image.fromarray(g8, 'L').convert('P').save(p('pal.png'))
+    Image.fromarray(g8, 'L').save(p('g8.jpg'), quality=95)
+    Image.fromarray(rgb, 'RGB').save(p('rgb.jpg'), quality=95)
+    a = read_raster(p('g8.png'))
+    assert a.dtype == np.float32 and a.shape == (7, 9) and np.array_equal(a, (g8 / 255.0).astype(np.float32))
+    a = read_raster(p('rgb.png'))
+    assert a.dtype == np.float32 and np.array_equal(a, (rgb / 255.0).astype(np.float32))
+    a = read_raster(p('rgba.png'))
+    assert a.shape == (7, 9, 4) and np.array_equal(a, (rgba / 255.0).astype(np.float32))
+    a = read_raster(p('g16.png'))
+    assert a.dtype == np.float32 and np.array_equal(a, (g16 / 65535.0).astype(np.float32))
+    a = read_raster(p('pal.png'))
+    assert a.shape == (7, 9, 4) and np.array_equal(a[..., 0], (g8 / 255.0).astype(np.float32)) and (a[..., 3] == 1).all()
+    a = read_raster(p('g8.jpg'))
+    assert a.dtype == np.uint8 and a.shape == (7, 9)
+    a = read_raster(p('rgb.jpg'))
+    assert a.dtype == np.uint8 and a.shape == (7, 9, 3)
