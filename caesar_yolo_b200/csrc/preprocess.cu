@@ -64,6 +64,7 @@ struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per
     double cdf[256];
     double center[256];   // (edges[k] + edges[k+1]) / 2
     double slope[256];    // (cdf[k+1] - cdf[k]) / (center[k+1] - center[k]), k < 255: the division np.interp does
+    double inv_step;      // 255 / (center[255] - center[0]) (0 when the range is empty): bracket guess of the fast lookup
 };
 
 struct PPParams {
@@ -224,8 +225,7 @@ __device__ __forceinline__ double histeq_interp_fast(const HistEq& h, double v) 
     const double c0 = h.center[0], c255 = h.center[255];
     if (!(v > c0)) return h.cdf[0];
     if (v >= c255) return h.cdf[255];
-    const double step = (c255 - c0) / 255.0;
-    int lo = step > 0.0 ? (int)((v - c0) / step) : 0;
+    int lo = (int)((v - c0) * h.inv_step);   // a guess only: the two loops below make the bracket exact
     lo = max(0, min(254, lo));
     while (lo > 0 && h.center[lo] > v) --lo;
     while (lo < 254 && h.center[lo + 1] <= v) ++lo;
@@ -429,12 +429,25 @@ __device__ void range_sums(const Chan& c, const Comp& cc, const HistEq& he, cons
             const int seg_end = (zi < c.nz && c.z0[zi] < end) ? c.z0[zi] : end;
             if (threadIdx.x == 0) n += (double)(seg_end - pos);
             if (simple) {
-#pragma unroll 4
-                for (int i = pos + threadIdx.x; i < seg_end; i += kPPThreads) {
+                // two independent accumulator pairs: the DADD / DFMA dependency chains were the stall of this loop
+                double u1 = 0.0, q1 = 0.0;
+                int i = pos + threadIdx.x;
+                for (; i + kPPThreads < seg_end; i += 2 * kPPThreads) {
+                    const float x0 = S[i], x1 = S[i + kPPThreads];
+                    const double d0 = fmin(fmax(fma(cc.a0, (double)x0, bp), lp), hp);
+                    const double d1 = fmin(fmax(fma(cc.a0, (double)x1, bp), lp), hp);
+                    u += d0;
+                    q = fma(d0, d0, q);
+                    u1 += d1;
+                    q1 = fma(d1, d1, q1);
+                }
+                if (i < seg_end) {
                     const double d = fmin(fmax(fma(cc.a0, (double)S[i], bp), lp), hp);
                     u += d;
                     q = fma(d, d, q);
                 }
+                u += u1;
+                q += q1;
             } else {
 #pragma unroll 2
                 for (int i = pos + threadIdx.x; i < seg_end; i += kPPThreads) {
@@ -739,6 +752,10 @@ __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const
         sh.he.slope[i] = i < 255 ? __ddiv_rn(__dsub_rn(sh.he.cdf[i + 1], sh.he.cdf[i]),
                                             __dsub_rn(sh.he.center[i + 1], sh.he.center[i]))
                                  : 0.0;
+    if (threadIdx.x == 0) {
+        const double step = (sh.he.center[255] - sh.he.center[0]) / 255.0;
+        sh.he.inv_step = step > 0.0 ? 1.0 / step : 0.0;
+    }
     __syncthreads();
     push_op(sh, ci, S, n, OP_HISTEQ, 0.0, 0.0, 0.0, 0.0);
 }
@@ -816,8 +833,10 @@ __device__ __forceinline__ void scan256_warp0(const int* a, int* out) {
 __device__ long long* g_sort_dbg = nullptr;   // optional phase timing (clock64 sums of thread 0 of block 0), tools only
 #define SORT_T(k) do { if (dbg) { const long long _c = clock64(); dbg[k] += _c - tprev; tprev = _c; } } while (0)
 
-// Returns the buffer (a or b) that holds the sorted keys.
-__device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem& sm) {
+// Returns the buffer (a or b) that holds the sorted keys.  *as_float is set when the top-digit pass moved the keys (it
+// then wrote them back as fp32 bit patterns, key2f fused into its write-out: no separate conversion pass).
+__device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem& sm, bool* as_float) {
+    *as_float = false;
     long long* dbg = (g_sort_dbg && blockIdx.x == 0 && threadIdx.x == 0) ? g_sort_dbg : nullptr;
     long long tprev = dbg ? clock64() : 0;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -923,7 +942,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
                 if (j < m) {
                     const uint32_t k = sm.sorted[j];
                     const uint32_t d = (k >> shift) & 255u;
-                    dst[sm.gcur[d] + (j - sm.dbase[d])] = k;
+                    dst[sm.gcur[d] + (j - sm.dbase[d])] = more ? k : __float_as_uint(key2f(k));
                     if (more) atomicAdd(&nh_next[(k >> (shift + 8)) & 255u], 1);
                 }
             }
@@ -931,6 +950,7 @@ __device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem&
             SORT_T(6);
             if (t < 256) sm.gcur[t] += sm.dtot[t];
         }
+        if (!more) *as_float = true;
         __syncthreads();
         uint32_t* x = src;
         src = dst;
@@ -990,14 +1010,24 @@ __global__ void __launch_bounds__(kSortThreads, 2) pp_sort_kernel(const __grid_c
     }
     __syncthreads();
     const int n = s_n, nb = s_nb;
+    // sorted keys -> fp32 values in `out`; usually nothing is left to do (four moving passes end in `out`, already
+    // converted by the last one)
+    auto finish = [&](const uint32_t* r, bool as_float, uint32_t* out, int cnt) {
+        if (as_float && r == out) return;
+        for (int i = threadIdx.x; i < cnt; i += kSortThreads) {
+            const uint32_t k = r[i];
+            out[i] = as_float ? k : __float_as_uint(key2f(k));
+        }
+    };
+    bool as_float;
     {
-        const uint32_t* r = block_radix_sort(A, Bk, n, sm);
-        for (int i = threadIdx.x; i < n; i += kSortThreads) A[i] = __float_as_uint(key2f(r[i]));
+        const uint32_t* r = block_radix_sort(A, Bk, n, sm, &as_float);
+        finish(r, as_float, A, n);
     }
     if (C) {
         __syncthreads();
-        const uint32_t* r = block_radix_sort(C, Bk, nb, sm);
-        for (int i = threadIdx.x; i < nb; i += kSortThreads) C[i] = __float_as_uint(key2f(r[i]));
+        const uint32_t* r = block_radix_sort(C, Bk, nb, sm, &as_float);
+        finish(r, as_float, C, nb);
     }
     if (threadIdx.x == 0) {
         p.nlive[b] = n;
@@ -1154,19 +1184,31 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
     }
     const bool same01 = sh.ch[0].hid == sh.ch[1].hid, same02 = sh.ch[0].hid == sh.ch[2].hid,
                same12 = sh.ch[1].hid == sh.ch[2].hid;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < N; i += kPPThreads) {
-        const float xf = tile[i];
-        const double x = (double)xf;
-        const double v0 = in_zero_x(sh.cc[0], xf) ? 0.0 : eval_fast(sh.cc[0], sh.ch[0], sh.he, x);
-        const double v1 = same01 ? v0 : (in_zero_x(sh.cc[1], xf) ? 0.0 : eval_fast(sh.cc[1], sh.ch[1], sh.he, x));
-        const double v2 = same02 ? v0
-                                 : (same12 ? v1
-                                           : (in_zero_x(sh.cc[2], xf) ? 0.0
-                                                                      : eval_fast(sh.cc[2], sh.ch[2], sh.he, x)));
-        out[(long long)i * 3 + 0] = (float)v0;
-        out[(long long)i * 3 + 1] = (float)v1;
-        out[(long long)i * 3 + 2] = (float)v2;
+    {
+        const float* __restrict__ tin = tile;
+        float* __restrict__ tout = out;
+        auto eval3 = [&](float xf, int i) {
+            const double x = (double)xf;
+            const double v0 = in_zero_x(sh.cc[0], xf) ? 0.0 : eval_fast(sh.cc[0], sh.ch[0], sh.he, x);
+            const double v1 = same01 ? v0 : (in_zero_x(sh.cc[1], xf) ? 0.0 : eval_fast(sh.cc[1], sh.ch[1], sh.he, x));
+            const double v2 = same02 ? v0
+                                     : (same12 ? v1
+                                               : (in_zero_x(sh.cc[2], xf) ? 0.0
+                                                                          : eval_fast(sh.cc[2], sh.ch[2], sh.he, x)));
+            tout[(long long)i * 3 + 0] = (float)v0;
+            tout[(long long)i * 3 + 1] = (float)v1;
+            tout[(long long)i * 3 + 2] = (float)v2;
+        };
+        // four independent loads in flight per thread before the (long) evaluation of each pixel
+        int i = threadIdx.x;
+        for (; i + 3 * kPPThreads < N; i += 4 * kPPThreads) {
+            const float x0 = tin[i], x1 = tin[i + kPPThreads], x2 = tin[i + 2 * kPPThreads], x3 = tin[i + 3 * kPPThreads];
+            eval3(x0, i);
+            eval3(x1, i + kPPThreads);
+            eval3(x2, i + 2 * kPPThreads);
+            eval3(x3, i + 3 * kPPThreads);
+        }
+        for (; i < N; i += kPPThreads) eval3(tin[i], i);
     }
     int bad = 0;
     for (int r = 0; r < 3 && r < p.Ty; ++r) {
@@ -1197,12 +1239,11 @@ struct ResizeParams {
 };
 
 __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)r.B * r.Sh * r.Sw;
-    if (idx >= total) return;
-    const int ox = (int)(idx % r.Sw);
-    const int oy = (int)((idx / r.Sw) % r.Sh);
-    const int b = (int)(idx / ((long long)r.Sw * r.Sh));
+    // grid = (column blocks, output rows, tiles): no 64-bit div/mod per pixel (they were 40 % of this kernel's stalls)
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    if (ox >= r.Sw) return;
+    const long long idx = ((long long)b * r.Sh + oy) * r.Sw + ox;
     float v[3] = {114.f, 114.f, 114.f};  // cv2.copyMakeBorder value
     const int ry = oy - r.top, rx = ox - r.left;
     if (ry >= 0 && ry < r.new_h && rx >= 0 && rx < r.new_w) {
@@ -1335,8 +1376,8 @@ extern "C" int cy_letterbox_resize(const float* chain, int B, int Ty, int Tx, in
     r.left = (int)nearbyint(((imgsz - r.new_w) % 32) / 2.0 - 0.1);
     r.scale_x = 1.0 / ((double)r.new_w / (double)Tx);
     r.scale_y = 1.0 / ((double)r.new_h / (double)Ty);
-    const long long total = (long long)B * Sh * Sw;
-    pp_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r);
+    if (Sh > 65535 || B > 65535) return set_error(CY_ERR_INVALID, "cy_letterbox_resize: batch or image too large");
+    pp_resize_kernel<<<dim3((unsigned)((Sw + 255) / 256), (unsigned)Sh, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(r);
     CY_CUDA_CHECK(cudaGetLastError());
     return CY_OK;
 }
