@@ -349,3 +349,4 @@ def test_png_input_serial_path(tmp_path):
     # colour + preprocessing is refused rather than approximated
     sf = SFinder(YOLO(w), _config(str(tmp_path / 'col.jpg'), str(tmp_path), mk(), False))
     assert sf.run() == -1
+
