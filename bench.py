@@ -24,7 +24,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ['NCCL_DEBUG'] = 'WARN'   # NCCL_DEBUG=VERSION/INFO print to stdout; the contract is ONE JSON line there
+os.environ['NCCL_DEBUG'] = 'WARN'   # keep warnings; the banner it prints is kept off stdout below
+
+# The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there at WARN/INFO), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 PP_FLAGS = dict(subtract_bkg=True, clip_data=True, zscale_stretch=True, chan3_preproc=True, normalize_minmax=True,
                 nchannels=3, norm_max=255.)
@@ -178,7 +189,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mpix_per_s": v * args.tile * args.tile / 1e6}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -333,7 +344,7 @@ def main():
         v, dt, nt = cpu_reference(args, img_native, args.cpu_tiles, threads)
         line["cpu_baseline"] = {"value": v, "unit": "tiles/s", "cores": threads, "kind": "port",
                                 "sample": "%d tiles of the same mosaic (top-left sub-mosaic), oracle SFinder.run_parallel FITS->catalog in %.1f s, torch CPU fp32 batch 1, logging silenced" % (nt, dt)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
