@@ -223,6 +223,7 @@ static int launch_stem_any(const void* in, const ConvW& w, void* out, int B, int
         case 6: return launch_stem<6>(in, w, out, B, H, W, act, st);
         case 8: return launch_stem<8>(in, w, out, B, H, W, act, st);
         case 10: return launch_stem<10>(in, w, out, B, H, W, act, st);
+        case 12: return launch_stem<12>(in, w, out, B, H, W, act, st);
         default: return (int)cudaErrorInvalidValue;
     }
 }
@@ -336,11 +337,162 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const __nv_bfloat16* __r
     *reinterpret_cast<uint4*>(o + row + out_ctot) = v;
 }
 
+// Depthwise 3x3 conv (stride 1, pad 1) + bias (+ SiLU) (+ residual) on NHWC bf16; thread = (pixel, 8 channels).
+// yolo11: DWConv of the Detect class branch and the `pe` positional conv of the attention block (which reads v
+// straight out of the qkv tensor: logical channel c -> input channel in_off + (c / gs) * gst + c % gs).  HBM-bound.
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_off,
+                                                        int gs, int gst, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                        int out_ctot, int out_off, const __nv_bfloat16* __restrict__ res,
+                                                        int res_ctot, int res_off, int H, int W, int C, int act) {
+    const int groups = C / 8;
+    const int x = blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups;   // blockDim.x is a multiple of groups
+    const int g = threadIdx.x % groups;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const int c0 = g * 8;
+    const int ci = in_off + (c0 / gs) * gst + (c0 % gs);
+    float acc[8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = x + kx - 1;
+            if (ix < 0 || ix >= W) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + iy) * W + ix) * in_ctot + ci));
+            const float* wt = w + (ky * 3 + kx) * C + c0;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt)), w1 = __ldg(reinterpret_cast<const float4*>(wt + 4));
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const float2 f0 = __bfloat1622float2(pv[0]), f1 = __bfloat1622float2(pv[1]), f2 = __bfloat1622float2(pv[2]),
+                         f3 = __bfloat1622float2(pv[3]);
+            acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
+            acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
+            acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
+            acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (act == 1) {   // the conv kernel's SiLU: h + h * tanh(h), h = y / 2
+                const float h = 0.5f * acc[j];
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+                acc[j] = fmaf(h, t, h);
+            } else {
+                acc[j] = __fdividef(acc[j], 1.0f + __expf(-acc[j]));
+            }
+        }
+    }
+    const long long pix = ((long long)b * H + y) * W + x;
+    if (res) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + pix * res_ctot + res_off + c0));
+        const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(pr[q]);
+            acc[2 * q] += f.x;
+            acc[2 * q + 1] += f.y;
+        }
+    }
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) po[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+    *reinterpret_cast<uint4*>(out + pix * out_ctot + out_off + c0) = o;
+}
+
+// Multi-head self-attention of the yolo11 PSA block over the N = H*W positions of one image (N = 400 at imgsz 640):
+// qkv [B,N,nh*128] bf16 with per head 32 q | 32 k | 64 v channels -> out [B,N,nh*64] bf16 slice,
+// out[n, head*64 + d] = sum_m softmax_m(q_n . k_m / sqrt(32)) v[m, d].  CTA = (64 queries, head, image): K and V of the
+// head sit in shared memory (K rows padded to 17 words: conflict-free when 32 lanes read 32 different keys), one warp
+// per query: scores -> shared memory, warp-shuffle max / sum, then every lane accumulates two of the 64 output
+// channels.  fp32 arithmetic on CUDA cores: 0.12 GFLOP per image of the 87 GFLOP model, so it is kept simple.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ctot,
+                                                                __nv_bfloat16* __restrict__ out, int out_ctot, int out_off,
+                                                                int N) {
+    extern __shared__ __align__(16) uint32_t attn_smem[];
+    uint32_t* sk = attn_smem;                 // [N][17] bf16x2 words (16 used)
+    uint32_t* sv = sk + (size_t)N * 17;       // [N][32] bf16x2 words
+    float* sp = reinterpret_cast<float*>(sv + (size_t)N * 32);   // [WARPS][N]
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __nv_bfloat16* base = qkv + (long long)b * N * qkv_ctot + head * 128;
+    for (int i = threadIdx.x; i < N * 16; i += WARPS * 32) {
+        const int m = i >> 4, wd = i & 15;
+        sk[m * 17 + wd] = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)m * qkv_ctot + 32) + wd);
+    }
+    for (int i = threadIdx.x; i < N * 32; i += WARPS * 32) {
+        const int m = i >> 5, wd = i & 31;
+        sv[i] = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)m * qkv_ctot + 64) + wd);
+    }
+    __syncthreads();
+    float* p = sp + (size_t)warp * N;
+    const float scale = 0.17677669529663687f;   // 32^-0.5
+    const int q_end = min(N, (int)(blockIdx.x + 1) * 64);
+    for (int n = blockIdx.x * 64 + warp; n < q_end; n += WARPS) {
+        float2 q[16];
+        {
+            const uint32_t* qp = reinterpret_cast<const uint32_t*>(base + (long long)n * qkv_ctot);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t u = __ldg(qp + j);
+                q[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+            }
+        }
+        float mx = -INFINITY;
+        for (int m = lane; m < N; m += 32) {
+            const uint32_t* kr = sk + m * 17;
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t u = kr[j];
+                const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+                sacc = fmaf(q[j].x, kf.x, sacc);
+                sacc = fmaf(q[j].y, kf.y, sacc);
+            }
+            sacc *= scale;
+            p[m] = sacc;
+            mx = fmaxf(mx, sacc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int m = lane; m < N; m += 32) {
+            const float e = __expf(p[m] - mx);
+            p[m] = e;
+            sum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncwarp();
+        float o0 = 0.f, o1 = 0.f;
+        for (int m = 0; m < N; ++m) {
+            const float pm = p[m];
+            const uint32_t u = sv[m * 32 + lane];
+            const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+            o0 = fmaf(pm, vf.x, o0);
+            o1 = fmaf(pm, vf.y, o1);
+        }
+        const float inv = 1.0f / sum;
+        const __nv_bfloat162 ov = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * N + n) * out_ctot + out_off + head * 64 + 2 * lane) = ov;
+        __syncwarp();
+    }
+}
+
 // Stand-alone stem launch for the parity tests (cy_stem_conv_nhwc4): w fp32 [cout,3,3,3] (OIHW), bias fp32 [cout].
 int stem_conv_run(const void* in, int B, int H, int W, const float* w_host, const float* bias_host, int cout, int act,
                   void* out, cudaStream_t st) {
-    if (cout % 8 != 0 || cout < 16 || cout > 80 || (cout / 8) % 2 != 0)
-        return set_error(CY_ERR_INVALID, "stem: cout must be 16, 32, 48, 64 or 80 (got %d)", cout);
+    if (cout % 16 != 0 || cout < 16 || cout > 96)
+        return set_error(CY_ERR_INVALID, "stem: cout must be 16, 32, 48, 64, 80 or 96 (got %d)", cout);
     if (H % 2 != 0 || W % 32 != 0) return set_error(CY_ERR_INVALID, "stem: H must be even and W a multiple of 32");
     std::vector<float> w(w_host, w_host + (size_t)cout * 27), scale(cout, 1.f);
     std::vector<uint32_t> frag;
@@ -368,6 +520,28 @@ static int make_divisible(double x, int d) { return (int)(ceil(x / d) * d); }
 int Model::init(const char* variant, int nc_) {
     double depth, width;
     int maxc;
+    if (variant[0] == '1' && variant[1] == '1') {   // yolo11{n,s,m,l,x}: cfg/models/11/yolo11.yaml scales
+        switch (variant[2]) {
+            case 'n': depth = 0.50; width = 0.25; maxc = 1024; break;
+            case 's': depth = 0.50; width = 0.50; maxc = 1024; break;
+            case 'm': depth = 0.50; width = 1.00; maxc = 512; break;
+            case 'l': depth = 1.00; width = 1.00; maxc = 512; break;
+            case 'x': depth = 1.00; width = 1.50; maxc = 512; break;
+            default: return set_error(CY_ERR_INVALID, "unknown YOLO11 variant '%s'", variant);
+        }
+        auto ch11 = [&](int c) { return make_divisible(std::min(c, maxc) * width, 8); };
+        family = 11;
+        this->variant = variant[2];
+        w64 = ch11(64); w128 = ch11(128); w256 = ch11(256); w512 = ch11(512); w1024 = ch11(1024);
+        n11 = std::max((int)lround(2 * depth), 1);
+        c3k11 = variant[2] == 'm' || variant[2] == 'l' || variant[2] == 'x';
+        nc = nc_;
+        if (nc < 1 || nc > 16) return set_error(CY_ERR_INVALID, "nc must be in [1,16] (got %d)", nc);
+        c1 = w64; c3 = w256; c4 = w512; c5 = w1024; c2 = w128;
+        cb = std::max(16, std::max(w256 / 4, 64));
+        cc = std::max(w256, std::min(nc, 100));
+        return CY_OK;
+    }
     switch (variant[0]) {
         case 'n': depth = 0.33; width = 0.25; maxc = 1024; break;
         case 's': depth = 0.33; width = 0.50; maxc = 1024; break;
@@ -401,7 +575,7 @@ const std::vector<float>* Model::get(const std::string& k) const {
 
 static inline float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn) {
+int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn, int cin_pad) {
     const std::vector<float>* w = get(bn ? p + ".conv.weight" : p + ".weight");
     if (!w) return set_error(CY_ERR_STATE, "missing tensor %s", (p + (bn ? ".conv.weight" : ".weight")).c_str());
     if ((long long)w->size() != (long long)cout * cin * k * k)
@@ -425,24 +599,28 @@ int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn) {
     ConvW cw;
     cw.cin = cin; cw.cout = cout; cw.k = k;
     if (cin == 3) {  // stem: mma.sync B fragments (pack_stem_weights), consumed by stem_conv_kernel
-        if (k != 3 || cout % 8 != 0 || cout > 80)
-            return set_error(CY_ERR_INVALID, "stem %s: expected a 3x3 conv with cout %% 8 == 0, cout <= 80", p.c_str());
+        if (k != 3 || cout % 16 != 0 || cout > 96)
+            return set_error(CY_ERR_INVALID, "stem %s: expected a 3x3 conv with cout %% 16 == 0, cout <= 96", p.c_str());
         cw.cout_pad = cout;
         std::vector<uint32_t> frag;
         pack_stem_weights(*w, scale, cout, frag);
         CY_CUDA_CHECK(cudaMalloc(&cw.w, frag.size() * sizeof(uint32_t)));
         CY_CUDA_CHECK(cudaMemcpy(cw.w, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     } else {
+        // cin_pad > cin: the input buffer carries zero-filled padding channels (the conv kernel needs cin % 16 == 0;
+        // yolo11n has 8-channel bottleneck intermediates) and their weights are zero
+        const int cinp = cin_pad > cin ? cin_pad : cin;
         const int bn_ = conv_block_n(cout);
         cw.cout_pad = (cout + bn_ - 1) / bn_ * bn_;
-        const size_t K = (size_t)k * k * cin;
+        const size_t K = (size_t)k * k * cinp;
         std::vector<__nv_bfloat16> hw((size_t)cw.cout_pad * K, __float2bfloat16(0.f));
         for (int o = 0; o < cout; ++o)
             for (int i = 0; i < cin; ++i)
                 for (int kh = 0; kh < k; ++kh)
                     for (int kw = 0; kw < k; ++kw)
-                        hw[(size_t)o * K + (size_t)(kh * k + kw) * cin + i] =
+                        hw[(size_t)o * K + (size_t)(kh * k + kw) * cinp + i] =
                             __float2bfloat16((*w)[(((size_t)o * cin + i) * k + kh) * k + kw] * scale[o]);
+        cw.cin = cinp;
         CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(__nv_bfloat16)));
         CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     }
@@ -468,7 +646,110 @@ int Model::add_c2f(const std::string& p, int cin, int cout, int n) {
     return CY_OK;
 }
 
+// Depthwise 3x3 Conv (+BN): fp32 [9][C] weights (BN folded, rounded to bf16 like every other weight) + fp32 bias.
+int Model::add_dwconv(const std::string& p, int c) {
+    const auto *w = get(p + ".conv.weight"), *g = get(p + ".bn.weight"), *b = get(p + ".bn.bias"),
+               *m = get(p + ".bn.running_mean"), *v = get(p + ".bn.running_var");
+    if (!w || !g || !b || !m || !v) return set_error(CY_ERR_STATE, "missing tensors for depthwise conv %s", p.c_str());
+    if ((long long)w->size() != (long long)c * 9) return set_error(CY_ERR_INVALID, "tensor %s: expected [%d,1,3,3]", p.c_str(), c);
+    std::vector<float> hw((size_t)9 * c), hb(c);
+    for (int o = 0; o < c; ++o) {
+        const float sc = (*g)[o] / sqrtf((*v)[o] + 1e-3f);
+        hb[o] = (*b)[o] - (*m)[o] * sc;
+        for (int t = 0; t < 9; ++t) hw[(size_t)t * c + o] = bf16_round((*w)[(size_t)o * 9 + t] * sc);
+    }
+    ConvW cw;
+    cw.cin = cw.cout = cw.cout_pad = c;
+    cw.k = 3;
+    CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(float)));
+    CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CY_CUDA_CHECK(cudaMalloc(&cw.b, hb.size() * sizeof(float)));
+    CY_CUDA_CHECK(cudaMemcpy(cw.b, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    nparams += (long long)c * 9;
+    convs[p] = cw;
+    return CY_OK;
+}
+
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+// C3k2(cin, cout, n11, c3k, e): C2f skeleton whose inner blocks are C3k(c, c, 2) or Bottleneck(c, c, e = 0.5).
+int Model::add_c3k2(const std::string& p, int cin, int cout, bool c3k, double e) {
+    const int c = (int)(cout * e);
+    int r;
+    if ((r = add_conv(p + ".cv1", cin, 2 * c, 1, true))) return r;
+    if ((r = add_conv(p + ".cv2", (2 + n11) * c, cout, 1, true))) return r;
+    for (int i = 0; i < n11; ++i) {
+        const std::string m = p + ".m." + std::to_string(i);
+        if (c3k) {
+            const int c_ = c / 2;
+            if ((r = add_conv(m + ".cv1", c, c_, 1, true))) return r;
+            if ((r = add_conv(m + ".cv2", c, c_, 1, true))) return r;
+            if ((r = add_conv(m + ".cv3", 2 * c_, c, 1, true))) return r;
+            for (int j = 0; j < 2; ++j) {
+                const std::string b = m + ".m." + std::to_string(j);
+                if ((r = add_conv(b + ".cv1", c_, c_, 3, true))) return r;
+                if ((r = add_conv(b + ".cv2", c_, c_, 3, true))) return r;
+            }
+        } else {
+            if ((r = add_conv(m + ".cv1", c, c / 2, 3, true))) return r;
+            if ((r = add_conv(m + ".cv2", c / 2, c, 3, true, pad16(c / 2)))) return r;
+        }
+    }
+    return CY_OK;
+}
+
+int Model::finalize11() {
+    int r;
+#define TRY(x) if ((r = (x))) return r
+    TRY(add_conv("model.0", 3, w64, 3, true));
+    TRY(add_conv("model.1", w64, w128, 3, true));
+    TRY(add_c3k2("model.2", w128, w256, c3k11, 0.25));
+    TRY(add_conv("model.3", w256, w256, 3, true));
+    TRY(add_c3k2("model.4", w256, w512, c3k11, 0.25));
+    TRY(add_conv("model.5", w512, w512, 3, true));
+    TRY(add_c3k2("model.6", w512, w512, true, 0.5));
+    TRY(add_conv("model.7", w512, w1024, 3, true));
+    TRY(add_c3k2("model.8", w1024, w1024, true, 0.5));
+    TRY(add_conv("model.9.cv1", w1024, w1024 / 2, 1, true));
+    TRY(add_conv("model.9.cv2", w1024 * 2, w1024, 1, true));
+    const int c = w1024 / 2, nh = c / 64;
+    if (c % 64) return set_error(CY_ERR_INVALID, "C2PSA width %d is not a multiple of 64", c);
+    TRY(add_conv("model.10.cv1", w1024, 2 * c, 1, true));
+    TRY(add_conv("model.10.cv2", 2 * c, w1024, 1, true));
+    for (int i = 0; i < n11; ++i) {
+        const std::string m = "model.10.m." + std::to_string(i);
+        TRY(add_conv(m + ".attn.qkv", c, c + 2 * nh * 32, 1, true));
+        TRY(add_dwconv(m + ".attn.pe", c));
+        TRY(add_conv(m + ".attn.proj", c, c, 1, true));
+        TRY(add_conv(m + ".ffn.0", c, 2 * c, 1, true));
+        TRY(add_conv(m + ".ffn.1", 2 * c, c, 1, true));
+    }
+    TRY(add_c3k2("model.13", w1024 + w512, w512, c3k11, 0.5));
+    TRY(add_c3k2("model.16", w512 + w512, w256, c3k11, 0.5));
+    TRY(add_conv("model.17", w256, w256, 3, true));
+    TRY(add_c3k2("model.19", w256 + w512, w512, c3k11, 0.5));
+    TRY(add_conv("model.20", w512, w512, 3, true));
+    TRY(add_c3k2("model.22", w512 + w1024, w1024, true, 0.5));
+    const int cl[3] = {w256, w512, w1024};
+    for (int l = 0; l < 3; ++l) {
+        const std::string b = "model.23.cv2." + std::to_string(l), cs = "model.23.cv3." + std::to_string(l);
+        TRY(add_conv(b + ".0", cl[l], cb, 3, true));
+        TRY(add_conv(b + ".1", cb, cb, 3, true));
+        TRY(add_conv(b + ".2", cb, 64, 1, false));
+        TRY(add_dwconv(cs + ".0.0", cl[l]));
+        TRY(add_conv(cs + ".0.1", cl[l], cc, 1, true));
+        TRY(add_dwconv(cs + ".1.0", cc));
+        TRY(add_conv(cs + ".1.1", cc, cc, 1, true));
+        TRY(add_conv(cs + ".2", cc, nc, 1, false));
+    }
+#undef TRY
+    raw.clear();
+    finalized = true;
+    return CY_OK;
+}
+
 int Model::finalize() {
+    if (family == 11) return finalize11();
     int r;
 #define TRY(x) if ((r = (x))) return r
     TRY(add_conv("model.0", 3, c1, 3, true));
@@ -576,6 +857,90 @@ struct PlanBuilder {
         }
         return conv(p + ".cv2", cat, 0, out, out_off, 1);
     }
+    // zero-filled buffer (padding channels of 8-channel intermediates must read as 0)
+    Buf alloc_zero(int H, int W, int C) {
+        Buf b = alloc(H, W, C);
+        if (b.p && cudaMemset(b.p, 0, (size_t)B * H * W * C * 2) != cudaSuccess) {
+            snprintf(err, sizeof(err), "cudaMemset failed");
+            b.p = nullptr;
+        }
+        return b;
+    }
+    int dwconv(const std::string& name, const Buf& in, int in_off, int gs, int gst, const Buf& out, int out_off, int C,
+               bool act, const Buf* res = nullptr, int res_off = 0) {
+        auto it = m.convs.find(name);
+        if (it == m.convs.end() || it->second.cout != C) {
+            snprintf(err, sizeof(err), "depthwise conv %s not loaded", name.c_str());
+            return -1;
+        }
+        if (C % 8 || gs % 8 || in_off % 8 || out_off % 8 || C / 8 > 256) {
+            snprintf(err, sizeof(err), "depthwise conv %s: unsupported channel layout", name.c_str());
+            return -1;
+        }
+        Op op;
+        op.type = Op::DWCONV; op.name = name;
+        op.in = in; op.in_off = in_off; op.out = out; op.out_off = out_off; op.C = C;
+        op.dw_w = (const float*)it->second.w; op.dw_b = it->second.b;
+        op.act = act ? 1 : 0; op.gs = gs; op.gst = gst;
+        if (res) { op.res = *res; op.res_off = res_off; }
+        op.conv.flops = 2.0 * B * in.H * in.W * C * 9;
+        pl.ops.push_back(op);
+        return 0;
+    }
+    // yolo11 C3k2 (see Model::add_c3k2): in (all channels) -> out slice
+    int c3k2(const std::string& p, const Buf& in, int cout, bool c3k, double e, const Buf& out, int out_off) {
+        const int n = m.n11, c = (int)(cout * e);
+        Buf cat = alloc(in.H, in.W, (2 + n) * c);
+        if (!cat.p) return -1;
+        if (conv(p + ".cv1", in, 0, cat, 0, 1)) return -1;
+        for (int i = 0; i < n; ++i) {
+            const std::string mm = p + ".m." + std::to_string(i);
+            const int src = (1 + i) * c, dst = (2 + i) * c;
+            if (c3k) {   // C3k: cv3(cat(m(cv1(x)), cv2(x))), m = two Bottleneck(c/2, c/2) with shortcut
+                const int c_ = c / 2;
+                Buf cat2 = alloc(in.H, in.W, 2 * c_), a0 = alloc(in.H, in.W, c_), a1 = alloc(in.H, in.W, c_),
+                    t = alloc(in.H, in.W, c_);
+                if (!cat2.p || !a0.p || !a1.p || !t.p) return -1;
+                if (conv(mm + ".cv1", cat, src, a0, 0, 1)) return -1;
+                if (conv(mm + ".cv2", cat, src, cat2, c_, 1)) return -1;
+                if (conv(mm + ".m.0.cv1", a0, 0, t, 0, 1)) return -1;
+                if (conv(mm + ".m.0.cv2", t, 0, a1, 0, 1, true, &a0, 0)) return -1;
+                if (conv(mm + ".m.1.cv1", a1, 0, t, 0, 1)) return -1;
+                if (conv(mm + ".m.1.cv2", t, 0, cat2, 0, 1, true, &a1, 0)) return -1;
+                if (conv(mm + ".cv3", cat2, 0, cat, dst, 1)) return -1;
+            } else {     // Bottleneck(c, c, e = 0.5) with shortcut; the c/2 intermediate is padded to 16 channels
+                const int ch = c / 2;
+                Buf t = (ch % 16) ? alloc_zero(in.H, in.W, (ch + 15) / 16 * 16) : alloc(in.H, in.W, ch);
+                if (!t.p) return -1;
+                if (conv(mm + ".cv1", cat, src, t, 0, 1)) return -1;
+                if (conv(mm + ".cv2", t, 0, cat, dst, 1, true, &cat, src)) return -1;
+            }
+        }
+        return conv(p + ".cv2", cat, 0, out, out_off, 1);
+    }
+    // yolo11 C2PSA(c1, c1, n, e = 0.5): cv2(cat(a, PSA^n(b))), (a, b) = split(cv1(x))
+    int c2psa(const std::string& p, const Buf& in, const Buf& out, int out_off) {
+        const int c = in.C / 2, nh = c / 64, H = in.H, W = in.W;
+        Buf y = alloc(H, W, 2 * c), qkv = alloc(H, W, nh * 128), ao = alloc(H, W, c), pe = alloc(H, W, c),
+            t1 = alloc(H, W, c), f = alloc(H, W, 2 * c);
+        if (!y.p || !qkv.p || !ao.p || !pe.p || !t1.p || !f.p) return -1;
+        if (conv(p + ".cv1", in, 0, y, 0, 1)) return -1;
+        for (int i = 0; i < m.n11; ++i) {
+            const std::string mm = p + ".m." + std::to_string(i);
+            if (conv(mm + ".attn.qkv", y, c, qkv, 0, 1, false)) return -1;
+            Op op;
+            op.type = Op::ATTN; op.name = mm + ".attn";
+            op.in = qkv; op.out = ao; op.out_off = 0; op.nh = nh;
+            op.conv.flops = 2.0 * B * nh * (double)(H * W) * (H * W) * (32 + 64);
+            pl.ops.push_back(op);
+            // pe(v) + attention output: v = channels [64, 128) of every head's 128-channel group of qkv
+            if (dwconv(mm + ".attn.pe", qkv, 64, 64, 128, pe, 0, c, false, &ao, 0)) return -1;
+            if (conv(mm + ".attn.proj", pe, 0, t1, 0, 1, false, &y, c)) return -1;       // b + attn(b)
+            if (conv(mm + ".ffn.0", t1, 0, f, 0, 1)) return -1;
+            if (conv(mm + ".ffn.1", f, 0, y, c, 1, false, &t1, 0)) return -1;            // + ffn(.) back into y[:, c:]
+        }
+        return conv(p + ".cv2", y, 0, out, out_off, 1);
+    }
 };
 
 // Plans (activation buffers + tensor maps) are cached per (batch, extent).  A large batch of YOLOv8l holds 148 MB per
@@ -602,6 +967,7 @@ int Model::get_plan(int B, int Sh, int Sw, Plan** out) {
 }
 
 int Model::build_plan(int B, int Sh, int Sw, Plan** out) {
+    if (family == 11) return build_plan11(B, Sh, Sw, out);
     const auto key = std::make_tuple(B, Sh, Sw);
     Plan* pl = new Plan();
     pl->B = B; pl->Sh = Sh; pl->Sw = Sw;
@@ -711,6 +1077,112 @@ int Model::build_plan(int B, int Sh, int Sw, Plan** out) {
     return CY_OK;
 }
 
+// yolo11 (cfg/models/11/yolo11.yaml): 0-1 Conv, 2 C3k2, 3 Conv, 4 C3k2, 5 Conv, 6 C3k2, 7 Conv, 8 C3k2, 9 SPPF,
+// 10 C2PSA, 11-13 up + cat(6) + C3k2, 14-16 up + cat(4) + C3k2, 17-19 Conv + cat(13) + C3k2, 20-22 Conv + cat(10) +
+// C3k2, 23 Detect(16, 19, 22).  Concats are channel slices of shared buffers like in the yolov8 plan.
+int Model::build_plan11(int B, int Sh, int Sw, Plan** out) {
+    const auto key = std::make_tuple(B, Sh, Sw);
+    Plan* pl = new Plan();
+    pl->B = B; pl->Sh = Sh; pl->Sw = Sw;
+    PlanBuilder pb(*this, *pl, B);
+#define PB(x)                                                            \
+    if ((x)) {                                                           \
+        int rc = set_error(CY_ERR_INVALID, "plan build failed: %s", pb.err); \
+        delete pl;                                                       \
+        return rc;                                                       \
+    }
+    const int H2 = Sh / 2, W2 = Sw / 2, H4 = Sh / 4, W4 = Sw / 4, H8 = Sh / 8, W8 = Sw / 8, H16 = Sh / 16,
+              W16 = Sw / 16, H32 = Sh / 32, W32 = Sw / 32;
+    Buf x0 = pb.alloc(H2, W2, w64), x1 = pb.alloc(H4, W4, w128), x2 = pb.alloc(H4, W4, w256);
+    Buf x3 = pb.alloc(H8, W8, w256);
+    Buf cat15 = pb.alloc(H8, W8, w512 + w512);     // [up(x13) | x4]
+    Buf x5 = pb.alloc(H16, W16, w512);
+    Buf cat12 = pb.alloc(H16, W16, w1024 + w512);  // [up(x10) | x6]
+    Buf x7 = pb.alloc(H32, W32, w1024), x8 = pb.alloc(H32, W32, w1024);
+    Buf sp = pb.alloc(H32, W32, 2 * w1024), x9 = pb.alloc(H32, W32, w1024);
+    Buf cat21 = pb.alloc(H32, W32, w512 + w1024);  // [x20 | x10]
+    Buf cat18 = pb.alloc(H16, W16, w256 + w512);   // [x17 | x13]
+    Buf x16 = pb.alloc(H8, W8, w256), x19 = pb.alloc(H16, W16, w512), x22 = pb.alloc(H32, W32, w1024);
+    PB(!x0.p || !x1.p || !x2.p || !x3.p || !cat15.p || !x5.p || !cat12.p || !x7.p || !x8.p || !sp.p || !x9.p ||
+       !cat21.p || !cat18.p || !x16.p || !x19.p || !x22.p);
+    {
+        auto it0 = convs.find("model.0");
+        if (it0 == convs.end() || it0->second.cout != w64) snprintf(pb.err, sizeof(pb.err), "stem model.0 not loaded");
+        PB(it0 == convs.end() || it0->second.cout != w64);
+        Op op;
+        op.type = Op::STEM; op.name = "model.0";
+        op.out = x0;
+        op.conv.flops = 2.0 * B * H2 * W2 * w64 * 27;
+        pl->flops += op.conv.flops;
+        pl->ops.push_back(op);
+    }
+    PB(pb.conv("model.1", x0, 0, x1, 0, 2));
+    PB(pb.c3k2("model.2", x1, w256, c3k11, 0.25, x2, 0));
+    PB(pb.conv("model.3", x2, 0, x3, 0, 2));
+    PB(pb.c3k2("model.4", x3, w512, c3k11, 0.25, cat15, w512));      // x4 -> cat15[:, w512:]
+    PB(pb.conv("model.5", cat15, w512, x5, 0, 2));
+    PB(pb.c3k2("model.6", x5, w512, true, 0.5, cat12, w1024));       // x6 -> cat12[:, w1024:]
+    PB(pb.conv("model.7", cat12, w1024, x7, 0, 2));
+    PB(pb.c3k2("model.8", x7, w1024, true, 0.5, x8, 0));
+    PB(pb.conv("model.9.cv1", x8, 0, sp, 0, 1));
+    if ((size_t)3 * H32 * W32 * 64 <= (size_t)kSppfMaxSmem && (w1024 / 2) % 32 == 0) {
+        Op op;
+        op.type = Op::SPPF_POOL; op.name = "model.9.m";
+        op.in = sp; op.out = sp; op.C = w1024 / 2;
+        pl->ops.push_back(op);
+    } else {
+        for (int i = 0; i < 3; ++i) {
+            Op op;
+            op.type = Op::MAXPOOL; op.name = "model.9.m";
+            op.in = sp; op.in_off = i * (w1024 / 2); op.out = sp; op.out_off = (i + 1) * (w1024 / 2); op.C = w1024 / 2;
+            pl->ops.push_back(op);
+        }
+    }
+    PB(pb.conv("model.9.cv2", sp, 0, x9, 0, 1));
+    PB(pb.c2psa("model.10", x9, cat21, w512));                        // x10 -> cat21[:, w512:]
+    {
+        Op op;
+        op.type = Op::UPSAMPLE; op.name = "model.11";
+        op.in = cat21; op.in_off = w512; op.out = cat12; op.out_off = 0; op.C = w1024;
+        pl->ops.push_back(op);
+    }
+    PB(pb.c3k2("model.13", cat12, w512, c3k11, 0.5, cat18, w256));    // x13 -> cat18[:, w256:]
+    {
+        Op op;
+        op.type = Op::UPSAMPLE; op.name = "model.14";
+        op.in = cat18; op.in_off = w256; op.out = cat15; op.out_off = 0; op.C = w512;
+        pl->ops.push_back(op);
+    }
+    PB(pb.c3k2("model.16", cat15, w256, c3k11, 0.5, x16, 0));
+    PB(pb.conv("model.17", x16, 0, cat18, 0, 2));
+    PB(pb.c3k2("model.19", cat18, w512, c3k11, 0.5, x19, 0));
+    PB(pb.conv("model.20", x19, 0, cat21, 0, 2));
+    PB(pb.c3k2("model.22", cat21, w1024, true, 0.5, x22, 0));
+    const Buf* feats[3] = {&x16, &x19, &x22};
+    for (int l = 0; l < 3; ++l) {
+        const Buf& f = *feats[l];
+        Buf tb1 = pb.alloc(f.H, f.W, cb), tb2 = pb.alloc(f.H, f.W, cb);
+        Buf d1 = pb.alloc(f.H, f.W, f.C), tc1 = pb.alloc(f.H, f.W, cc), d2 = pb.alloc(f.H, f.W, cc),
+            tc2 = pb.alloc(f.H, f.W, cc);
+        Buf head = pb.alloc(f.H, f.W, kHeadC, true);
+        PB(!tb1.p || !tb2.p || !d1.p || !tc1.p || !d2.p || !tc2.p || !head.p);
+        const std::string b = "model.23.cv2." + std::to_string(l), c = "model.23.cv3." + std::to_string(l);
+        PB(pb.conv(b + ".0", f, 0, tb1, 0, 1));
+        PB(pb.conv(b + ".1", tb1, 0, tb2, 0, 1));
+        PB(pb.conv(b + ".2", tb2, 0, head, 0, 1, false, nullptr, 0, true));
+        PB(pb.dwconv(c + ".0.0", f, 0, f.C, 0, d1, 0, f.C, true));
+        PB(pb.conv(c + ".0.1", d1, 0, tc1, 0, 1));
+        PB(pb.dwconv(c + ".1.0", tc1, 0, cc, 0, d2, 0, cc, true));
+        PB(pb.conv(c + ".1.1", d2, 0, tc2, 0, 1));
+        PB(pb.conv(c + ".2", tc2, 0, head, 64, 1, false, nullptr, 0, true));
+        pl->head[l] = head;
+    }
+#undef PB
+    plans[key] = pl;
+    *out = pl;
+    return CY_OK;
+}
+
 int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaStream_t st) {
     switch (op.type) {
         case Op::STEM: {
@@ -744,6 +1216,37 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
             }
             sppf_pool3_kernel<<<dim3((unsigned)(op.C / 32), (unsigned)B), 256, smem, st>>>(
                 (__nv_bfloat16*)op.in.p, op.in.C, op.C, op.in.H, op.in.W);
+            break;
+        }
+        case Op::DWCONV: {
+            const int groups = op.C / 8, ppb = std::max(1, 256 / groups);
+            const char* ex = getenv("CY_CONV_SILU_EXACT");
+            const int act = op.act ? ((ex && atoi(ex)) ? 2 : 1) : 0;
+            dwconv3x3_kernel<<<dim3((unsigned)((op.in.W + ppb - 1) / ppb), (unsigned)op.in.H, (unsigned)B), groups * ppb, 0, st>>>(
+                (const __nv_bfloat16*)op.in.p, op.in.C, op.in_off, op.gs, op.gst, op.dw_w, op.dw_b,
+                (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, (const __nv_bfloat16*)op.res.p, op.res.C, op.res_off,
+                op.in.H, op.in.W, op.C, act);
+            break;
+        }
+        case Op::ATTN: {
+            const int N = op.in.H * op.in.W;
+            const size_t kv = (size_t)N * (17 + 32) * 4;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e1 = cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                cudaError_t e2 = cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error(CY_ERR_CUDA, "attention attribute failed");
+                attr_done = true;
+            }
+            const dim3 grid((unsigned)((N + 63) / 64), (unsigned)op.nh, (unsigned)B);
+            if (kv + (size_t)8 * N * 4 <= 200 * 1024)
+                attention_kernel<8><<<grid, 256, kv + (size_t)8 * N * 4, st>>>(
+                    (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N);
+            else if (kv + (size_t)4 * N * 4 <= 220 * 1024)
+                attention_kernel<4><<<grid, 128, kv + (size_t)4 * N * 4, st>>>(
+                    (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N);
+            else
+                return set_error(CY_ERR_INVALID, "attention over %d positions does not fit shared memory (imgsz > 1024)", N);
             break;
         }
         case Op::UPSAMPLE: {
@@ -790,7 +1293,7 @@ int Model::profile(const void* in, int B, int Sh, int Sw, int cap, const char** 
         cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
         if (ms) ms[i] = t;
         if (names) names[i] = pl->ops[i].name.c_str();
-        if (flops) flops[i] = (pl->ops[i].type == Op::CONV || pl->ops[i].type == Op::STEM) ? pl->ops[i].conv.flops : 0.0;
+        if (flops) flops[i] = (pl->ops[i].type == Op::CONV || pl->ops[i].type == Op::STEM) ? pl->ops[i].conv.flops : 0.0;   // tensor-pipe ops only
     }
     for (auto& e : ev) cudaEventDestroy(e);
     if (nops) *nops = n;

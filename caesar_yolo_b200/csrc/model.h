@@ -24,11 +24,20 @@ struct ConvW {
 };
 
 struct Op {
-    enum Type { STEM, CONV, MAXPOOL, SPPF_POOL, UPSAMPLE } type;
+    enum Type { STEM, CONV, MAXPOOL, SPPF_POOL, UPSAMPLE, DWCONV, ATTN } type;
     std::string name;
     ConvPlan conv;
     Buf in, out;
     int in_off = 0, out_off = 0, C = 0;
+    // DWCONV: depthwise 3x3 (+ bias, optional SiLU, optional residual); logical channel c reads input channel
+    // in_off + (c / gs) * gst + c % gs (gs = C, gst = 0 for a plain slice; the attention `pe` conv gathers v out of qkv)
+    const float* dw_w = nullptr;   // fp32 [9][C], BN folded, bf16-rounded values
+    const float* dw_b = nullptr;   // fp32 [C]
+    int act = 0, gs = 0, gst = 0;
+    Buf res;
+    int res_off = 0;
+    // ATTN: in = qkv buffer [B,H,W,nh*128] (per head 32 q | 32 k | 64 v), out = [B,H,W,nh*64] slice
+    int nh = 0;
 };
 
 struct Plan {
@@ -43,7 +52,11 @@ struct Plan {
 
 struct Model {
     char variant = 'n';
+    int family = 8;   // 8: yolov8 (yolov8.yaml), 11: yolo11 (yolo11.yaml)
     int nc = 5;
+    // yolo11 widths / repeats (init11)
+    int w64 = 0, w128 = 0, w256 = 0, w512 = 0, w1024 = 0, n11 = 1;
+    bool c3k11 = false;
     int c1, c2, c3, c4, c5, n2, n4, n6, n8, nh, cb, cc;
     bool finalized = false;
     long long nparams = 0;
@@ -56,6 +69,8 @@ struct Model {
     int finalize();
     int get_plan(int B, int Sh, int Sw, Plan** out);
     int build_plan(int B, int Sh, int Sw, Plan** out);
+    int build_plan11(int B, int Sh, int Sw, Plan** out);
+    int finalize11();
     int forward(const void* in, int B, int Sh, int Sw, cudaStream_t st, Plan** plan_out);
     int launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaStream_t st);
     int profile(const void* in, int B, int Sh, int Sw, int cap, const char** names, float* ms, double* flops, int* nops,
@@ -64,7 +79,9 @@ struct Model {
 
    private:
     const std::vector<float>* get(const std::string& k) const;
-    int add_conv(const std::string& p, int cin, int cout, int k, bool bn);
+    int add_conv(const std::string& p, int cin, int cout, int k, bool bn, int cin_pad = 0);
+    int add_dwconv(const std::string& p, int c);
+    int add_c3k2(const std::string& p, int cin, int cout, bool c3k, double e);
     int add_c2f(const std::string& p, int cin, int cout, int n);
 };
 

@@ -150,7 +150,7 @@ class DeviceModel(object):
         check(lib.cy_model_create(self.variant.encode(), c_int(self.nc), ctypes.byref(h)))
         self._h = h
         for k, v in weights['state_dict'].items():
-            if k.startswith('model.22.dfl'):
+            if '.dfl.' in k:
                 continue
             a = np.ascontiguousarray(v.detach().cpu().float().numpy())
             check(lib.cy_model_set_tensor(self._h, k.encode(), _np_ptr(a), c_i64(a.size)))

@@ -78,6 +78,131 @@ def conv_bn_layers(variant, nc=5):
     return L, cb, cc
 
 
+# ------------------------------------------------------------------------------------------------ YOLO11
+# ultralytics cfg/models/11/yolo11.yaml (the reference's README ships yolo11 weights next to yolov8, README.md:200-207).
+# Variant names here: '11n', '11s', '11m', '11l', '11x'.  The layer table below reproduces the published parameter
+# counts of all five scales exactly (tests/test_weights_cpu.py::test_yolo11_parameter_counts).
+SCALES11 = {'n': (0.50, 0.25, 1024), 's': (0.50, 0.50, 1024), 'm': (0.50, 1.00, 512), 'l': (1.00, 1.00, 512),
+            'x': (1.00, 1.50, 512)}
+
+
+def is_yolo11(variant):
+    return str(variant).startswith('11')
+
+
+def arch11(variant):
+    """Channel widths / repeats / block kinds of yolo11{n,s,m,l,x}.  c3k: C3k2 blocks of layers 2, 4, 13, 16, 19 use
+    C3k inner blocks only for the m/l/x scales (parse_model forces c3k=True there); layers 6, 8, 22 always do."""
+    depth, width, maxc = SCALES11[variant[2:]]
+    ch = lambda c: make_divisible(min(c, maxc) * width, 8)
+    return dict(c64=ch(64), c128=ch(128), c256=ch(256), c512=ch(512), c1024=ch(1024), n=max(round(2 * depth), 1),
+                c3k=variant[2:] in 'mlx')
+
+
+def conv_layers11(variant, nc=5):
+    """Ordered list of (prefix, cin, cout, k, groups, has_bn) for every conv of yolo11 in forward order (Conv modules
+    have BN + SiLU unless the block says otherwise; the two head outputs per level are plain Conv2d with bias)."""
+    a = arch11(variant)
+    c64, c128, c256, c512, c1024, n, big = a['c64'], a['c128'], a['c256'], a['c512'], a['c1024'], a['n'], a['c3k']
+    L = []
+
+    def conv(p, cin, cout, k, g=1, bn=True):
+        L.append((p, cin, cout, k, g, bn))
+
+    def c3k2(p, cin, cout, c3k, e=0.5):
+        c = int(cout * e)
+        conv(p + '.cv1', cin, 2 * c, 1)
+        for i in range(n):
+            m = '%s.m.%d' % (p, i)
+            if c3k:     # C3k(c, c, 2): cv1, cv2 -> c/2; two Bottleneck(c/2, c/2, e=1.0); cv3
+                c_ = c // 2
+                conv(m + '.cv1', c, c_, 1)
+                conv(m + '.cv2', c, c_, 1)
+                for j in range(2):
+                    conv('%s.m.%d.cv1' % (m, j), c_, c_, 3)
+                    conv('%s.m.%d.cv2' % (m, j), c_, c_, 3)
+                conv(m + '.cv3', 2 * c_, c, 1)
+            else:       # Bottleneck(c, c, e=0.5)
+                conv(m + '.cv1', c, c // 2, 3)
+                conv(m + '.cv2', c // 2, c, 3)
+        conv(p + '.cv2', (2 + n) * c, cout, 1)
+
+    conv('model.0', 3, c64, 3)
+    conv('model.1', c64, c128, 3)
+    c3k2('model.2', c128, c256, big, 0.25)
+    conv('model.3', c256, c256, 3)
+    c3k2('model.4', c256, c512, big, 0.25)
+    conv('model.5', c512, c512, 3)
+    c3k2('model.6', c512, c512, True)
+    conv('model.7', c512, c1024, 3)
+    c3k2('model.8', c1024, c1024, True)
+    conv('model.9.cv1', c1024, c1024 // 2, 1)
+    conv('model.9.cv2', c1024 * 2, c1024, 1)
+    c = c1024 // 2                                        # C2PSA(c1024, c1024, n, e=0.5)
+    conv('model.10.cv1', c1024, 2 * c, 1)
+    for i in range(n):
+        m = 'model.10.m.%d' % i
+        nh = c // 64
+        conv(m + '.attn.qkv', c, c + 2 * nh * 32, 1)      # head_dim 64, key_dim 32 (attn_ratio 0.5); no activation
+        conv(m + '.attn.pe', c, c, 3, g=c)                # depthwise positional conv, no activation
+        conv(m + '.attn.proj', c, c, 1)                   # no activation
+        conv(m + '.ffn.0', c, 2 * c, 1)
+        conv(m + '.ffn.1', 2 * c, c, 1)                   # no activation
+    conv('model.10.cv2', 2 * c, c1024, 1)
+    c3k2('model.13', c1024 + c512, c512, big)
+    c3k2('model.16', c512 + c512, c256, big)
+    conv('model.17', c256, c256, 3)
+    c3k2('model.19', c256 + c512, c512, big)
+    conv('model.20', c512, c512, 3)
+    c3k2('model.22', c512 + c1024, c1024, True)
+    cb = max(16, c256 // 4, 64)
+    cc = max(c256, min(nc, 100))
+    for l, cl in enumerate((c256, c512, c1024)):
+        conv('model.23.cv2.%d.0' % l, cl, cb, 3)
+        conv('model.23.cv2.%d.1' % l, cb, cb, 3)
+        conv('model.23.cv2.%d.2' % l, cb, 64, 1, bn=False)
+        conv('model.23.cv3.%d.0.0' % l, cl, cl, 3, g=cl)  # DWConv
+        conv('model.23.cv3.%d.0.1' % l, cl, cc, 1)
+        conv('model.23.cv3.%d.1.0' % l, cc, cc, 3, g=cc)  # DWConv
+        conv('model.23.cv3.%d.1.1' % l, cc, cc, 1)
+        conv('model.23.cv3.%d.2' % l, cc, nc, 1, bn=False)
+    return L
+
+
+def count_parameters11(variant, nc=80):
+    """nn.Module parameter count of the unfused ultralytics model (conv weights, BN weight + bias, head biases, DFL)."""
+    tot = 16
+    for (p, cin, cout, k, g, bn) in conv_layers11(variant, nc):
+        tot += cout * (cin // g) * k * k + (2 * cout if bn else cout)
+    return tot
+
+
+def make_random_weights11(variant='11n', nc=5, seed=0, cls_bias=-3.0, calibration='auto'):
+    """Seeded random-init yolo11 with the ultralytics state-dict key names (same recipe as make_random_weights: BN
+    running statistics from init_calibration.json for the (variant, seed) pairs tools/calibrate_init.py lists)."""
+    calib = _load_calibration(variant, seed) if calibration == 'auto' else calibration
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for (p, cin, cout, k, grp, bn) in conv_layers11(variant, nc):
+        fan_in = (cin // grp) * k * k
+        if bn:
+            sd[p + '.conv.weight'] = torch.randn(cout, cin // grp, k, k, generator=g) / math.sqrt(fan_in)
+            sd[p + '.bn.weight'] = 1.0 + 0.1 * torch.randn(cout, generator=g)
+            sd[p + '.bn.bias'] = 0.1 * torch.randn(cout, generator=g)
+            mu, var = (calib[p] if calib and p in calib else (0.0, 1.0))
+            sd[p + '.bn.running_mean'] = torch.full((cout,), float(mu))
+            sd[p + '.bn.running_var'] = float(var) * (0.8 + 0.4 * torch.rand(cout, generator=g))
+        elif '.cv2.' in p:
+            sd[p + '.weight'] = torch.randn(cout, cin, 1, 1, generator=g) * (1.5 / math.sqrt(cin))
+            sd[p + '.bias'] = (-0.6 * torch.arange(16, dtype=torch.float32)).repeat(4) + 1.0
+        else:
+            sd[p + '.weight'] = torch.randn(cout, cin, 1, 1, generator=g) * (2.5 / math.sqrt(cin))
+            sd[p + '.bias'] = torch.full((cout,), float(cls_bias))
+    sd['model.23.dfl.conv.weight'] = torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)
+    return {'format': FORMAT, 'variant': variant, 'nc': nc, 'names': dict(CLASS_NAMES) if nc == 5 else
+            {i: 'class%d' % i for i in range(nc)}, 'state_dict': sd}
+
+
 def _load_calibration(variant, seed):
     if os.path.exists(_CALIB_PATH):
         with open(_CALIB_PATH) as f:
@@ -92,6 +217,8 @@ def make_random_weights(variant='n', nc=5, seed=0, cls_bias=-3.0, calibration='a
     synthetic preprocessed tile, produced by tools/calibrate_init.py for the (variant, seed) pairs it lists; other
     seeds fall back to mean 0 / var 1) so that every layer works at unit scale and detections depend on the image.  The class-branch bias sets the candidate density; a linear DFL bias keeps
     boxes a few cells wide."""
+    if is_yolo11(variant):
+        return make_random_weights11(variant, nc, seed, cls_bias, calibration)
     calib = _load_calibration(variant, seed) if calibration == 'auto' else calibration
     g = torch.Generator().manual_seed(seed)
     layers, cb, cc = conv_bn_layers(variant, nc)
@@ -157,11 +284,13 @@ def weights_from_state_dict(sd, names=None):
     w0 = sd.get('model.0.conv.weight')
     if w0 is None or w0.dim() != 4 or tuple(w0.shape[1:]) != (3, 3, 3) or int(w0.shape[0]) not in _STEM_WIDTH_TO_VARIANT:
         raise ValueError("not a YOLOv8 detection checkpoint: model.0.conv.weight should be [16|32|48|64|80, 3, 3, 3]")
+    if 'model.23.cv3.0.2.weight' in sd and 'model.10.m.0.attn.qkv.conv.weight' in sd:
+        return _weights11_from_state_dict(sd, names)
     variant = _STEM_WIDTH_TO_VARIANT[int(w0.shape[0])]
     head = sd.get('model.22.cv3.0.2.weight')
     if head is None:
-        raise ValueError("not a YOLOv8 detection checkpoint: no Detect head at model.22 (yolo11 / segmentation / pose "
-                         "models are not supported by this build)")
+        raise ValueError("not a YOLOv8 / YOLO11 detection checkpoint: no Detect head at model.22 / model.23 "
+                         "(segmentation / pose / other families are not supported by this build)")
     nc = int(head.shape[0])
     layers, cb, cc = conv_bn_layers(variant, nc)
     out = {}
@@ -203,6 +332,54 @@ def weights_from_state_dict(sd, names=None):
     return {'format': FORMAT, 'variant': variant, 'nc': nc, 'names': names, 'state_dict': out}
 
 
+def _names_dict(names, nc):
+    if names is None:
+        names = dict(CLASS_NAMES) if nc == len(CLASS_NAMES) else {i: 'class%d' % i for i in range(nc)}
+    elif not isinstance(names, dict):
+        names = {i: n for i, n in enumerate(names)}
+    names = {int(k): str(v) for k, v in names.items()}
+    if sorted(names) != list(range(nc)):
+        raise ValueError("checkpoint names %r do not cover nc=%d classes" % (names, nc))
+    return names
+
+
+def _weights11_from_state_dict(sd, names):
+    """yolo11 detection state dict -> weight dict (variant from the stem width + the depth of model.2 / block kind)."""
+    c0 = int(sd['model.0.conv.weight'].shape[0])
+    nc = int(sd['model.23.cv3.0.2.weight'].shape[0])
+    cands = [v for v in ('11n', '11s', '11m', '11l', '11x') if arch11(v)['c64'] == c0]
+    # m and l share widths (64): l has n = 2 repeats
+    variant = None
+    for v in cands:
+        if all((p + ('.conv.weight' if bn else '.weight')) in sd for (p, _, _, _, _, bn) in conv_layers11(v, nc)) and \
+                ('model.2.m.%d.cv1.conv.weight' % arch11(v)['n']) not in sd:
+            variant = v
+            break
+    if variant is None:
+        raise ValueError("checkpoint does not match any yolo11 scale (stem width %d)" % c0)
+    out = {}
+    for (p, cin, cout, k, g, bn) in conv_layers11(variant, nc):
+        if bn:
+            w = sd[p + '.conv.weight']
+            if tuple(w.shape) != (cout, cin // g, k, k):
+                raise ValueError("checkpoint does not match yolo%s (nc=%d): %s.conv.weight has shape %s, expected %s"
+                                 % (variant, nc, p, tuple(w.shape), (cout, cin // g, k, k)))
+            out[p + '.conv.weight'] = w
+            if p + '.bn.weight' in sd:
+                for f in ('weight', 'bias', 'running_mean', 'running_var'):
+                    out['%s.bn.%s' % (p, f)] = sd['%s.bn.%s' % (p, f)]
+            else:
+                out[p + '.bn.weight'] = torch.ones(cout)
+                out[p + '.bn.bias'] = sd[p + '.conv.bias']
+                out[p + '.bn.running_mean'] = torch.zeros(cout)
+                out[p + '.bn.running_var'] = torch.full((cout,), 1.0 - 1e-3)
+        else:
+            out[p + '.weight'] = sd[p + '.weight']
+            out[p + '.bias'] = sd[p + '.bias']
+    out['model.23.dfl.conv.weight'] = torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)
+    return {'format': FORMAT, 'variant': variant, 'nc': nc, 'names': _names_dict(names, nc), 'state_dict': out}
+
+
 def load_ultralytics_checkpoint(path):
     """Reads an ultralytics YOLOv8 detection `.pt` without the ultralytics package (see _StubPickle).  Follows
     ultralytics' own loader: the EMA model when present, else 'model'; weights converted to fp32 (they are stored as
@@ -213,6 +390,8 @@ def load_ultralytics_checkpoint(path):
     obj = ck
     if isinstance(ck, dict) and ('model' in ck or 'ema' in ck):
         obj = ck.get('ema') if ck.get('ema') is not None else ck.get('model')
+        if obj is None:
+            obj = ck
     if isinstance(obj, torch.nn.Module):
         names = getattr(obj, 'names', None)
         return weights_from_state_dict(obj.state_dict(), names)

@@ -43,7 +43,7 @@ class OracleYolo(object):
         self.variant = weights['variant']
         self.nc = weights['nc']
         self.names = dict(weights['names'])
-        self.a = arch(self.variant)
+        self.a = arch(self.variant) if not str(self.variant).startswith('11') else None
         self.emu = emulate_bf16
         sd = weights['state_dict']
         self.w = {}
@@ -254,7 +254,11 @@ class OracleModel(object):
     """Duck-typed stand-in for ultralytics.YOLO as the reference uses it (evaluation.py:46-47,181-193,261-264)."""
 
     def __init__(self, weights, emulate_bf16=False):
-        self.net = OracleYolo(weights, emulate_bf16)
+        if str(weights['variant']).startswith('11'):
+            from .yolo11 import OracleYolo11
+            self.net = OracleYolo11(weights, emulate_bf16)
+        else:
+            self.net = OracleYolo(weights, emulate_bf16)
         self.names = self.net.names
 
     def __call__(self, image, save=False, device='cpu', imgsz=640, conf=0.25, iou=0.7, **kw):

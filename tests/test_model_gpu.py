@@ -128,3 +128,30 @@ def test_postprocess_matches_oracle(B, Sh, Sw, Ty, Tx, conf, bias):
         got = dets[b, :n]
         assert torch.equal(got[:, 4], want[:, 4]) and torch.equal(got[:, 5], want[:, 5])
         assert torch.allclose(got[:, :4], want[:, :4], rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("variant,B,Sh,Sw", [('11n', 2, 640, 640), ('11n', 1, 640, 320), ('11s', 1, 320, 320),
+                                             ('11l', 2, 320, 320), ('11x', 1, 256, 256)])
+def test_forward_yolo11_matches_oracle(variant, B, Sh, Sw):
+    """YOLO11 (C3k2 / C3k, C2PSA attention, depthwise-separable class branch) on the tcgen05 conv stack + the
+    depthwise-conv and attention kernels vs the oracle restatement (bf16-emulated and fp32)."""
+    from caesar_yolo_b200 import ops, weights as W
+    w = W.make_random_weights(variant, 5, seed=0)
+    dm = ops.DeviceModel(w)
+    x = _input(B, Sh, Sw, seed=B + Sh)
+    heads = dm.forward_tensors(_to_nhwc4(x).to(DEV))
+    torch.cuda.synchronize()
+    from oracle.yolo11 import OracleYolo11
+    with torch.no_grad():
+        he = OracleYolo11(w, emulate_bf16=True).forward_heads(x)
+        hf = OracleYolo11(w, emulate_bf16=False).forward_heads(x)
+    for l in range(3):
+        got = heads[l].cpu()[..., :69].permute(0, 3, 1, 2)
+        assert got.shape == hf[l].shape
+        scale = hf[l].abs().max().item()
+        err_emu = (got - he[l]).abs().max().item() / scale
+        err_f32 = (got - hf[l]).abs().max().item() / scale
+        q = (he[l] - hf[l]).abs().max().item() / scale
+        print("%s level %d: max err vs emu %.4f, vs fp32 %.4f (emu vs fp32 %.4f)" % (variant, l, err_emu, err_f32, q))
+        assert err_emu < 0.04, (l, err_emu, err_f32, q)
+        assert err_f32 < max(0.08, 3 * q), (l, err_emu, err_f32, q)

@@ -202,3 +202,26 @@ def test_own_weight_file_roundtrip(tmp_path):
     w2 = W.load_weights(p)
     assert w2['variant'] == 'n' and w2['names'] == W.CLASS_NAMES
     assert all(torch.equal(w2['state_dict'][k], v) for k, v in w['state_dict'].items())
+
+
+def test_yolo11_parameter_counts():
+    """The yolo11 layer table (shared by the device model's graph builder and the oracle) reproduces the parameter
+    counts ultralytics publishes for the five scales at nc = 80 (model summaries of yolo11{n,s,m,l,x}.pt)."""
+    want = {'11n': 2624080, '11s': 9458752, '11m': 20114688, '11l': 25372160, '11x': 56966176}
+    for v, n in want.items():
+        assert W.count_parameters11(v, 80) == n, v
+
+
+def test_yolo11_state_dict_roundtrip_and_variant_inference(tmp_path):
+    for v in ('11n', '11m', '11l'):
+        w = W.make_random_weights(v, 5, seed=0)
+        p = str(tmp_path / ('%s.pt' % v))
+        torch.save({'model': None, 'ema': None, 'state_dict': w['state_dict'], 'names': list(W.CLASS_NAMES.values())}, p)
+        w2 = W.load_weights(p)
+        assert w2['variant'] == v and w2['nc'] == 5 and w2['names'] == W.CLASS_NAMES
+        assert set(w2['state_dict']) == set(w['state_dict'])
+    sd = dict(W.make_random_weights('11n', 5, seed=0)['state_dict'])
+    del sd['model.10.m.0.ffn.1.conv.weight']
+    torch.save(sd, str(tmp_path / 'bad.pt'))
+    with pytest.raises(ValueError, match="does not match any yolo11 scale"):
+        W.load_weights(str(tmp_path / 'bad.pt'))

@@ -12,10 +12,10 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from caesar_yolo_b200 import synth, weights as W  # noqa: E402
-from oracle import preprocessing as opp, yolo as oy  # noqa: E402
+from oracle import preprocessing as opp, yolo as oy, yolo11 as oy11  # noqa: E402
 
 
-class Calib(oy.OracleYolo):
+class _CalibMixin(object):
     def __init__(self, weights):
         super().__init__(weights)
         self.sd = weights['state_dict']
@@ -23,13 +23,22 @@ class Calib(oy.OracleYolo):
 
     def conv(self, x, p, k, s, act=True):
         if p + '.bn.weight' in self.sd:
-            raw = F.conv2d(x, self.sd[p + '.conv.weight'].float(), None, stride=s, padding=k // 2)
+            wt = self.sd[p + '.conv.weight'].float()
+            raw = F.conv2d(x, wt, None, stride=s, padding=k // 2, groups=x.shape[1] // wt.shape[1])
             mu, var = float(raw.mean()), float(raw.var())
             self.table[p] = (mu, var)
             gamma, beta = self.sd[p + '.bn.weight'], self.sd[p + '.bn.bias']
             sc = gamma / torch.sqrt(torch.full_like(gamma, var) + 1e-3)
             self.w[p] = (self.sd[p + '.conv.weight'].float() * sc.view(-1, 1, 1, 1), beta - mu * sc)
         return super().conv(x, p, k, s, act)
+
+
+class Calib(_CalibMixin, oy.OracleYolo):
+    pass
+
+
+class Calib11(_CalibMixin, oy11.OracleYolo11):
+    pass
 
 
 def calib_input(n=2, imgsz=640):
@@ -46,14 +55,14 @@ def calib_input(n=2, imgsz=640):
 
 
 def main():
-    variants = sys.argv[1:] or ['n:0', 'n:1', 's:0', 'm:0', 'l:0', 'l:1', 'x:0']
+    variants = sys.argv[1:] or ['n:0', 'n:1', 's:0', 'm:0', 'l:0', 'l:1', 'x:0', '11n:0', '11s:0', '11m:0', '11l:0', '11x:0']
     path = os.path.join(ROOT, 'caesar_yolo_b200', 'init_calibration.json')
     table = json.load(open(path)) if os.path.exists(path) else {}
     x = calib_input()
     for vs in variants:
         v, seed = vs.split(':')
         w = W.make_random_weights(v, 5, seed=int(seed), calibration=None)
-        c = Calib(w)
+        c = (Calib11 if v.startswith('11') else Calib)(w)
         with torch.no_grad():
             c.forward_heads(x)
         table[vs] = {k: [round(a, 6), round(b, 8)] for k, (a, b) in c.table.items()}
