@@ -40,7 +40,7 @@ def emit(line):
 PP_FLAGS = dict(subtract_bkg=True, clip_data=True, zscale_stretch=True, chan3_preproc=True, normalize_minmax=True,
                 nchannels=3, norm_max=255.)
 SCORE_THR, IOU_THR, SOFT, HARD = 0.5, 0.5, 0.3, 0.8
-CLS_BIAS = {'n': -16.0, 'l': -24.0}
+CLS_BIAS = {'n': -16.0, 'l': -24.0, '11n': -20.0, '11l': -24.0}
 
 
 def parse():

@@ -615,7 +615,8 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
 
     // ---- mode: tap reuse for 3x3 stride-1 convs with 128-byte channel chunks on maps that 8 x 16 tiles cover well
     int mode = 0;
-    if (d.ksize == 3 && d.stride == 1 && kc == 64) {
+    // (kc = 32: 64-byte rows with SWIZZLE_64B take the same descriptor-offset reuse; CY_CONV_MODE32=0 disables it)
+    if (d.ksize == 3 && d.stride == 1 && (kc == 64 || (kc == 32 && env_int("CY_CONV_MODE32", 1)))) {
         const double util = (double)Wout * Hout / ((double)((Wout + 7) / 8 * 8) * ((Hout + 15) / 16 * 16));
         if (util >= 0.8) mode = 2;
     }

@@ -53,6 +53,9 @@ def _run_case(B, H, W, cin, cout, k, s, act, res, out_f32, in_extra=0, out_extra
     dict(B=2, H=32, W=32, cin=32, cout=32, k=3, s=2, act=True, res=False, out_f32=False),
     dict(B=1, H=160, W=160, cin=64, cout=64, k=3, s=1, act=True, res=True, out_f32=False),
     dict(B=4, H=20, W=20, cin=512, cout=512, k=3, s=1, act=True, res=False, out_f32=False),
+    # 64-byte channel rows (kc = 32, SWIZZLE_64B) with the 3x3 tap reuse through descriptor offsets (yolo11 / v8n,s)
+    dict(B=3, H=80, W=80, cin=32, cout=32, k=3, s=1, act=True, res=True, out_f32=False),
+    dict(B=2, H=32, W=48, cin=96, cout=64, k=3, s=1, act=True, res=False, out_f32=False, in_extra=32, out_extra=8),
 ])
 def test_conv_matches_torch(case):
     _run_case(**case)

@@ -350,3 +350,23 @@ def test_png_input_serial_path(tmp_path):
     sf = SFinder(YOLO(w), _config(str(tmp_path / 'col.jpg'), str(tmp_path), mk(), False))
     assert sf.run() == -1
 
+
+def test_tiled_mosaic_yolo11(tmp_path):
+    """The same tiled FITS -> catalog run with a yolo11n model (the reference README ships yolo11 weights): drop-in
+    SFinder vs the oracle's run_parallel with the yolo11 restatement."""
+    from caesar_yolo_b200 import synth, weights as W
+    mosaic = synth.make_mosaic(1024, 1536, seed=41, nan_border_frac=0.0)
+    path = str(tmp_path / "mosaic.fits")
+    synth.write_fits(path, mosaic)
+    w = W.make_random_weights('11n', 5, seed=0, cls_bias=-20.0)   # ~100 detections over the 6 tiles
+    _run_ours(w, path, str(tmp_path), True)
+    got = json.load(open(str(tmp_path / "catalog_mosaic.json")))['sources']
+    emu = _run_oracle(w, path, str(tmp_path), True, True).sources['sources']
+    f32 = _run_oracle(w, path, str(tmp_path), True, False).sources['sources']
+    m_emu, m_f32, m_ref = match_fraction(got, emu), match_fraction(got, f32), match_fraction(emu, f32)
+    print("yolo11n: ours %d, oracle(bf16-emulated) %d, oracle(fp32) %d sources; matched@IoU0.9: vs emu %.4f, vs fp32 %.4f "
+          "(emu vs fp32 %.4f)" % (len(got), len(emu), len(f32), m_emu, m_f32, m_ref))
+    assert len(emu) >= 10, "threshold too high: the test would be vacuous"
+    slack = 0.05 + 2.0 / max(len(emu), 1)
+    assert m_emu >= 0.90 - slack, m_emu
+    assert m_f32 >= min(0.995, m_ref) - slack, (m_f32, m_ref)
