@@ -515,6 +515,144 @@ __global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat
     }
 }
 
+// Tensor-core version of the attention above (the one the plan launches; the CUDA-core kernel stays as the fallback
+// for maps whose K/V do not fit shared memory in this layout and as a second implementation for the parity tests:
+// CY_ATTN_SIMPLE=1).  Flash-style: CTA = (64 queries, head, image), 4 warps x 16 queries; K [Npad][32] and V
+// [Npad][64] of the head in shared memory (rows padded to 80 / 144 bytes: conflict-free fragment loads); per chunk of
+// 64 keys S = Q K^T with mma.sync.m16n8k16 (bf16, fp32 accumulate), online softmax in registers (exp2, running max /
+// sum per query row, quad shuffles), P re-packed as the A operand and O += P V with V fragments from
+// ldmatrix.x4.trans.  48 MMAs per warp and chunk; 2.7 ms -> see profiles/ for the measured time.
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ctot,
+                                                            __nv_bfloat16* __restrict__ out, int out_ctot, int out_off,
+                                                            int N, int Npad) {
+    extern __shared__ __align__(16) unsigned char attn_mma_smem[];
+    unsigned char* sK = attn_mma_smem;                       // [Npad] rows of 80 bytes (64 used)
+    unsigned char* sV = attn_mma_smem + (size_t)Npad * 80;   // [Npad] rows of 144 bytes (128 used)
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* base = qkv + (long long)b * N * qkv_ctot + head * 128;
+    for (int i = threadIdx.x; i < Npad * 4; i += 128) {
+        const int m = i >> 2, ch = i & 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (m < N) v = __ldg(reinterpret_cast<const uint4*>(base + (long long)m * qkv_ctot + 32) + ch);
+        *reinterpret_cast<uint4*>(sK + (size_t)m * 80 + ch * 16) = v;
+    }
+    for (int i = threadIdx.x; i < Npad * 8; i += 128) {
+        const int m = i >> 3, ch = i & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (m < N) v = __ldg(reinterpret_cast<const uint4*>(base + (long long)m * qkv_ctot + 64) + ch);
+        *reinterpret_cast<uint4*>(sV + (size_t)m * 144 + ch * 16) = v;
+    }
+    // Q fragments of this warp's 16 queries (rows past N are clamped; their results are not stored)
+    const int q0 = blockIdx.x * 64 + warp * 16;
+    uint32_t qa[2][4];
+    {
+        const int r0 = min(q0 + g, N - 1), r1 = min(q0 + g + 8, N - 1);
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(base + (long long)r0 * qkv_ctot);
+        const uint32_t* p1 = reinterpret_cast<const uint32_t*>(base + (long long)r1 * qkv_ctot);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            qa[ks][0] = __ldg(p0 + ks * 8 + t);
+            qa[ks][1] = __ldg(p1 + ks * 8 + t);
+            qa[ks][2] = __ldg(p0 + ks * 8 + t + 4);
+            qa[ks][3] = __ldg(p1 + ks * 8 + t + 4);
+        }
+    }
+    __syncthreads();
+    const float c = 0.17677669529663687f * 1.4426950408889634f;   // 32^-0.5 * log2(e): softmax through exp2
+    float o[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const uint32_t sV_addr = (uint32_t)__cvta_generic_to_shared(sV);
+    for (int kc = 0; kc < Npad; kc += 64) {
+        float sc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+            const uint32_t* kr = reinterpret_cast<const uint32_t*>(sK + (size_t)(kc + nt * 8 + g) * 80);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) mma16816(sc[nt], qa[ks], kr[ks * 8 + t], kr[ks * 8 + t + 4]);
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int key = kc + nt * 8 + 2 * t;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool valid = key + (j & 1) < N;
+                sc[nt][j] = valid ? sc[nt][j] * c : -INFINITY;
+            }
+            mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: key 0 of chunk 0 is always valid
+        const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
+        m0 = mn0;
+        m1 = mn1;
+        float rs0 = 0.f, rs1 = 0.f;
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = exp2f(sc[nt][0] - mn0), p1 = exp2f(sc[nt][1] - mn0);
+            const float p2 = exp2f(sc[nt][2] - mn1), p3 = exp2f(sc[nt][3] - mn1);
+            rs0 += p0 + p1;
+            rs1 += p2 + p3;
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        l0 = l0 * al0 + rs0;    // per-lane partial sums of the row; the quad is reduced once at the end
+        l1 = l1 * al1 + rs1;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            o[d][0] *= al0; o[d][1] *= al0;
+            o[d][2] *= al1; o[d][3] *= al1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // lane L addresses row (L % 8) of 8x8 matrix L / 8: matrices 0/1 = keys +0 / +8 of dim tile d, 2/3 of d + 1
+            const int key = kc + 16 * j + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                const uint32_t addr = sV_addr + (uint32_t)key * 144u + (uint32_t)(2 * dp + (lane >> 4)) * 16u;
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+                mma16816(o[2 * dp], pa[j], r0, r1);
+                mma16816(o[2 * dp + 1], pa[j], r2, r3);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        const int col = out_off + head * 64 + d * 8 + 2 * t;
+        if (r0 < N)
+            *reinterpret_cast<uint32_t*>(out + ((long long)b * N + r0) * out_ctot + col) = pack_bf16x2(o[d][0] * i0, o[d][1] * i0);
+        if (r1 < N)
+            *reinterpret_cast<uint32_t*>(out + ((long long)b * N + r1) * out_ctot + col) = pack_bf16x2(o[d][2] * i1, o[d][3] * i1);
+    }
+}
+
 // Stand-alone stem launch for the parity tests (cy_stem_conv_nhwc4): w fp32 [cout,3,3,3] (OIHW), bias fp32 [cout].
 int stem_conv_run(const void* in, int B, int H, int W, const float* w_host, const float* bias_host, int cout, int act,
                   void* out, cudaStream_t st) {
@@ -1266,7 +1404,19 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
                 attr_done = true;
             }
             const dim3 grid((unsigned)((N + 63) / 64), (unsigned)op.nh, (unsigned)B);
-            if (kv + (size_t)8 * N * 4 <= 200 * 1024)
+            const int Npad = (N + 63) / 64 * 64;
+            const size_t mma_smem = (size_t)Npad * (80 + 144);
+            const char* simple = getenv("CY_ATTN_SIMPLE");
+            if (!(simple && atoi(simple)) && mma_smem <= 227 * 1024) {
+                static bool mma_attr = false;
+                if (!mma_attr) {
+                    if (cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                        return set_error(CY_ERR_CUDA, "attention attribute failed");
+                    mma_attr = true;
+                }
+                attention_mma_kernel<<<grid, 128, mma_smem, st>>>((const __nv_bfloat16*)op.in.p, op.in.C,
+                                                                 (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N, Npad);
+            } else if (kv + (size_t)8 * N * 4 <= 200 * 1024)
                 attention_kernel<8><<<grid, 256, kv + (size_t)8 * N * 4, st>>>(
                     (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N);
             else if (kv + (size_t)4 * N * 4 <= 220 * 1024)

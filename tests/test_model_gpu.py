@@ -155,3 +155,22 @@ def test_forward_yolo11_matches_oracle(variant, B, Sh, Sw):
         print("%s level %d: max err vs emu %.4f, vs fp32 %.4f (emu vs fp32 %.4f)" % (variant, l, err_emu, err_f32, q))
         assert err_emu < 0.04, (l, err_emu, err_f32, q)
         assert err_f32 < max(0.08, 3 * q), (l, err_emu, err_f32, q)
+
+
+def test_yolo11_attention_kernels_agree(monkeypatch):
+    """The plan launches the mma.sync flash-attention kernel; the CUDA-core kernel (CY_ATTN_SIMPLE=1, also the fallback
+    for maps whose K/V do not fit shared memory in the padded layout) must give the same head maps up to the bf16
+    rounding of P (fp32 softmax weights there, bf16 here)."""
+    from caesar_yolo_b200 import ops, weights as W
+    w = W.make_random_weights('11s', 5, seed=0)
+    dm = ops.DeviceModel(w)
+    x = _to_nhwc4(_input(2, 640, 320, seed=5)).to(DEV)
+    a = [h.clone() for h in dm.forward_tensors(x)]
+    torch.cuda.synchronize()
+    monkeypatch.setenv("CY_ATTN_SIMPLE", "1")
+    b = [h.clone() for h in dm.forward_tensors(x)]
+    torch.cuda.synchronize()
+    for l in range(3):
+        scale = b[l][..., :69].abs().max().item()
+        assert (a[l][..., :69] - b[l][..., :69]).abs().max().item() / scale < 0.02
+    assert any(not torch.equal(a[l], b[l]) for l in range(3))    # two different kernels did run
