@@ -363,10 +363,25 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __r
             acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
         }
     }
+    // branch-free taps: out-of-image rows / columns are read at a clamped address and zeroed, so the compiler can
+    // issue all 18 window loads of the thread back to back
+    uint4 win[3][6];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = y + ky - 1;
-        if (iy < 0 || iy >= H) continue;
+        const bool rok = iy >= 0 && iy < H;
+        const __nv_bfloat16* rowp = in + (((long long)b * H + min(max(iy, 0), H - 1)) * W) * in_ctot + ci;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int ix = x0 - 1 + j;
+            const bool ok = rok && ix >= 0 && ix < W;
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (long long)min(max(ix, 0), W - 1) * in_ctot));
+            if (!ok) v = make_uint4(0u, 0u, 0u, 0u);
+            win[ky][j] = v;
+        }
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
         float wk[3][8];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
@@ -375,13 +390,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __r
             wk[kx][0] = w0.x; wk[kx][1] = w0.y; wk[kx][2] = w0.z; wk[kx][3] = w0.w;
             wk[kx][4] = w1.x; wk[kx][5] = w1.y; wk[kx][6] = w1.z; wk[kx][7] = w1.w;
         }
-        const __nv_bfloat16* rowp = in + (((long long)b * H + iy) * W) * in_ctot + ci;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {   // input column x0 - 1 + j feeds output p = j - kx for kx = 0..2
-            const int ix = x0 - 1 + j;
-            if (ix < 0 || ix >= W) continue;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (long long)ix * in_ctot));
-            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&win[ky][j]);
             float f[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
