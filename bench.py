@@ -327,6 +327,8 @@ def main():
         # dram traffic per launch from the committed ncu capture (profiles/conv_traffic.json), scaled to this batch;
         # algorithmic bytes per launch from the plan (input + weights + output + residual, each once)
         try:
+            if args.variant != 'l' or args.imgsz != 640 or args.tile != 512:
+                raise ValueError('the committed ncu capture is of the yolov8l / 512 / 640 workload')
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_traffic.json')))
             line["roofline"]["traffic"] = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["conv_launches"] * (
                 args.batch / float(tj["tiles"]))
