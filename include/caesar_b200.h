@@ -119,9 +119,10 @@ int cy_stem_conv_nhwc4(const void* in, int B, int H, int W, const float* w_host,
 
 /* ------------------------------------------------------------------------------------------------ model
  * Replaces `YOLO(weights)` (scripts/run.py:347) and `model(image, ...)` (caesar_yolo/evaluation.py:181-193):
- * YOLOv8 n/s/m/l/x DetectionModel.forward with Conv+BN folded.  Tensors are given under their
- * ultralytics state-dict names (model.0.conv.weight, model.0.bn.running_var, ..., model.22.cv3.2.2.bias), fp32,
- * host memory.  forward: in = [B,Sh,Sw,4] bf16 NHWC (cy_preprocess output); heads_host receives three DEVICE
+ * YOLOv8 (variant "n" "s" "m" "l" "x"; yolov8.yaml) or YOLO11 (variant "11n" ... "11x"; yolo11.yaml:
+ * C3k2 / C2PSA / depthwise-separable Detect; the reference README lists yolo11 weights, README.md:200-207)
+ * DetectionModel.forward with Conv+BN folded.  Tensors are given under their ultralytics state-dict names
+ * (model.0.conv.weight, model.0.bn.running_var, ..., model.22.cv3.2.2.bias / model.23... for YOLO11), fp32, host memory.  forward: in = [B,Sh,Sw,4] bf16 NHWC (cy_preprocess output); heads_host receives three DEVICE
  * pointers (owned by the model, valid until the next forward of the same shape) to the raw Detect maps
  * [B, Sh/s, Sw/s, 80] fp32, s = 8,16,32: 64 DFL logits + nc class logits per anchor. */
 int cy_model_create(const char* variant, int nc, void** model_host);
