@@ -57,7 +57,14 @@ static constexpr int kNmsWords = kNmsThreads / 32;
 // Greedy NMS over K boxes already in descending score order.  boxes: global [K] float4.
 // keep_pos: global scratch [>= min(K, max_keep)] receives positions (in sorted order) of kept boxes.
 // Returns number kept (valid in all threads).  Uses static shared memory.
-__device__ int nms_sorted_block(const float4* __restrict__ boxes, int K, double thr, int max_keep, int* keep_pos) {
+struct NoPrep {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+// prep(base): called by every thread before chunk [base, base + 512) is read — the fused path decodes the chunk's
+// boxes there (thread t produces boxes[base + t], the element it reads itself), so only as many candidates are decoded
+// as the greedy pass actually visits before max_keep boxes are kept.
+template <class Prep>
+__device__ int nms_sorted_block(const float4* boxes, int K, double thr, int max_keep, int* keep_pos, Prep prep) {
     __shared__ uint32_t s_mask[kNmsThreads][kNmsWords];
     __shared__ float4 s_kb[256];
     __shared__ float s_ka[256];
@@ -71,6 +78,7 @@ __device__ int nms_sorted_block(const float4* __restrict__ boxes, int K, double 
     for (int base = 0; base < K; base += kNmsThreads) {
         const int nk0 = s_nkeep;
         if (nk0 >= max_keep) break;
+        prep(base);
         const int idx = base + t;
         const bool have = idx < K;
         float4 bx = make_float4(0, 0, 0, 0);
@@ -219,97 +227,167 @@ __global__ void score_key_kernel(HeadLevels L, int B, int nc, float conf, unsign
     }
 }
 
-// Stage 2: one CTA per tile. Sort keys (score desc, anchor asc), decode boxes of the candidates, NMS with class
-// offsets, rescale to tile pixels, emit dets[max_det][6].
+// DFL decode of one candidate (key = score | inverted anchor | class) -> xywh centre form in letterboxed pixels.
+__device__ __forceinline__ void decode_candidate(const HeadLevels& L, int b, unsigned long long key, float& cx, float& cy,
+                                                 float& hw, float& hh, int& cls) {
+    const int a = (int)(0xFFFFFu - (uint32_t)((key >> 8) & 0xFFFFFu));
+    cls = (int)(key & 0xFFu);
+    const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
+    const int la = a - L.a0[l];
+    const float stride = l == 0 ? 8.f : (l == 1 ? 16.f : 32.f);
+    const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC;
+    const float ax = (float)(la % L.w[l]) + 0.5f, ay = (float)(la / L.w[l]) + 0.5f;
+    float d[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float v[16], mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 r = *reinterpret_cast<const float4*>(rec + s * 16 + q * 4);
+            v[4 * q] = r.x; v[4 * q + 1] = r.y; v[4 * q + 2] = r.z; v[4 * q + 3] = r.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mx = fmaxf(mx, v[q]);
+        float sum = 0.f, acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float e = expf(v[q] - mx);
+            sum += e;
+            acc += e * (float)q;
+        }
+        d[s] = acc / sum;
+    }
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
+    cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
+    const float w = __fmul_rn(__fsub_rn(x2, x1), stride), h = __fmul_rn(__fsub_rn(y2, y1), stride);
+    hw = __fdiv_rn(w, 2.f);
+    hh = __fdiv_rn(h, 2.f);
+}
+
+static constexpr int kSelKeys = 4096;     // candidates sorted in shared memory
+static constexpr int kSelBins = 2048;     // score histogram of the dense path (bins of the top 16 score bits)
+static constexpr int kSelTarget = 2048;   // dense path: take at least this many of the best candidates first
+
+// Stage 2: one CTA per tile.  Sort keys (score desc, anchor asc), NMS with class offsets over lazily decoded boxes,
+// rescale to tile pixels, emit dets[max_det][6].
+//  * up to 4096 candidates: the whole list is sorted in shared memory;
+//  * more (dense tiles, BASELINE configs[4]): a histogram over the top 16 score bits finds the score bin above which
+//    2048..4096 candidates lie; only those — exactly the head of the sorted list — are sorted (in shared memory) and
+//    fed to the greedy pass, which stops at max_det kept boxes.  If it runs out of candidates first (rare: > 2048
+//    candidates of which fewer than max_det survive), the full list is sorted in global memory and the pass repeated.
+//  * boxes are decoded chunk by chunk inside the greedy pass (only the chunks it visits), and once more, without the
+//    class offset, for the kept ones (subtracting the offset again would lose bits).
 __global__ void __launch_bounds__(kNmsThreads) nms_tiles_kernel(HeadLevels L, int B, unsigned long long* keys,
                                                                 int key_stride, const int* __restrict__ cand_count,
-                                                                float4* boxes_scratch,
-                                                                int* keep_scratch, double iou_thr, int max_det,
-                                                                int max_nms, float max_wh, const LetterboxInfo* lb,
-                                                                float* __restrict__ dets, int* __restrict__ ndets) {
+                                                                float4* boxes_scratch, int* keep_scratch,
+                                                                unsigned long long* sel_keys, float conf, double iou_thr,
+                                                                int max_det, int max_nms, float max_wh,
+                                                                const LetterboxInfo* lb, float* __restrict__ dets,
+                                                                int* __restrict__ ndets) {
+    extern __shared__ __align__(16) unsigned long long nms_dyn[];
+    unsigned long long* skeys = nms_dyn;                                   // [kSelKeys]
+    int* hist = reinterpret_cast<int*>(nms_dyn + kSelKeys);                // [kSelBins]
+    __shared__ int s_sel, s_thr_bin, s_total;
     const int b = blockIdx.x;
     unsigned long long* k = keys + (long long)b * key_stride;
+    unsigned long long* sel = sel_keys + (long long)b * kSelKeys;
     const int ncand = cand_count[b];
-    int npow2 = 2;
-    while (npow2 < ncand) npow2 <<= 1;
-    for (int i = ncand + threadIdx.x; i < npow2; i += blockDim.x) k[i] = 0ull;
-    __syncthreads();
-    block_bitonic_sort_desc(k, npow2);
-    int K = min(ncand, max_nms);
-    float4* bx = boxes_scratch + (long long)b * key_stride;
-    // decode candidate boxes (xyxy in letterboxed image pixels, + class offset as ultralytics does)
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        const unsigned long long key = k[i];
-        const int a = (int)(0xFFFFFu - (uint32_t)((key >> 8) & 0xFFFFFu));
-        const int cls = (int)(key & 0xFFu);
-        const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
-        const int la = a - L.a0[l];
-        const float stride = l == 0 ? 8.f : (l == 1 ? 16.f : 32.f);
-        const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC;
-        const float ax = (float)(la % L.w[l]) + 0.5f, ay = (float)(la / L.w[l]) + 0.5f;
-        float d[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            float v[16], mx = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                v[q] = rec[s * 16 + q];
-                mx = fmaxf(mx, v[q]);
+    const int Kfull = min(ncand, max_nms);
+    const uint32_t base16 = __float_as_uint(conf) >> 16;
+    auto score_bin = [&](unsigned long long key) {
+        const int v = (int)((uint32_t)(key >> 48)) - (int)base16;
+        return min(max(v, 0), kSelBins - 1);
+    };
+    int n_sel;
+    if (ncand <= kSelKeys) {
+        n_sel = ncand;
+        int n2 = 2;
+        while (n2 < ncand) n2 <<= 1;
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) skeys[i] = i < ncand ? k[i] : 0ull;
+        __syncthreads();
+        block_bitonic_sort_desc(skeys, n2);
+    } else {
+        for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hist[i] = 0;
+        if (threadIdx.x == 0) s_sel = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncand; i += blockDim.x) atomicAdd(&hist[score_bin(k[i])], 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {   // highest bin T with count(bins >= T) >= kSelTarget (bin 0 if there is none)
+            const int lane = threadIdx.x;
+            int part = 0;         // lane owns bins [lane*64, lane*64+64)
+            for (int q = 0; q < kSelBins / 32; ++q) part += hist[lane * (kSelBins / 32) + q];
+            int above = 0;        // candidates in the lanes above mine
+            for (int o = 0; o < 32; ++o) {
+                const int v = __shfl_sync(0xffffffffu, part, o);
+                if (o > lane) above += v;
             }
-            float sum = 0.f, acc = 0.f;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float e = expf(v[q] - mx);
-                sum += e;
-                acc += e * (float)q;
+            const bool mine = above < kSelTarget && above + part >= kSelTarget;
+            const uint32_t who = __ballot_sync(0xffffffffu, mine);
+            if (who == 0u) {
+                if (lane == 0) { s_thr_bin = 0; s_total = above + part; }
+            } else if (mine) {
+                int acc = above, T = lane * (kSelBins / 32);
+                for (int q = kSelBins / 32 - 1; q >= 0; --q) {
+                    acc += hist[lane * (kSelBins / 32) + q];
+                    if (acc >= kSelTarget) { T = lane * (kSelBins / 32) + q; break; }
+                }
+                s_thr_bin = T;
+                s_total = acc;
             }
-            d[s] = acc / sum;
         }
-        const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
-        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
-        const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
-        const float w = __fmul_rn(__fsub_rn(x2, x1), stride), h = __fmul_rn(__fsub_rn(y2, y1), stride);
-        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
-        const float off = __fmul_rn((float)cls, max_wh);
-        bx[i] = make_float4(__fadd_rn(__fsub_rn(cx, hw), off), __fadd_rn(__fsub_rn(cy, hh), off),
-                            __fadd_rn(__fadd_rn(cx, hw), off), __fadd_rn(__fadd_rn(cy, hh), off));
+        __syncthreads();
+        if (s_total <= kSelKeys) {
+            const int T = s_thr_bin;
+            for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+                const unsigned long long key = k[i];
+                if (score_bin(key) >= T) skeys[atomicAdd(&s_sel, 1)] = key;
+            }
+            __syncthreads();
+            n_sel = s_sel;
+            int n2 = 2;
+            while (n2 < n_sel) n2 <<= 1;
+            for (int i = n_sel + threadIdx.x; i < n2; i += blockDim.x) skeys[i] = 0ull;
+            __syncthreads();
+            block_bitonic_sort_desc(skeys, n2);
+        } else {
+            n_sel = 0;   // one score bin holds thousands of candidates: straight to the full sort
+        }
     }
+    for (int i = threadIdx.x; i < n_sel; i += blockDim.x) sel[i] = skeys[i];
     __syncthreads();
+    float4* bx = boxes_scratch + (long long)b * key_stride;
     int* kp = keep_scratch + (long long)b * max_det;
-    const int nk = nms_sorted_block(bx, K, iou_thr, max_det, kp);
-    // output: undo class offset by re-deriving? No: ultralytics returns x[i] = un-offset boxes.  We recompute them
-    // from the offset ones would lose bits, so decode again from the head record for the kept few.
+    const unsigned long long* ks = sel;
+    auto prep = [&](int base) {
+        const int i = base + (int)threadIdx.x;
+        if (i < (ks == sel ? n_sel : Kfull)) {
+            float cx, cy, hw, hh;
+            int cls;
+            decode_candidate(L, b, ks[i], cx, cy, hw, hh, cls);
+            const float off = __fmul_rn((float)cls, max_wh);   // class offset as ultralytics does (agnostic = False)
+            bx[i] = make_float4(__fadd_rn(__fsub_rn(cx, hw), off), __fadd_rn(__fsub_rn(cy, hh), off),
+                                __fadd_rn(__fadd_rn(cx, hw), off), __fadd_rn(__fadd_rn(cy, hh), off));
+        }
+    };
+    int nk = n_sel > 0 ? nms_sorted_block(bx, min(n_sel, max_nms), iou_thr, max_det, kp, prep) : 0;
+    if (n_sel < Kfull && nk < max_det) {   // the head of the list was not enough: full sort, full pass
+        int npow2 = 2;
+        while (npow2 < ncand) npow2 <<= 1;
+        __syncthreads();
+        for (int i = ncand + threadIdx.x; i < npow2; i += blockDim.x) k[i] = 0ull;
+        __syncthreads();
+        block_bitonic_sort_desc(k, npow2);
+        ks = k;
+        nk = nms_sorted_block(bx, Kfull, iou_thr, max_det, kp, prep);
+    }
     const LetterboxInfo li = lb[b];
     for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-        const unsigned long long key = k[kp[i]];
-        const int a = (int)(0xFFFFFu - (uint32_t)((key >> 8) & 0xFFFFFu));
-        const int cls = (int)(key & 0xFFu);
+        const unsigned long long key = ks[kp[i]];
         const float score = __uint_as_float((uint32_t)(key >> 32));
-        const int l = a >= L.a0[2] ? 2 : (a >= L.a0[1] ? 1 : 0);
-        const int la = a - L.a0[l];
-        const float stride = l == 0 ? 8.f : (l == 1 ? 16.f : 32.f);
-        const float* rec = L.p[l] + ((long long)b * L.h[l] * L.w[l] + la) * kHeadC;
-        const float ax = (float)(la % L.w[l]) + 0.5f, ay = (float)(la / L.w[l]) + 0.5f;
-        float d[4];
-        for (int s = 0; s < 4; ++s) {
-            float v[16], mx = -INFINITY;
-            for (int q = 0; q < 16; ++q) {
-                v[q] = rec[s * 16 + q];
-                mx = fmaxf(mx, v[q]);
-            }
-            float sum = 0.f, acc = 0.f;
-            for (int q = 0; q < 16; ++q) {
-                const float e = expf(v[q] - mx);
-                sum += e;
-                acc += e * (float)q;
-            }
-            d[s] = acc / sum;
-        }
-        const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
-        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
-        const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
-        const float w = __fmul_rn(__fsub_rn(x2, x1), stride), h = __fmul_rn(__fsub_rn(y2, y1), stride);
-        const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+        float cx, cy, hw, hh;
+        int cls;
+        decode_candidate(L, b, key, cx, cy, hw, hh, cls);
         // scale_boxes: subtract pad, divide by gain, clip to the original tile
         float bx1 = __fdiv_rn(__fsub_rn(__fsub_rn(cx, hw), li.pad_x), li.gain);
         float by1 = __fdiv_rn(__fsub_rn(__fsub_rn(cy, hh), li.pad_y), li.gain);
@@ -350,7 +428,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_generic_kernel(const float* _
     }
     __syncthreads();
     int* kp = keep_pos + (long long)b * stride_n;
-    const int nk = nms_sorted_block(bs, N, thr, max_keep, kp);
+    const int nk = nms_sorted_block(bs, N, thr, max_keep, kp, NoPrep());
     for (int i = threadIdx.x; i < nk; i += blockDim.x)
         keep[(long long)b * stride_n + i] = (long long)(0xFFFFFFFFu - (uint32_t)(k[kp[i]] & 0xFFFFFFFFull));
     if (threadIdx.x == 0) nkeep[b] = nk;
@@ -521,7 +599,7 @@ static int next_pow2(int n) {
 size_t postprocess_scratch_bytes(int B, int Sh, int Sw, int max_det) {
     const int np2 = next_pow2(num_anchors(Sh, Sw));
     return (size_t)B * np2 * (sizeof(unsigned long long) + sizeof(float4)) + (size_t)B * max_det * sizeof(int) +
-           (size_t)B * sizeof(int) + 256;
+           (size_t)B * sizeof(int) + 256 + (size_t)B * kSelKeys * sizeof(unsigned long long) + 256;
 }
 
 int postprocess(const float* h0, const float* h1, const float* h2, int B, int Sh, int Sw, int nc, float conf,
@@ -534,11 +612,18 @@ int postprocess(const float* h0, const float* h1, const float* h2, int B, int Sh
     float4* boxes = (float4*)(keys + (size_t)B * np2);
     int* keep = (int*)(boxes + (size_t)B * np2);
     int* cand = keep + (size_t)B * max_det;
+    unsigned long long* sel = (unsigned long long*)(((uintptr_t)(cand + B) + 255) & ~(uintptr_t)255);
+    const int dyn = kSelKeys * (int)sizeof(unsigned long long) + kSelBins * (int)sizeof(int);
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(nms_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) return -1;
+        attr_done = true;
+    }
     const long long total = (long long)B * L.A;
     cudaMemsetAsync(cand, 0, (size_t)B * sizeof(int), st);
     score_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, B, nc, conf, keys, np2, cand);
-    nms_tiles_kernel<<<B, kNmsThreads, 0, st>>>(L, B, keys, np2, cand, boxes, keep, (double)iou, max_det, 30000,
-                                                7680.f, lb, dets, ndets);
+    nms_tiles_kernel<<<B, kNmsThreads, dyn, st>>>(L, B, keys, np2, cand, boxes, keep, sel, conf, (double)iou, max_det,
+                                                  30000, 7680.f, lb, dets, ndets);
     return (int)cudaGetLastError();
 }
 
