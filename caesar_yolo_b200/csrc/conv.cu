@@ -667,10 +667,12 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     // CTA pairs: 128-byte channel chunks, a weight tile that splits into two halves of >= 32 rows, and enough units
     // to give every pair of SMs work
     // Measured per layer (profiles/): pairs win once the K loop is long enough to amortise the cluster hand-shakes
-    // (K = taps * cin >= 768); short-K layers are epilogue-bound and run better as independent CTAs.
+    // (K = taps * cin >= 768, or >= 512 without a residual operand: re-measured per layer at batch 296 — K = 576 / 640
+    // layers gain 5-12 % unless they carry a residual (then -11 %), K <= 320 layers lose 9-35 %); short-K layers are
+    // epilogue-bound and run better as independent CTAs.
     int pair = 0;
     const bool pair_ok = kc == 64 && bn_ >= 64;
-    if (pair_ok && ntaps * d.cin >= 768 &&
+    if (pair_ok && ntaps * d.cin >= (d.res ? 768 : env_int("CY_CONV_PAIR_MINK", 512)) &&
         ((kp.n_half_tiles + 2 * halves - 1) / (2 * halves)) * kp.n_tiles_n >= num_sms() / 2)
         pair = 1;
     const int force_pair = env_int("CY_CONV_PAIR", -1);   // -1 auto, 0 off, 2 force wherever possible
