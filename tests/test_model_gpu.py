@@ -131,7 +131,8 @@ def test_postprocess_matches_oracle(B, Sh, Sw, Ty, Tx, conf, bias):
 
 
 @pytest.mark.parametrize("variant,B,Sh,Sw", [('11n', 2, 640, 640), ('11n', 1, 640, 320), ('11s', 1, 320, 320),
-                                             ('11l', 2, 320, 320), ('11x', 1, 256, 256)])
+                                             ('11l', 2, 320, 320), ('11x', 1, 256, 256),
+                                             ('11n', 1, 1024, 1024)])   # 1024 attention positions: the largest map
 def test_forward_yolo11_matches_oracle(variant, B, Sh, Sw):
     """YOLO11 (C3k2 / C3k, C2PSA attention, depthwise-separable class branch) on the tcgen05 conv stack + the
     depthwise-conv and attention kernels vs the oracle restatement (bf16-emulated and fp32)."""
