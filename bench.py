@@ -197,9 +197,10 @@ def workload_config(args, n, T=None):
     if T is None:
         from caesar_yolo_b200 import ops
         T = len(ops.generate_tiles(0, args.mosaic - 1, 0, args.mosaic - 1, args.tile, args.tile, args.step, args.step))
-    return {"workload": "synthetic %dx%d f32 mosaic (FITS byte order), %dx%d tiles step %.1f (%d tiles), YOLOv8%s nc=5 "
+    return {"workload": "synthetic %dx%d f32 mosaic (FITS byte order), %dx%d tiles step %.1f (%d tiles), %s nc=5 "
                         "random-init, imgsz %d, full preprocessing chain, FITS payload -> merged catalog"
-                        % (args.mosaic, args.mosaic, args.tile, args.tile, args.step, T, args.variant, args.imgsz),
+                        % (args.mosaic, args.mosaic, args.tile, args.tile, args.step, T,
+                           ("YOLO" + args.variant) if args.variant.startswith('11') else ("YOLOv8" + args.variant), args.imgsz),
             "tiles": T, "tile_batch": args.batch, "parallelism": "tile-row bands x%d + NCCL all-gather of records" % n,
             "l2": "inputs larger than L2 (mosaic band >= 134 MB, activations > 1 GB per batch)",
             "score_thr": SCORE_THR, "iou_thr": IOU_THR}
