@@ -65,6 +65,14 @@ def test_validation_errors_return_1(tmp_path):
     assert run.main(['--weights', str(w), '--image', str(txt)]) == 1               # extension check
     # chan3_preproc needs nchannels == 3 (reference scripts/run.py:253-256)
     assert run.main(['--weights', str(w), '--image', str(img), '--preprocessing', '--chan3_preproc']) == 1
+    # .png / .jpg pass the extension check (scripts/run.py:164) but only whole-image runs can use them: tiles are cut
+    # with read_fits_crop in the reference (inference.py:190-195)
+    png = tmp_path / "a.png"
+    png.write_bytes(b"x")
+    args = run.parse_args(['--weights', str(w), '--image', str(png)])
+    assert run.validate_args(args) == 0
+    args = run.parse_args(['--weights', str(w), '--image', str(png), '--split_img_in_tiles'])
+    assert run.validate_args(args) == -1
 
 
 def test_writers_formats(tmp_path):
