@@ -179,7 +179,7 @@ def count_parameters11(variant, nc=80):
 
 def make_random_weights11(variant='11n', nc=5, seed=0, cls_bias=-3.0, calibration='auto'):
     """Seeded random-init yolo11 with the ultralytics state-dict key names (same recipe as make_random_weights: BN
-    running statistics from init_calibration.json for the (variant, seed) pairs tools/calibrate_init.py lists)."""
+    running statistics from init_calibration.json for the (variant, seed) pairs tests/diag/calibrate_init.py lists)."""
     calib = _load_calibration(variant, seed) if calibration == 'auto' else calibration
     g = torch.Generator().manual_seed(seed)
     sd = {}
@@ -214,7 +214,7 @@ def _load_calibration(variant, seed):
 def make_random_weights(variant='n', nc=5, seed=0, cls_bias=-3.0, calibration='auto'):
     """Seeded random-init YOLOv8 (our own init; the reference has none).  Conv weights ~ N(0, 1/fan_in); the BN
     running statistics come from init_calibration.json (per-layer scalar mean/var of the pre-BN activation on a
-    synthetic preprocessed tile, produced by tools/calibrate_init.py for the (variant, seed) pairs it lists; other
+    synthetic preprocessed tile, produced by tests/diag/calibrate_init.py for the (variant, seed) pairs it lists; other
     seeds fall back to mean 0 / var 1) so that every layer works at unit scale and detections depend on the image.  The class-branch bias sets the candidate density; a linear DFL bias keeps
     boxes a few cells wide."""
     if is_yolo11(variant):

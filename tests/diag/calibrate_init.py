@@ -1,6 +1,6 @@
 """Generates caesar_yolo_b200/init_calibration.json: per-layer scalar (mean, var) of the pre-BN conv output
 for the seeded random init, measured with the CPU oracle on synthetic preprocessed tiles.  Run once, commit
-the JSON.  Usage: python tools/calibrate_init.py [variant:seed ...]"""
+the JSON.  Usage: python tests/diag/calibrate_init.py [variant:seed ...]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from caesar_yolo_b200 import synth, weights as W  # noqa: E402
 from oracle import preprocessing as opp, yolo as oy, yolo11 as oy11  # noqa: E402

@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from caesar_yolo_b200 import ops, pipeline, synth, weights as W  # noqa: E402
 from oracle import preprocessing as opp, yolo as oy  # noqa: E402

@@ -3,7 +3,7 @@
 against this path's catalog?  Prints, for every unmatched oracle source, the best IoU of any source here (any class),
 that partner's class / score, and whether it is a merged (cross-tile hull) source.
 
-usage: python tools/diag_robust.py [--step 1.0] [--thr-hi 0.6]
+usage: python tests/diag/diag_robust.py [--step 1.0] [--thr-hi 0.6]
 """
 import argparse
 import json
@@ -13,7 +13,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 

@@ -7,7 +7,7 @@ Why the bar here is not 99.5 %: with RANDOM-INIT weights the detections are the 
 distribution (threshold ~4 sigma out), where the fraction of sources that appear/disappear under a logit perturbation
 d is about hazard(4 sigma) * d / sigma ~ 4 d / sigma.  bf16 storage alone gives d/sigma ~ 1 % (oracle-bf16 vs
 oracle-fp32 catalogs agree at only ~0.90), and the tensor-core accumulation order adds about half of that between this
-path and the bf16-emulating oracle (measured head-map rms: ours-emu 0.02, emu-fp32 0.04; tools/diag_heads.py).  Every
+path and the bf16-emulating oracle (measured head-map rms: ours-emu 0.02, emu-fp32 0.04; tests/diag/diag_heads.py).  Every
 stage AFTER the head maps is bit-exact (tests/test_model_gpu.py, test_nms_merge_gpu.py).  So the asserts are relative:
 this path must agree with the fp32 oracle at least as well as the bf16-emulating oracle does (minus a small margin),
 and the measured fractions are printed for the record (profiles/)."""
