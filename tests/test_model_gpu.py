@@ -175,3 +175,37 @@ def test_yolo11_attention_kernels_agree(monkeypatch):
         scale = b[l][..., :69].abs().max().item()
         assert (a[l][..., :69] - b[l][..., :69]).abs().max().item() / scale < 0.02
     assert any(not torch.equal(a[l], b[l]) for l in range(3))    # two different kernels did run
+
+
+def test_postprocess_dense_tile_that_runs_out_of_candidates():
+    """Dense-tile path of the fused NMS: with more than 4096 candidates only the head of the sorted list is sorted and
+    fed to the greedy pass; when that head is exhausted before max_det boxes are kept the kernel must fall back to the
+    full sort and still return exactly the ultralytics result.  Here every anchor is a candidate of ONE class and the
+    boxes are ~30 cells wide, so NMS keeps far fewer than 300 of the 21 504 candidates."""
+    from caesar_yolo_b200 import ops
+    B, S, nc, conf = 2, 1024, 5, 0.05
+    g = torch.Generator().manual_seed(7)
+    heads = []
+    for s in (8, 16, 32):
+        h = torch.zeros(B, S // s, S // s, 80)
+        dfl = torch.randn(B, S // s, S // s, 4, 16, generator=g) * 0.3
+        dfl[..., 15] += 8.0                                     # ltrb distances ~15 cells: boxes ~30 cells wide
+        h[..., :64] = dfl.reshape(B, S // s, S // s, 64)
+        h[..., 64] = 1.0 + torch.randn(B, S // s, S // s, generator=g)
+        h[..., 65:64 + nc] = -20.0
+        heads.append(h)
+    _, _, lb = ops.letterbox_shape(512, 512, S)
+    lbd = ops.letterbox_array([lb] * B, DEV)
+    dets, nd = ops.postprocess([h.to(DEV) for h in heads], B, S, S, nc, conf, 0.5, lbd, DEV)
+    dets, nd = dets.cpu(), nd.cpu()
+    pred = ops.decode_pred([h.to(DEV) for h in heads], B, S, S, nc, DEV).cpu()
+    for b in range(B):
+        assert int((pred[b, 4:].amax(0) > conf).sum()) > 4096
+        want = oy.nms_single(pred[b], conf, 0.5)
+        assert 0 < want.shape[0] < 300                           # the greedy pass cannot stop early
+        want[:, :4] = oy.scale_boxes((S, S), want[:, :4], (512, 512))
+        n = int(nd[b])
+        assert n == want.shape[0]
+        got = dets[b, :n]
+        assert torch.equal(got[:, 4], want[:, 4]) and torch.equal(got[:, 5], want[:, 5])
+        assert torch.allclose(got[:, :4], want[:, :4], rtol=0, atol=2e-3)
