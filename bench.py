@@ -29,13 +29,22 @@ os.environ['NCCL_DEBUG'] = 'WARN'   # keep warnings; the banner it prints is kep
 # The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
 # version banner there at WARN/INFO), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
 # private duplicate of the original stdout.
-_JSON_OUT = os.fdopen(os.dup(1), 'w')
-os.dup2(2, 1)
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Called once by main(): keeps a private handle on the real stdout and sends everything else to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
 
 
 def emit(line):
-    _JSON_OUT.write(json.dumps(line) + "\n")
-    _JSON_OUT.flush()
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 PP_FLAGS = dict(subtract_bkg=True, clip_data=True, zscale_stretch=True, chan3_preproc=True, normalize_minmax=True,
                 nchannels=3, norm_max=255.)
@@ -208,6 +217,7 @@ def workload_config(args, n, T=None):
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == 'reference':
         return run_reference(args)
     import torch
