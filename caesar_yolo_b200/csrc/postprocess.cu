@@ -472,7 +472,15 @@ __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict
         return;
     }
     const int n_in = min(ndets[b], kMergeMaxN);
-    const float* D = dets + (long long)b * det_stride * 6;
+    // the tile's detections are staged in shared memory first: the ordered compaction below is done by one thread, and
+    // reading its 6 x 300 values straight from global memory was ~300 dependent L2 round trips
+    __shared__ float s_raw[kMergeMaxN * 6];
+    {
+        const float* G = dets + (long long)b * det_stride * 6;
+        for (int i = threadIdx.x; i < n_in * 6; i += blockDim.x) s_raw[i] = G[i];
+    }
+    __syncthreads();
+    const float* D = s_raw;
     if (threadIdx.x == 0) {
         // score filter keeps order (evaluation.py:276-287); sequential compaction of <=300 entries
         int n = 0, bad = 0;
