@@ -225,3 +225,155 @@ def test_yolo11_state_dict_roundtrip_and_variant_inference(tmp_path):
     torch.save(sd, str(tmp_path / 'bad.pt'))
     with pytest.raises(ValueError, match="does not match any yolo11 scale"):
         W.load_weights(str(tmp_path / 'bad.pt'))
+
+
+def _fake_package11():
+    """Throw-away `ultralytics.*` modules with the attribute layout of the YOLO11 blocks (Conv / DWConv / Bottleneck /
+    C3k / C3k2 / SPPF / Attention / PSABlock / C2PSA / Detect with the depthwise-separable class branch)."""
+    mods = {n: types.ModuleType(n) for n in _MODS}
+
+    def reg(modname):
+        def deco(cls):
+            cls.__module__ = modname
+            cls.__qualname__ = cls.__name__
+            setattr(mods[modname], cls.__name__, cls)
+            return cls
+        return deco
+
+    @reg('ultralytics.nn.modules.conv')
+    class Conv(nn.Module):
+        def __init__(self, c1, c2, k=1, s=1, g=1, act=True):
+            super().__init__()
+            self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=False)
+            self.bn = nn.BatchNorm2d(c2, eps=1e-3, momentum=0.03)
+            self.act = nn.SiLU() if act else nn.Identity()
+
+    @reg('ultralytics.nn.modules.conv')
+    class DWConv(Conv):
+        def __init__(self, c1, c2, k=1, s=1):
+            super().__init__(c1, c2, k, s, g=c1)
+
+    @reg('ultralytics.nn.modules.conv')
+    class Concat(nn.Module):
+        def __init__(self, d=1):
+            super().__init__()
+            self.d = d
+
+    @reg('ultralytics.nn.modules.block')
+    class Bottleneck(nn.Module):
+        def __init__(self, c1, c2, e=0.5):
+            super().__init__()
+            c_ = int(c2 * e)
+            self.cv1, self.cv2, self.add = Conv(c1, c_, 3), Conv(c_, c2, 3), True
+
+    @reg('ultralytics.nn.modules.block')
+    class C3k(nn.Module):
+        def __init__(self, c1, c2, n=2):
+            super().__init__()
+            c_ = int(c2 * 0.5)
+            self.cv1, self.cv2, self.cv3 = Conv(c1, c_, 1), Conv(c1, c_, 1), Conv(2 * c_, c2, 1)
+            self.m = nn.Sequential(*(Bottleneck(c_, c_, e=1.0) for _ in range(n)))
+
+    @reg('ultralytics.nn.modules.block')
+    class C3k2(nn.Module):
+        def __init__(self, c1, c2, n, c3k, e=0.5):
+            super().__init__()
+            self.c = int(c2 * e)
+            self.cv1, self.cv2 = Conv(c1, 2 * self.c, 1), Conv((2 + n) * self.c, c2, 1)
+            self.m = nn.ModuleList(C3k(self.c, self.c, 2) if c3k else Bottleneck(self.c, self.c) for _ in range(n))
+
+    @reg('ultralytics.nn.modules.block')
+    class SPPF(nn.Module):
+        def __init__(self, c1, c2):
+            super().__init__()
+            self.cv1, self.cv2 = Conv(c1, c1 // 2, 1), Conv(c1 * 2, c2, 1)
+            self.m = nn.MaxPool2d(5, 1, 2)
+
+    @reg('ultralytics.nn.modules.block')
+    class Attention(nn.Module):
+        def __init__(self, dim, num_heads, attn_ratio=0.5):
+            super().__init__()
+            self.num_heads, self.head_dim = num_heads, dim // num_heads
+            self.key_dim = int(self.head_dim * attn_ratio)
+            self.qkv = Conv(dim, dim + 2 * self.key_dim * num_heads, 1, act=False)
+            self.proj = Conv(dim, dim, 1, act=False)
+            self.pe = Conv(dim, dim, 3, 1, g=dim, act=False)
+
+    @reg('ultralytics.nn.modules.block')
+    class PSABlock(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.attn = Attention(c, c // 64)
+            self.ffn = nn.Sequential(Conv(c, c * 2, 1), Conv(c * 2, c, 1, act=False))
+
+    @reg('ultralytics.nn.modules.block')
+    class C2PSA(nn.Module):
+        def __init__(self, c1, n):
+            super().__init__()
+            self.c = c1 // 2
+            self.cv1, self.cv2 = Conv(c1, 2 * self.c, 1), Conv(2 * self.c, c1, 1)
+            self.m = nn.Sequential(*(PSABlock(self.c) for _ in range(n)))
+
+    @reg('ultralytics.nn.modules.block')
+    class DFL(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(16, 1, 1, bias=False).requires_grad_(False)
+            self.conv.weight.data[:] = torch.arange(16, dtype=torch.float).view(1, 16, 1, 1)
+
+    @reg('ultralytics.nn.modules.head')
+    class Detect(nn.Module):
+        def __init__(self, nc, ch, cb, cc):
+            super().__init__()
+            self.nc = nc
+            self.cv2 = nn.ModuleList(nn.Sequential(Conv(c, cb, 3), Conv(cb, cb, 3), nn.Conv2d(cb, 64, 1)) for c in ch)
+            self.cv3 = nn.ModuleList(nn.Sequential(nn.Sequential(DWConv(c, c, 3), Conv(c, cc, 1)),
+                                                   nn.Sequential(DWConv(cc, cc, 3), Conv(cc, cc, 1)),
+                                                   nn.Conv2d(cc, nc, 1)) for c in ch)
+            self.dfl = DFL()
+
+    @reg('ultralytics.nn.tasks')
+    class DetectionModel(nn.Module):
+        def __init__(self, variant, nc, names):
+            super().__init__()
+            a = W.arch11(variant)
+            c64, c128, c256, c512, c1024, n, big = (a['c64'], a['c128'], a['c256'], a['c512'], a['c1024'], a['n'],
+                                                    a['c3k'])
+            cb, cc = max(16, c256 // 4, 64), max(c256, min(nc, 100))
+            up = lambda: nn.Upsample(None, 2, 'nearest')
+            self.model = nn.Sequential(
+                Conv(3, c64, 3, 2), Conv(c64, c128, 3, 2), C3k2(c128, c256, n, big, 0.25), Conv(c256, c256, 3, 2),
+                C3k2(c256, c512, n, big, 0.25), Conv(c512, c512, 3, 2), C3k2(c512, c512, n, True),
+                Conv(c512, c1024, 3, 2), C3k2(c1024, c1024, n, True), SPPF(c1024, c1024), C2PSA(c1024, n), up(),
+                Concat(), C3k2(c1024 + c512, c512, n, big), up(), Concat(), C3k2(c512 + c512, c256, n, big),
+                Conv(c256, c256, 3, 2), Concat(), C3k2(c256 + c512, c512, n, big), Conv(c512, c512, 3, 2), Concat(),
+                C3k2(c512 + c1024, c1024, n, True), Detect(nc, (c256, c512, c1024), cb, cc))
+            self.names = names
+    return mods, DetectionModel
+
+
+@pytest.mark.parametrize("variant", ['11n', '11l'])
+def test_yolo11_checkpoint_loads_without_ultralytics(tmp_path, variant):
+    """A pickled YOLO11 DetectionModel (module tree with the ultralytics attribute names, built from throw-away
+    classes) loads through the stand-in unpickler; the state-dict keys of that tree are exactly the keys of this build's
+    layer table, and the parameter count of the tree at nc = 80 is the published one."""
+    mods, DetectionModel = _fake_package11()
+    ours = W.make_random_weights(variant, 5, seed=4)
+    p = str(tmp_path / 'yolo11.pt')
+    sys.modules.update(mods)
+    try:
+        m = DetectionModel(variant, 5, dict(W.CLASS_NAMES))
+        missing, unexpected = m.load_state_dict(ours['state_dict'], strict=False)
+        assert not unexpected and all(k.endswith('num_batches_tracked') for k in missing), (missing, unexpected)
+        m80 = DetectionModel(variant, 80, {i: str(i) for i in range(80)})
+        assert sum(p_.numel() for p_ in m80.parameters()) == {'11n': 2624080, '11l': 25372160}[variant]
+        torch.save({'epoch': -1, 'model': m.half(), 'ema': None, 'train_args': {}}, p)
+    finally:
+        for n in _MODS:
+            sys.modules.pop(n, None)
+    assert 'ultralytics' not in sys.modules
+    w = W.load_weights(p)
+    assert w['variant'] == variant and w['nc'] == 5 and w['names'] == W.CLASS_NAMES
+    assert set(w['state_dict']) == set(ours['state_dict'])
+    for k, v in ours['state_dict'].items():
+        assert torch.equal(w['state_dict'][k], v.half().float()), k
