@@ -98,3 +98,26 @@ def test_generate_tiles_micro():
     t = outils.generate_tiles(0, 131, 0, 131, 64, 64, .5, .5)
     assert len(t) == 25 and t[-1] == (128, 132, 128, 132) and t[0] == (0, 64, 0, 64)
     assert len(outils.generate_tiles(0, 32767, 0, 32767, 512, 512, .5, .5)) == 16384
+
+
+def test_yolo11_oracle_attention_against_torch_sdpa():
+    """oracle/yolo11.py's Attention (written out with explicit matmuls like the ultralytics module) against
+    torch.nn.functional.scaled_dot_product_attention on the same q, k, v split + the depthwise `pe` and `proj` convs."""
+    import torch
+    import torch.nn.functional as F
+    from caesar_yolo_b200 import weights as W
+    from oracle.yolo11 import OracleYolo11
+    w = W.make_random_weights('11n', 5, seed=0)
+    net = OracleYolo11(w)
+    p = 'model.10.m.0.attn'
+    C, H, Wd = 128, 6, 5
+    x = torch.randn(2, C, H, Wd, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        got = net.attention(x, p)
+        nh, kd, hd, N = C // 64, 32, 64, H * Wd
+        qkv = net.conv(x, p + '.qkv', 1, 1, act=False).view(2, nh, 2 * kd + hd, N)
+        q, k, v = qkv[:, :, :kd], qkv[:, :, kd:2 * kd], qkv[:, :, 2 * kd:]
+        o = F.scaled_dot_product_attention(q.transpose(-2, -1), k.transpose(-2, -1), v.transpose(-2, -1))  # [B,nh,N,hd]
+        o = o.transpose(-2, -1).reshape(2, C, H, Wd) + net.conv(v.reshape(2, C, H, Wd), p + '.pe', 3, 1, act=False)
+        want = net.conv(o, p + '.proj', 1, 1, act=False)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
