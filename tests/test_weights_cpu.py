@@ -377,3 +377,17 @@ def test_yolo11_checkpoint_loads_without_ultralytics(tmp_path, variant):
     assert set(w['state_dict']) == set(ours['state_dict'])
     for k, v in ours['state_dict'].items():
         assert torch.equal(w['state_dict'][k], v.half().float()), k
+
+
+def test_yolo11_conv_gflops_match_published():
+    """2 x conv MACs of the layer table at 640 x 640, nc = 80 (each layer at the stride its position in yolo11.yaml
+    gives it) against the GFLOPs ultralytics publishes for the fused models: pins the strides / resolutions of the
+    graph on top of the parameter counts."""
+    def res_of(p):
+        i = int(p.split('.')[1])
+        if i == 23:
+            return (80, 40, 20)[int(p.split('.')[3])]
+        return {0: 320, 1: 160, 2: 160, 3: 80, 4: 80, 16: 80, 5: 40, 6: 40, 13: 40, 17: 40, 19: 40}.get(i, 20)
+    for v, pub in (('11n', 6.5), ('11s', 21.5), ('11m', 68.0), ('11l', 86.9), ('11x', 194.9)):
+        macs = sum(res_of(p) ** 2 * cout * (cin // g) * k * k for (p, cin, cout, k, g, bn) in W.conv_layers11(v, 80))
+        assert abs(2 * macs / 1e9 - pub) < 0.06, (v, 2 * macs / 1e9, pub)
