@@ -20,8 +20,9 @@ PARITY STATUS — pinned where the reference's code can execute here, unpinned f
    their published algorithms (astropy.stats.sigma_clipping, ZScaleInterval, skimage equalize_hist, ultralytics
    LetterBox / YOLOv8 DetectionModel / Detect decode / non_max_suppression / scale_boxes) and uses
    the installed libraries directly where they exist (numpy, cv2.resize, torchvision.ops.nms, torch CPU conv2d).
-   oracle/yolo11.py (YOLO11: C3k2 / C2PSA / depthwise-separable Detect) is such a restatement too; its layer table is
-   pinned only by the parameter counts ultralytics publishes for the five scales (tests/test_weights_cpu.py).
+   oracle/yolo11.py (YOLO11: C3k2 / C2PSA / depthwise-separable Detect) is such a restatement too.  The layer tables
+   of both model families are pinned by the parameter counts and GFLOPs ultralytics publishes for all ten scales
+   (tests/test_weights_cpu.py); the forward semantics on top of them are not.
    The reference's only fixture, test/galaxy0001.fits, is a known-answer input whose expected statistics match the
    survey-time hand probe (tests/golden/galaxy0001_golden.json, make_golden.py).
 """

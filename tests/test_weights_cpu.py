@@ -391,3 +391,24 @@ def test_yolo11_conv_gflops_match_published():
     for v, pub in (('11n', 6.5), ('11s', 21.5), ('11m', 68.0), ('11l', 86.9), ('11x', 194.9)):
         macs = sum(res_of(p) ** 2 * cout * (cin // g) * k * k for (p, cin, cout, k, g, bn) in W.conv_layers11(v, 80))
         assert abs(2 * macs / 1e9 - pub) < 0.06, (v, 2 * macs / 1e9, pub)
+
+
+def test_yolov8_parameter_counts_and_gflops_match_published():
+    """The yolov8 layer table (yolov8.yaml restated in weights.conv_bn_layers / the device model's graph builder / the
+    oracle) against the numbers ultralytics publishes for nc = 80: parameter counts of the unfused models and GFLOPs
+    of the fused models at 640 x 640 (2 x conv MACs at each layer's stride)."""
+    want = {'n': (3157200, 8.7), 's': (11166560, 28.6), 'm': (25902640, 78.9), 'l': (43691520, 165.2),
+            'x': (68229648, 257.8)}
+
+    def res_of(p):
+        i = int(p.split('.')[1])
+        if i == 22:
+            return (80, 40, 20)[int(p.split('.')[3])]
+        return {0: 320, 1: 160, 2: 160, 3: 80, 4: 80, 15: 80, 5: 40, 6: 40, 12: 40, 16: 40, 18: 40}.get(i, 20)
+    for v, (npar, gf) in want.items():
+        L, cb, cc = W.conv_bn_layers(v, 80)
+        params = 16 + sum(cout * cin * k * k + 2 * cout for (_, cin, cout, k) in L) + 3 * (64 * cb + 64 + 80 * cc + 80)
+        macs = sum(res_of(p) ** 2 * cout * cin * k * k for (p, cin, cout, k) in L)
+        macs += sum(r * r * (64 * cb + 80 * cc) for r in (80, 40, 20))
+        assert params == npar, (v, params)
+        assert abs(2 * macs / 1e9 - gf) < 0.06, (v, 2 * macs / 1e9)
