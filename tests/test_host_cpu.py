@@ -153,3 +153,50 @@ def test_read_raster_follows_plt_imread(tmp_path):
     assert a.dtype == np.uint8 and a.shape == (7, 9)
     a = read_raster(p('rgb.jpg'))
     assert a.dtype == np.uint8 and a.shape == (7, 9, 3)
+
+
+def _write_fits_raw(path, cards, payload):
+    hdr = "".join(("%-80s" % c)[:80] for c in cards + ["END"])
+    hdr += " " * (-len(hdr) % 2880)
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        f.write(payload)
+        f.write(b"\0" * (-len(payload) % 2880))
+
+
+def test_fits_reader_cubes_scaling_and_integer_payloads(tmp_path):
+    """fits.FitsImage against hand-written FITS files: a 4-D radio cube (RA, DEC, FREQ, STOKES) is read as its plane
+    [0, 0] (utils.py:378-380); BITPIX 16 / 32 / -64 payloads and BSCALE / BZERO give float32 rows (what astropy's
+    fits.getdata hands the reference); BITPIX -32 without scaling is shipped raw (big-endian) for the GPU to decode."""
+    from caesar_yolo_b200.fits import FitsImage
+    rng = np.random.default_rng(3)
+    ny, nx = 7, 11
+    cube = rng.standard_normal((2, 3, ny, nx)).astype('>f4')          # [stokes, freq, y, x]
+    p = str(tmp_path / "cube.fits")
+    _write_fits_raw(p, ["SIMPLE  =                    T", "BITPIX  =                  -32", "NAXIS   =                    4",
+                        "NAXIS1  =                   11", "NAXIS2  =                    7", "NAXIS3  =                    3",
+                        "NAXIS4  =                    2", "BUNIT   = 'Jy/beam '           / brightness unit",
+                        "CTYPE3  = 'FREQ    '"], cube.tobytes())
+    f = FitsImage(p)
+    assert (f.nx, f.ny, f.bitpix, f.is_raw_f32) == (nx, ny, -32, True)
+    assert f.header['BUNIT'] == 'Jy/beam' and f.header['CTYPE3'] == 'FREQ'
+    rows = f.rows(2, 5)
+    assert rows.dtype == np.dtype('>f4') and np.array_equal(rows.astype('f4'), cube[0, 0, 2:5].astype('f4'))
+    # 16-bit integers with BSCALE / BZERO
+    img = rng.integers(-2000, 2000, (ny, nx)).astype('>i2')
+    p = str(tmp_path / "i16.fits")
+    _write_fits_raw(p, ["SIMPLE  =                    T", "BITPIX  =                   16", "NAXIS   =                    2",
+                        "NAXIS1  =                   11", "NAXIS2  =                    7", "BSCALE  =                 0.25",
+                        "BZERO   =               1000.0"], img.tobytes())
+    f = FitsImage(p)
+    assert not f.is_raw_f32
+    want = img.astype(np.float32) * np.float32(0.25) + np.float32(1000.0)
+    assert f.rows(0, ny).dtype == np.float32 and np.array_equal(f.rows(0, ny), want)
+    # 32-bit integers and 64-bit floats, no scaling
+    for bitpix, dt in ((32, '>i4'), (-64, '>f8')):
+        a = (rng.standard_normal((ny, nx)) * 1000).astype(dt)
+        p = str(tmp_path / ("b%d.fits" % bitpix))
+        _write_fits_raw(p, ["SIMPLE  =                    T", "BITPIX  = %20d" % bitpix, "NAXIS   =                    2",
+                            "NAXIS1  =                   11", "NAXIS2  =                    7"], a.tobytes())
+        f = FitsImage(p)
+        assert f.bitpix == bitpix and np.array_equal(f.rows(1, 6), a[1:6].astype(np.float32))
