@@ -40,7 +40,7 @@ class PPConfig(ctypes.Structure):
         ("zscale_stretch", ctypes.c_int32), ("zscale_contrasts", c_double * 3),
         ("chan3_preproc", ctypes.c_int32), ("sigma_clip_baseline", c_double),
         ("normalize_minmax", ctypes.c_int32), ("norm_min", c_double), ("norm_max", c_double),
-        ("enabled", ctypes.c_int32),
+        ("enabled", ctypes.c_int32), ("out_f16", ctypes.c_int32),
     ]
 
 
@@ -55,7 +55,7 @@ SYMBOLS = [
     "cy_last_error", "cy_version", "cy_device_check", "cy_memcpy_d2d", "cy_generate_tiles", "cy_tile_neighbors",
     "cy_letterbox_shape", "cy_preprocess_scratch_bytes", "cy_preprocess", "cy_letterbox_resize", "cy_conv_block_n", "cy_conv2d_nhwc",
     "cy_conv_set_debug", "cy_conv_plan_info", "cy_sort_set_debug",
-    "cy_model_create", "cy_model_set_tensor", "cy_model_finalize", "cy_model_forward", "cy_model_info",
+    "cy_model_create", "cy_model_set_tensor", "cy_model_set_precision", "cy_model_plan_summary", "cy_letterbox_resize_fmt", "cy_model_finalize", "cy_model_forward", "cy_model_info",
     "cy_stem_conv_nhwc4", "cy_model_profile", "cy_model_conv_bytes", "cy_model_destroy", "cy_num_anchors", "cy_decode_pred", "cy_postprocess_scratch_bytes",
     "cy_postprocess", "cy_nms_scratch_bytes", "cy_nms_batched", "cy_merge_tile", "cy_make_records",
     "cy_compact_scratch_bytes", "cy_compact_records", "cy_merge_global",

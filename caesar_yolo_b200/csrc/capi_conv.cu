@@ -43,6 +43,7 @@ extern "C" int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ct
     d.w = (const __nv_bfloat16*)w; d.cout_pad = cout_pad; d.bias = bias; d.cout = cout;
     d.out = out; d.out_ctot = out_ctot; d.out_coff = out_coff; d.out_f32 = out_f32;
     d.res = (const __nv_bfloat16*)res; d.res_ctot = res_ctot; d.res_coff = res_coff; d.act = act;
+    d.f16 = 0;
     cy::ConvPlan plan;
     char err[256];
     if (cy::conv_make_plan(d, &plan, err, sizeof(err)) != 0) return cy::set_error(CY_ERR_INVALID, "%s", err);

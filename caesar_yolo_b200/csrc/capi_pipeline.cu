@@ -31,6 +31,30 @@ extern "C" int cy_model_set_tensor(void* model, const char* name, const float* d
     if (!model || !name || !data_host) return set_error(CY_ERR_INVALID, "null argument");
     return ((Model*)model)->set_tensor(name, data_host, numel);
 }
+extern "C" int cy_model_set_precision(void* model, int fp16) {
+    if (!model) return set_error(CY_ERR_INVALID, "null model");
+    Model* m = (Model*)model;
+    if (m->finalized) return set_error(CY_ERR_STATE, "cy_model_set_precision must be called before cy_model_finalize");
+    m->f16 = fp16 ? 1 : 0;
+    return CY_OK;
+}
+extern "C" int cy_model_plan_summary(void* model, int B, int Sh, int Sw, int* info_host) {
+    if (!model || !info_host) return set_error(CY_ERR_INVALID, "null argument");
+    Plan* pl = nullptr;
+    int r = ((Model*)model)->get_plan(B, Sh, Sw, &pl);
+    if (r) return r;
+    for (int i = 0; i < 8; ++i) info_host[i] = 0;
+    for (const Op& op : pl->ops)
+        if (op.type == Op::CONV) {
+            const ConvKParams& kp = op.conv.kp;
+            info_host[0] += 1;
+            info_host[1] += kp.pair ? 1 : 0;
+            if (kp.mode >= 0 && kp.mode <= 3) info_host[2 + kp.mode] += 1;
+            info_host[6] += kp.block_n > 128 ? 1 : 0;
+            info_host[7] += kp.halves == 2 ? 1 : 0;
+        }
+    return CY_OK;
+}
 extern "C" int cy_model_finalize(void* model) {
     if (!model) return set_error(CY_ERR_INVALID, "null model");
     return ((Model*)model)->finalize();

@@ -1,5 +1,6 @@
 // tcgen05 implicit-GEMM convolution kernel + host-side planning (tensor-map encoding).  See conv.cuh.
 #include "conv.cuh"
+#include "common.h"
 #include "ptx.cuh"
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -56,7 +57,7 @@ __device__ __forceinline__ float silu_f(float y) {
 // swizzled staging row.  cc0 = first column inside the store group.
 template <bool F32OUT>
 __device__ __forceinline__ void epi_cols32(const uint32_t (&v)[32], const float4 (&bias4)[8], int act, bool has_res,
-                                           uint8_t* sbuf, uint32_t my_row, uint32_t sw_mask, int cc0, int ncols) {
+                                           uint8_t* sbuf, uint32_t my_row, uint32_t sw_mask, int cc0, int ncols, int f16) {
     // stage 1: bias (+ SiLU) on all 32 columns with the 32 MUFU ops issued back to back (their latency overlaps)
     float y[32];
 #pragma unroll
@@ -90,18 +91,18 @@ __device__ __forceinline__ void epi_cols32(const uint32_t (&v)[32], const float4
                 uint4* dst = reinterpret_cast<uint4*>(sbuf + a);
                 if (has_res) {
                     const uint4 r = *dst;
-                    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+                    const uint32_t* r2 = reinterpret_cast<const uint32_t*>(&r);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float2 f = __bfloat1622float2(r2[j]);
+                        const float2 f = unpack_h2(r2[j], f16);
                         y[g8 * 8 + 2 * j] += f.x;
                         y[g8 * 8 + 2 * j + 1] += f.y;
                     }
                 }
                 uint4 o;
-                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+                uint32_t* o2 = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(y[g8 * 8 + 2 * j], y[g8 * 8 + 2 * j + 1]);
+                for (int j = 0; j < 4; ++j) o2[j] = pack_h2(y[g8 * 8 + 2 * j], y[g8 * 8 + 2 * j + 1], f16);
                 *dst = o;
             } else {
                 uint32_t a0 = my_row + (uint32_t)(cc >> 2) * 16u;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     } else if (warp == 1) {
       if (rank == 0) {
         // ------------------------------------------------------------ MMA issuer (one elected thread of the leader)
-        const uint32_t idesc = make_idesc_bf16(kBlockM * kCtasPerUnit, p.block_n);
+        const uint32_t idesc = make_idesc_bf16(kBlockM * kCtasPerUnit, p.block_n, p.f16);
         const uint32_t a_ring_addr = smem_u32(a_ring);
         const uint32_t b_ring_addr = smem_u32(b_ring);
         int sa = 0, sb = 0;
@@ -427,10 +428,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                         else rphase0 ^= 1;
                     }
                     if (p.o_esz == 2) {
-                        epi_cols32<false>(va, bias_a, p.act, has_res, sbuf, my_row, p.o_sw_mask, 0, ncols0);
-                        if (two) epi_cols32<false>(vb, bias_b, p.act, has_res, sbuf, my_row, p.o_sw_mask, 32, 32);
+                        epi_cols32<false>(va, bias_a, p.act, has_res, sbuf, my_row, p.o_sw_mask, 0, ncols0, p.f16);
+                        if (two) epi_cols32<false>(vb, bias_b, p.act, has_res, sbuf, my_row, p.o_sw_mask, 32, 32, p.f16);
                     } else {
-                        epi_cols32<true>(va, bias_a, p.act, false, sbuf, my_row, p.o_sw_mask, 0, ncols0);
+                        epi_cols32<true>(va, bias_a, p.act, false, sbuf, my_row, p.o_sw_mask, 0, ncols0, p.f16);
                     }
                     if (dbg) tq3 = clock64();
                     fence_proxy_async_smem();
@@ -523,15 +524,7 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+static int num_sms() { return current_device_sms(); }   // per device (common.h)
 
 static unsigned long long* g_dbg = nullptr;
 static int g_dbg_units = 0;
@@ -542,12 +535,11 @@ void conv_set_debug(unsigned long long* dev_buf, int units_per_cta) {
 
 template <int HALVES, int KSTEPS, bool PAIR>
 static int launch_t(const ConvPlan& pl, cudaStream_t st) {
-    static bool attr_done = false;
+    static std::atomic<unsigned long long> attr_done{0};
     auto kern = conv_igemm_kernel<HALVES, KSTEPS, PAIR>;
-    if (!attr_done) {
+    if (first_use_on_device(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        attr_done = true;
     }
     ConvKParams kp = pl.kp;
     if (g_dbg) {
@@ -653,6 +645,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     kp.res_cstride = d.res_ctot;
     kp.res_coff = d.res_coff;
     kp.cout_store = (d.cout + 7) / 8 * 8;
+    kp.f16 = d.f16 ? 1 : 0;
     kp.act = d.act ? (env_int("CY_CONV_SILU_EXACT", 0) ? 2 : 1) : 0;   // 1: tanh.approx form, 2: ex2 + rcp
     kp.out_f32 = d.out_f32;
     if ((d.out_ctot % 8) || (d.out_coff % 8)) FAIL("output channel stride/offset must be multiples of 8");

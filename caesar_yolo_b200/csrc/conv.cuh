@@ -83,6 +83,7 @@ struct ConvKParams {
     int act;                       // 1 = SiLU
     int out_f32;                   // 1 = write fp32
     int mode;
+    int f16;                       // storage format of in / w / res / bf16-sized out: 0 bf16, 1 fp16
     int pair;                      // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2), a unit = 2 x halves half tiles
     unsigned long long* dbg;       // optional per-CTA timeline (clock64 stamps), 8 words per unit, see conv_probe
     int dbg_units;
@@ -101,6 +102,7 @@ struct ConvDesc {
     void* out;                int out_ctot, out_coff, out_f32;
     const __nv_bfloat16* res; int res_ctot, res_coff;
     int act;
+    int f16;                                              // 0: bf16 tensors, 1: fp16 tensors
 };
 
 struct ConvPlan {

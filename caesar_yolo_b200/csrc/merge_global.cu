@@ -409,15 +409,14 @@ int merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const 
     }
     // workspace (stream-ordered allocation keeps the entry point allocation-free for callers); keep freed blocks in
     // the pool instead of returning them to the driver at every synchronisation
-    static bool pool_set = false;
-    if (!pool_set) {
+    static std::atomic<unsigned long long> pool_set{0};
+    if (first_use_on_device(pool_set)) {
         int dev = 0;
         cudaMemPool_t pool;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long thr = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
-        pool_set = true;
     }
     const int nsums = n / kScanBlock + T / kScanBlock + 16;
     int *is_edge, *is_plain, *epos, *ppos, *vert_rec, *tile_vcount, *tile_vstart, *deg, *adj_off, *parent, *is_root,

@@ -7,6 +7,7 @@
 // (yolov8.yaml).  Concats are zero-copy: producers store into channel slices.
 #include "model.h"
 #include "common.h"
+#include "half16.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,7 +48,7 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
                  const uint32_t* __restrict__ wfrag,     // [3][NT][32][2] B fragments (see pack_stem_weights)
                  const float* __restrict__ bias,         // [8*NT]
                  __nv_bfloat16* __restrict__ out,        // [B,H/2,W/2,8*NT]
-                 int B, int H, int W, int act) {
+                 int B, int H, int W, int act, int f16) {
     using S = StemSmem<NT>;
     constexpr int kRows = S::kRows, kCols = S::kCols, kCout = S::kCout, kStageW = S::kStageW;
     extern __shared__ __align__(16) unsigned char stem_smem_raw[];
@@ -115,13 +116,23 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
                     // pixel 2*(16*mx + p) + kx + 1; word index inside the row = 2 * pixel + channel pair
                     const uint32_t* row = reinterpret_cast<const uint32_t*>(&sm.patch[buf][2 * warp + ky][0]) + 64 * mx + lane + 2;
                     const uint32_t a0 = row[0], a1 = row[32], a2 = row[4], a3 = row[36];
+                    if (f16) {
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        asm volatile(
-                            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
-                            "{%8,%9}, {%0,%1,%2,%3};"
-                            : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
-                            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wb[ky][nt][0]), "r"(wb[ky][nt][1]));
+                        for (int nt = 0; nt < NT; ++nt)
+                            asm volatile(
+                                "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+                                "{%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wb[ky][nt][0]), "r"(wb[ky][nt][1]));
+                    } else {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            asm volatile(
+                                "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+                                "{%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(wb[ky][nt][0]), "r"(wb[ky][nt][1]));
+                    }
                 }
                 // epilogue: thread holds pixels g, g+8 x channels nt*8 + 2t, +1
                 // (SiLU tanh form: h = (acc + bias) / 2 exactly as the conv kernel computes it — the halving is exact)
@@ -154,10 +165,8 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
                 __syncwarp();
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(y[nt][0], y[nt][1]);
-                    __nv_bfloat162 hi = __floats2bfloat162_rn(y[nt][2], y[nt][3]);
-                    st[g * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&lo);
-                    st[(g + 8) * kStageW + nt * 4 + t] = *reinterpret_cast<uint32_t*>(&hi);
+                    st[g * kStageW + nt * 4 + t] = pack_h2(y[nt][0], y[nt][1], f16);
+                    st[(g + 8) * kStageW + nt * 4 + t] = pack_h2(y[nt][2], y[nt][3], f16);
                 }
                 __syncwarp();
                 uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * Ho + oy) * Wo + ox) * kCout);
@@ -175,15 +184,26 @@ stem_conv_kernel(const __nv_bfloat16* __restrict__ in,   // [B,H,W,4]
 // B fragments of the stem weights for mma.m16n8k16 (col operand): lane (g = lane / 4, t = lane % 4) of n-tile nt and
 // K-step ky holds {B[2t][g], B[2t+1][g]} and {B[2t+8][g], B[2t+9][g]} with B[k][n] = w[n][c][ky][kx] * bn_scale[n],
 // k = kx*4 + c (zero for c = 3 and kx = 3).
+static inline unsigned short to_h16(float x, int f16) {
+    if (f16) {
+        const __half h = __float2half_rn(x);
+        return *reinterpret_cast<const unsigned short*>(&h);
+    }
+    const __nv_bfloat16 h = __float2bfloat16(x);
+    return *reinterpret_cast<const unsigned short*>(&h);
+}
+static inline float round_h16(float x, int f16) {
+    return f16 ? __half2float(__float2half_rn(x)) : __bfloat162float(__float2bfloat16(x));
+}
+
 static void pack_stem_weights(const std::vector<float>& w, const std::vector<float>& scale, int cout,
-                              std::vector<uint32_t>& frag) {
+                              std::vector<uint32_t>& frag, int f16) {
     const int NT = cout / 8;
     frag.assign((size_t)3 * NT * 32 * 2, 0u);
     auto wt = [&](int n, int ky, int k) -> uint32_t {
         const int kx = k >> 2, c = k & 3;
         if (kx > 2 || c > 2) return 0u;
-        const __nv_bfloat16 h = __float2bfloat16(w[((n * 3 + c) * 3 + ky) * 3 + kx] * scale[n]);
-        return (uint32_t)*reinterpret_cast<const unsigned short*>(&h);
+        return (uint32_t)to_h16(w[((n * 3 + c) * 3 + ky) * 3 + kx] * scale[n], f16);
     };
     for (int ky = 0; ky < 3; ++ky)
         for (int nt = 0; nt < NT; ++nt)
@@ -196,12 +216,14 @@ static void pack_stem_weights(const std::vector<float>& w, const std::vector<flo
 }
 
 template <int NT>
-static int launch_stem(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, cudaStream_t st) {
-    static int ctas = 0;   // persistent grid: resident CTAs per SM x SMs of the current device
+static int launch_stem(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, int f16, cudaStream_t st) {
+    static int ctas_dev[64] = {0};   // persistent grid: resident CTAs per SM x SMs, per device ordinal
     const int smem = (int)sizeof(StemSmem<NT>);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& ctas = ctas_dev[dev & 63];
     if (!ctas) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess)
@@ -212,18 +234,18 @@ static int launch_stem(const void* in, const ConvW& w, void* out, int B, int H, 
     const long long ntiles = (long long)B * ((H / 2 + 7) / 8) * ((W / 2 + 63) / 64);
     const unsigned grid = (unsigned)std::min<long long>(ntiles, ctas);
     stem_conv_kernel<NT><<<grid, 256, smem, st>>>((const __nv_bfloat16*)in, (const uint32_t*)w.w, w.b,
-                                                  (__nv_bfloat16*)out, B, H, W, act);
+                                                  (__nv_bfloat16*)out, B, H, W, act, f16);
     return 0;
 }
 
-static int launch_stem_any(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, cudaStream_t st) {
+static int launch_stem_any(const void* in, const ConvW& w, void* out, int B, int H, int W, int act, int f16, cudaStream_t st) {
     switch (w.cout / 8) {
-        case 2: return launch_stem<2>(in, w, out, B, H, W, act, st);
-        case 4: return launch_stem<4>(in, w, out, B, H, W, act, st);
-        case 6: return launch_stem<6>(in, w, out, B, H, W, act, st);
-        case 8: return launch_stem<8>(in, w, out, B, H, W, act, st);
-        case 10: return launch_stem<10>(in, w, out, B, H, W, act, st);
-        case 12: return launch_stem<12>(in, w, out, B, H, W, act, st);
+        case 2: return launch_stem<2>(in, w, out, B, H, W, act, f16, st);
+        case 4: return launch_stem<4>(in, w, out, B, H, W, act, f16, st);
+        case 6: return launch_stem<6>(in, w, out, B, H, W, act, f16, st);
+        case 8: return launch_stem<8>(in, w, out, B, H, W, act, f16, st);
+        case 10: return launch_stem<10>(in, w, out, B, H, W, act, f16, st);
+        case 12: return launch_stem<12>(in, w, out, B, H, W, act, f16, st);
         default: return (int)cudaErrorInvalidValue;
     }
 }
@@ -346,7 +368,7 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __nv_bfloat16* 
                                                         int gs, int gst, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                         int out_ctot, int out_off, const __nv_bfloat16* __restrict__ res,
-                                                        int res_ctot, int res_off, int H, int W, int C, int act) {
+                                                        int res_ctot, int res_off, int H, int W, int C, int act, int f16) {
     const int groups = C / 8;
     const int x0 = 4 * (blockIdx.x * (blockDim.x / groups) + threadIdx.x / groups);   // blockDim.x: multiple of groups
     const int g = threadIdx.x % groups;
@@ -402,11 +424,11 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __nv_bfloat16* 
         }
 #pragma unroll
         for (int j = 0; j < 6; ++j) {   // input column x0 - 1 + j feeds output p = j - kx for kx = 0..2
-            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&win[ky][j]);
+            const uint32_t* pv = reinterpret_cast<const uint32_t*>(&win[ky][j]);
             float f[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float2 t = __bfloat1622float2(pv[q]);
+                const float2 t = unpack_h2(pv[q], f16);
                 f[2 * q] = t.x;
                 f[2 * q + 1] = t.y;
             }
@@ -440,18 +462,18 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __nv_bfloat16* 
         const long long pix = ((long long)b * H + y) * W + x;
         if (res) {
             const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + pix * res_ctot + res_off + c0));
-            const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&r);
+            const uint32_t* pr = reinterpret_cast<const uint32_t*>(&r);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(pr[q]);
+                const float2 f = unpack_h2(pr[q], f16);
                 acc[p][2 * q] += f.x;
                 acc[p][2 * q + 1] += f.y;
             }
         }
         uint4 o;
-        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+        uint32_t* po = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) po[q] = __floats2bfloat162_rn(acc[p][2 * q], acc[p][2 * q + 1]);
+        for (int q = 0; q < 4; ++q) po[q] = pack_h2(acc[p][2 * q], acc[p][2 * q + 1], f16);
         *reinterpret_cast<uint4*>(out + pix * out_ctot + out_off + c0) = o;
     }
 }
@@ -465,7 +487,7 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __nv_bfloat16* 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ctot,
                                                                 __nv_bfloat16* __restrict__ out, int out_ctot, int out_off,
-                                                                int N) {
+                                                                int N, int f16) {
     extern __shared__ __align__(16) uint32_t attn_smem[];
     uint32_t* sk = attn_smem;                 // [N][17] bf16x2 words (16 used)
     uint32_t* sv = sk + (size_t)N * 17;       // [N][32] bf16x2 words
@@ -492,7 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t u = __ldg(qp + j);
-                q[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+                q[j] = unpack_h2(u, f16);
             }
         }
         float mx = -INFINITY;
@@ -502,7 +524,7 @@ __global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t u = kr[j];
-                const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+                const float2 kf = unpack_h2(u, f16);
                 sacc = fmaf(q[j].x, kf.x, sacc);
                 sacc = fmaf(q[j].y, kf.y, sacc);
             }
@@ -525,13 +547,13 @@ __global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat
         for (int m = 0; m < N; ++m) {
             const float pm = p[m];
             const uint32_t u = sv[m * 32 + lane];
-            const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+            const float2 vf = unpack_h2(u, f16);
             o0 = fmaf(pm, vf.x, o0);
             o1 = fmaf(pm, vf.y, o1);
         }
         const float inv = 1.0f / sum;
-        const __nv_bfloat162 ov = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-        *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * N + n) * out_ctot + out_off + head * 64 + 2 * lane) = ov;
+        *reinterpret_cast<uint32_t*>(out + ((long long)b * N + n) * out_ctot + out_off + head * 64 + 2 * lane) =
+            pack_h2(o0 * inv, o1 * inv, f16);
         __syncwarp();
     }
 }
@@ -543,16 +565,23 @@ __global__ void __launch_bounds__(WARPS * 32) attention_kernel(const __nv_bfloat
 // 64 keys S = Q K^T with mma.sync.m16n8k16 (bf16, fp32 accumulate), online softmax in registers (exp2, running max /
 // sum per query row, quad shuffles), P re-packed as the A operand and O += P V with V fragments from
 // ldmatrix.x4.trans.  48 MMAs per warp and chunk; 2.7 ms -> see profiles/ for the measured time.
+template <bool F16>
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    if (F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+template <bool F16>
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&v);
+    return pack_h2(lo, hi, F16 ? 1 : 0);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ctot,
                                                             __nv_bfloat16* __restrict__ out, int out_ctot, int out_off,
                                                             int N, int Npad) {
@@ -603,7 +632,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
             sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
             const uint32_t* kr = reinterpret_cast<const uint32_t*>(sK + (size_t)(kc + nt * 8 + g) * 80);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) mma16816(sc[nt], qa[ks], kr[ks * 8 + t], kr[ks * 8 + t + 4]);
+            for (int ks = 0; ks < 2; ++ks) mma16816<F16>(sc[nt], qa[ks], kr[ks * 8 + t], kr[ks * 8 + t + 4]);
         }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -633,8 +662,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
             const float p2 = exp2f(sc[nt][2] - mn1), p3 = exp2f(sc[nt][3] - mn1);
             rs0 += p0 + p1;
             rs1 += p2 + p3;
-            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2<F16>(p0, p1);
+            pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2<F16>(p2, p3);
         }
         l0 = l0 * al0 + rs0;    // per-lane partial sums of the row; the quad is reduced once at the end
         l1 = l1 * al1 + rs1;
@@ -653,8 +682,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
                 uint32_t r0, r1, r2, r3;
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                              : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-                mma16816(o[2 * dp], pa[j], r0, r1);
-                mma16816(o[2 * dp + 1], pa[j], r2, r3);
+                mma16816<F16>(o[2 * dp], pa[j], r0, r1);
+                mma16816<F16>(o[2 * dp + 1], pa[j], r2, r3);
             }
         }
     }
@@ -668,9 +697,9 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16*
     for (int d = 0; d < 8; ++d) {
         const int col = out_off + head * 64 + d * 8 + 2 * t;
         if (r0 < N)
-            *reinterpret_cast<uint32_t*>(out + ((long long)b * N + r0) * out_ctot + col) = pack_bf16x2(o[d][0] * i0, o[d][1] * i0);
+            *reinterpret_cast<uint32_t*>(out + ((long long)b * N + r0) * out_ctot + col) = pack_bf16x2<F16>(o[d][0] * i0, o[d][1] * i0);
         if (r1 < N)
-            *reinterpret_cast<uint32_t*>(out + ((long long)b * N + r1) * out_ctot + col) = pack_bf16x2(o[d][2] * i1, o[d][3] * i1);
+            *reinterpret_cast<uint32_t*>(out + ((long long)b * N + r1) * out_ctot + col) = pack_bf16x2<F16>(o[d][2] * i1, o[d][3] * i1);
     }
 }
 
@@ -682,14 +711,14 @@ int stem_conv_run(const void* in, int B, int H, int W, const float* w_host, cons
     if (H % 2 != 0 || W % 32 != 0) return set_error(CY_ERR_INVALID, "stem: H must be even and W a multiple of 32");
     std::vector<float> w(w_host, w_host + (size_t)cout * 27), scale(cout, 1.f);
     std::vector<uint32_t> frag;
-    pack_stem_weights(w, scale, cout, frag);
+    pack_stem_weights(w, scale, cout, frag, 0);
     ConvW cw;
     cw.cout = cw.cout_pad = cout;
     CY_CUDA_CHECK(cudaMalloc(&cw.w, frag.size() * sizeof(uint32_t)));
     CY_CUDA_CHECK(cudaMalloc(&cw.b, cout * sizeof(float)));
     CY_CUDA_CHECK(cudaMemcpyAsync(cw.w, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CY_CUDA_CHECK(cudaMemcpyAsync(cw.b, bias_host, cout * sizeof(float), cudaMemcpyHostToDevice, st));
-    const int lrc = launch_stem_any(in, cw, out, B, H, W, act, st);
+    const int lrc = launch_stem_any(in, cw, out, B, H, W, act, 0, st);
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(st);
     cudaFree(cw.w);
@@ -789,7 +818,7 @@ int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn, int
             return set_error(CY_ERR_INVALID, "stem %s: expected a 3x3 conv with cout %% 16 == 0, cout <= 96", p.c_str());
         cw.cout_pad = cout;
         std::vector<uint32_t> frag;
-        pack_stem_weights(*w, scale, cout, frag);
+        pack_stem_weights(*w, scale, cout, frag, f16);
         CY_CUDA_CHECK(cudaMalloc(&cw.w, frag.size() * sizeof(uint32_t)));
         CY_CUDA_CHECK(cudaMemcpy(cw.w, frag.data(), frag.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     } else {
@@ -799,16 +828,16 @@ int Model::add_conv(const std::string& p, int cin, int cout, int k, bool bn, int
         const int bn_ = conv_block_n(cout);
         cw.cout_pad = (cout + bn_ - 1) / bn_ * bn_;
         const size_t K = (size_t)k * k * cinp;
-        std::vector<__nv_bfloat16> hw((size_t)cw.cout_pad * K, __float2bfloat16(0.f));
+        std::vector<unsigned short> hw((size_t)cw.cout_pad * K, (unsigned short)0);
         for (int o = 0; o < cout; ++o)
             for (int i = 0; i < cin; ++i)
                 for (int kh = 0; kh < k; ++kh)
                     for (int kw = 0; kw < k; ++kw)
                         hw[(size_t)o * K + (size_t)(kh * k + kw) * cinp + i] =
-                            __float2bfloat16((*w)[(((size_t)o * cin + i) * k + kh) * k + kw] * scale[o]);
+                            to_h16((*w)[(((size_t)o * cin + i) * k + kh) * k + kw] * scale[o], f16);
         cw.cin = cinp;
-        CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(__nv_bfloat16)));
-        CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        CY_CUDA_CHECK(cudaMalloc(&cw.w, hw.size() * sizeof(unsigned short)));
+        CY_CUDA_CHECK(cudaMemcpy(cw.w, hw.data(), hw.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     }
     std::vector<float> hb(cw.cout_pad, 0.f);
     for (int o = 0; o < cout; ++o) hb[o] = bias[o];
@@ -842,7 +871,7 @@ int Model::add_dwconv(const std::string& p, int c) {
     for (int o = 0; o < c; ++o) {
         const float sc = (*g)[o] / sqrtf((*v)[o] + 1e-3f);
         hb[o] = (*b)[o] - (*m)[o] * sc;
-        for (int t = 0; t < 9; ++t) hw[(size_t)t * c + o] = bf16_round((*w)[(size_t)o * 9 + t] * sc);
+        for (int t = 0; t < 9; ++t) hw[(size_t)t * c + o] = round_h16((*w)[(size_t)o * 9 + t] * sc, f16);
     }
     ConvW cw;
     cw.cin = cw.cout = cw.cout_pad = c;
@@ -1024,6 +1053,7 @@ struct PlanBuilder {
         d.out = out.p; d.out_ctot = out.C; d.out_coff = out_off; d.out_f32 = out_f32 ? 1 : 0;
         d.res = res ? (const __nv_bfloat16*)res->p : nullptr; d.res_ctot = res ? res->C : 0; d.res_coff = res_off;
         d.act = act ? 1 : 0;
+        d.f16 = m.f16;
         if (conv_make_plan(d, &op.conv, err, sizeof(err)) != 0) return -1;
         pl.flops += op.conv.flops;
         pl.ops.push_back(op);
@@ -1375,7 +1405,7 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
             const ConvW& w = convs.at("model.0");
             const char* ex = getenv("CY_CONV_SILU_EXACT");   // same switch as the conv kernel (1: tanh form, 2: ex2 + rcp)
             const int act = (ex && atoi(ex)) ? 2 : 1;
-            const int e = launch_stem_any(in, w, op.out.p, B, Sh, Sw, act, st);
+            const int e = launch_stem_any(in, w, op.out.p, B, Sh, Sw, act, f16, st);
             if (e) return set_error(CY_ERR_CUDA, "stem launch failed: %s", cudaGetErrorString((cudaError_t)e));
             break;
         }
@@ -1394,11 +1424,10 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
         }
         case Op::SPPF_POOL: {
             const int smem = 3 * op.in.H * op.in.W * 64;
-            static bool attr_done = false;
-            if (!attr_done) {
+            static std::atomic<unsigned long long> attr_done{0};
+            if (first_use_on_device(attr_done)) {
                 cudaError_t e = cudaFuncSetAttribute(sppf_pool3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSppfMaxSmem);
                 if (e != cudaSuccess) return set_error(CY_ERR_CUDA, "sppf_pool3 attribute: %s", cudaGetErrorString(e));
-                attr_done = true;
             }
             sppf_pool3_kernel<<<dim3((unsigned)(op.C / 32), (unsigned)B), 256, smem, st>>>(
                 (__nv_bfloat16*)op.in.p, op.in.C, op.C, op.in.H, op.in.W);
@@ -1411,38 +1440,41 @@ int Model::launch_op(const Op& op, const void* in, int B, int Sh, int Sw, cudaSt
             dwconv3x3_kernel<<<dim3((unsigned)((op.in.W + 4 * ppb - 1) / (4 * ppb)), (unsigned)op.in.H, (unsigned)B), groups * ppb, 0, st>>>(
                 (const __nv_bfloat16*)op.in.p, op.in.C, op.in_off, op.gs, op.gst, op.dw_w, op.dw_b,
                 (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, (const __nv_bfloat16*)op.res.p, op.res.C, op.res_off,
-                op.in.H, op.in.W, op.C, act);
+                op.in.H, op.in.W, op.C, act, f16);
             break;
         }
         case Op::ATTN: {
             const int N = op.in.H * op.in.W;
             const size_t kv = (size_t)N * (17 + 32) * 4;
-            static bool attr_done = false;
-            if (!attr_done) {
+            static std::atomic<unsigned long long> attr_done{0};
+            if (first_use_on_device(attr_done)) {
                 cudaError_t e1 = cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
                 cudaError_t e2 = cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
                 if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error(CY_ERR_CUDA, "attention attribute failed");
-                attr_done = true;
             }
             const dim3 grid((unsigned)((N + 63) / 64), (unsigned)op.nh, (unsigned)B);
             const int Npad = (N + 63) / 64 * 64;
             const size_t mma_smem = (size_t)Npad * (80 + 144);
             const char* simple = getenv("CY_ATTN_SIMPLE");
             if (!(simple && atoi(simple)) && mma_smem <= 227 * 1024) {
-                static bool mma_attr = false;
-                if (!mma_attr) {
-                    if (cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+                static std::atomic<unsigned long long> mma_attr{0};
+                if (first_use_on_device(mma_attr)) {
+                    if (cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+                        cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
                         return set_error(CY_ERR_CUDA, "attention attribute failed");
-                    mma_attr = true;
                 }
-                attention_mma_kernel<<<grid, 128, mma_smem, st>>>((const __nv_bfloat16*)op.in.p, op.in.C,
-                                                                 (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N, Npad);
+                if (f16)
+                    attention_mma_kernel<true><<<grid, 128, mma_smem, st>>>((const __nv_bfloat16*)op.in.p, op.in.C,
+                                                                           (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N, Npad);
+                else
+                    attention_mma_kernel<false><<<grid, 128, mma_smem, st>>>((const __nv_bfloat16*)op.in.p, op.in.C,
+                                                                            (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N, Npad);
             } else if (kv + (size_t)8 * N * 4 <= 200 * 1024)
                 attention_kernel<8><<<grid, 256, kv + (size_t)8 * N * 4, st>>>(
-                    (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N);
+                    (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N, f16);
             else if (kv + (size_t)4 * N * 4 <= 220 * 1024)
                 attention_kernel<4><<<grid, 128, kv + (size_t)4 * N * 4, st>>>(
-                    (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N);
+                    (const __nv_bfloat16*)op.in.p, op.in.C, (__nv_bfloat16*)op.out.p, op.out.C, op.out_off, N, f16);
             else
                 return set_error(CY_ERR_INVALID, "attention over %d positions does not fit shared memory (imgsz > 1024)", N);
             break;

@@ -54,6 +54,7 @@ struct Model {
     char variant = 'n';
     int family = 8;   // 8: yolov8 (yolov8.yaml), 11: yolo11 (yolo11.yaml)
     int nc = 5;
+    int f16 = 0;      // storage format of weights / activations: 0 bf16, 1 fp16 (set before finalize)
     // yolo11 widths / repeats (init11)
     int w64 = 0, w128 = 0, w256 = 0, w512 = 0, w1024 = 0, n11 = 1;
     bool c3k11 = false;

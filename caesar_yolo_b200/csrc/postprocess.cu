@@ -622,10 +622,9 @@ int postprocess(const float* h0, const float* h1, const float* h2, int B, int Sh
     int* cand = keep + (size_t)B * max_det;
     unsigned long long* sel = (unsigned long long*)(((uintptr_t)(cand + B) + 255) & ~(uintptr_t)255);
     const int dyn = kSelKeys * (int)sizeof(unsigned long long) + kSelBins * (int)sizeof(int);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (first_use_on_device(attr_done)) {
         if (cudaFuncSetAttribute(nms_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) return -1;
-        attr_done = true;
     }
     const long long total = (long long)B * L.A;
     cudaMemsetAsync(cand, 0, (size_t)B * sizeof(int), st);

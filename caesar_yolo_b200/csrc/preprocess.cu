@@ -21,6 +21,8 @@
 //   kernel 3 (pp_resize_kernel): half-pixel bilinear letterbox resize (double-precision source coordinates like
 //                                cv2.resize on float64), pad 114, channel reversal, /255, bf16 NHWC(4) store.
 #include "common.h"
+#include "half16.cuh"
+#include <stddef.h>
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
@@ -67,6 +69,7 @@ struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per
     double inv_step;      // 255 / (center[255] - center[0]) (0 when the range is empty): bracket guess of the fast lookup
 };
 
+struct TileFinal;
 struct PPParams {
     cy_pp_config cfg;
     const uint32_t* img;
@@ -81,8 +84,9 @@ struct PPParams {
     uint32_t* keysC;    // [B][N] sorted live values outside the bkg box (only when use_box_mask_in_bkg)
     int* nlive;         // [B]
     int* nbox;          // [B]
-    float* chain_out;   // [B][N][3]
+    float* chain_out;   // [B][N][3] (optional parity output, written by pp_final_kernel)
     int* status;        // [B]
+    struct TileFinal* fin;   // [B] final per-channel maps of every tile (chain kernel -> final kernel)
 };
 
 // ------------------------------------------------------------------------------------------ small device helpers
@@ -374,6 +378,19 @@ struct Shared {
     int fail;                // tile status
     int sidx;                // block-wide search scratch
 };
+
+// Final state of a tile's chain: what pp_final_kernel needs to evaluate the three channel maps per pixel.
+struct TileFinal {
+    Comp cc[3];
+    Chan ch[3];       // op lists: interpreter fallback for maps the compiled form cannot represent (cc.ok == 0)
+    HistEq he;        // valid when use_he
+    int same01, same02, same12;
+    int use_he;
+    int status;       // 0 ok, < 0: tile rejected (model input zero-filled)
+    int pad_[3];
+};
+static_assert(sizeof(TileFinal) % 16 == 0 && offsetof(TileFinal, he) % 16 == 0 && sizeof(HistEq) % 16 == 0,
+              "TileFinal is copied in 16-byte words");
 
 // Block-cooperative version of lower_index (all threads call it with the same arguments): every round probes
 // kPPThreads equally spaced elements at once, so 2^18 elements need two rounds of one load each instead of 18
@@ -1175,40 +1192,35 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
         }
     }
 
-    // ---- chain output (fp32 HWC) + the reference's degenerate-image check on rows 0..2 (evaluation.py:171-176)
-    float* out = p.chain_out + (long long)b * N * 3;
+    // ---- hand the final per-channel maps to pp_final_kernel (which evaluates them per pixel, fused with the letterbox
+    // resize) + the reference's degenerate-image check on rows 0..2 (evaluation.py:171-176)
+    TileFinal& tf = p.fin[b];
     if (!ok) {
-        for (int i = threadIdx.x; i < N * 3; i += kPPThreads) out[i] = 0.f;
-        if (threadIdx.x == 0) p.status[b] = sh.fail ? sh.fail : -1;
+        if (threadIdx.x == 0) {
+            const int stt = sh.fail ? sh.fail : -1;
+            p.status[b] = stt;
+            tf.status = stt;
+        }
         return;
     }
-    const bool same01 = sh.ch[0].hid == sh.ch[1].hid, same02 = sh.ch[0].hid == sh.ch[2].hid,
-               same12 = sh.ch[1].hid == sh.ch[2].hid;
     {
-        const float* __restrict__ tin = tile;
-        float* __restrict__ tout = out;
-        auto eval3 = [&](float xf, int i) {
-            const double x = (double)xf;
-            const double v0 = in_zero_x(sh.cc[0], xf) ? 0.0 : eval_fast(sh.cc[0], sh.ch[0], sh.he, x);
-            const double v1 = same01 ? v0 : (in_zero_x(sh.cc[1], xf) ? 0.0 : eval_fast(sh.cc[1], sh.ch[1], sh.he, x));
-            const double v2 = same02 ? v0
-                                     : (same12 ? v1
-                                               : (in_zero_x(sh.cc[2], xf) ? 0.0
-                                                                          : eval_fast(sh.cc[2], sh.ch[2], sh.he, x)));
-            tout[(long long)i * 3 + 0] = (float)v0;
-            tout[(long long)i * 3 + 1] = (float)v1;
-            tout[(long long)i * 3 + 2] = (float)v2;
-        };
-        // four independent loads in flight per thread before the (long) evaluation of each pixel
-        int i = threadIdx.x;
-        for (; i + 3 * kPPThreads < N; i += 4 * kPPThreads) {
-            const float x0 = tin[i], x1 = tin[i + kPPThreads], x2 = tin[i + 2 * kPPThreads], x3 = tin[i + 3 * kPPThreads];
-            eval3(x0, i);
-            eval3(x1, i + kPPThreads);
-            eval3(x2, i + 2 * kPPThreads);
-            eval3(x3, i + 3 * kPPThreads);
+        __syncthreads();
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&tf);
+        const uint32_t* s_cc = reinterpret_cast<const uint32_t*>(&sh.cc[0]);
+        const uint32_t* s_ch = reinterpret_cast<const uint32_t*>(&sh.ch[0]);
+        const uint32_t* s_he = reinterpret_cast<const uint32_t*>(&sh.he);
+        constexpr int n_cc = sizeof(Comp) * 3 / 4, n_ch = sizeof(Chan) * 3 / 4, n_he = sizeof(HistEq) / 4;
+        for (int i = threadIdx.x; i < n_cc; i += kPPThreads) dst[offsetof(TileFinal, cc) / 4 + i] = s_cc[i];
+        for (int i = threadIdx.x; i < n_ch; i += kPPThreads) dst[offsetof(TileFinal, ch) / 4 + i] = s_ch[i];
+        const bool any_he = sh.cc[0].has_he || sh.cc[1].has_he || sh.cc[2].has_he || !sh.cc[0].ok || !sh.cc[1].ok || !sh.cc[2].ok;
+        if (any_he)
+            for (int i = threadIdx.x; i < n_he; i += kPPThreads) dst[offsetof(TileFinal, he) / 4 + i] = s_he[i];
+        if (threadIdx.x == 0) {
+            tf.same01 = sh.ch[0].hid == sh.ch[1].hid;
+            tf.same02 = sh.ch[0].hid == sh.ch[2].hid;
+            tf.same12 = sh.ch[1].hid == sh.ch[2].hid;
+            tf.use_he = any_he ? 1 : 0;
         }
-        for (; i < N; i += kPPThreads) eval3(tin[i], i);
     }
     int bad = 0;
     for (int r = 0; r < 3 && r < p.Ty; ++r) {
@@ -1224,10 +1236,169 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
         block_minmax(mn, mx, sh.red);
         if (mn == mx) bad = 1;
     }
-    if (threadIdx.x == 0) p.status[b] = sh.fail ? sh.fail : (bad ? -1 : 0);
+    if (threadIdx.x == 0) {
+        const int stt = sh.fail ? sh.fail : (bad ? -1 : 0);
+        p.status[b] = stt;
+        tf.status = stt;
+    }
 }
 
-// ------------------------------------------------------------------------------------------ kernel 3: letterbox resize
+// ------------------------------------------------------------------------------------------ kernel 3: final maps + letterbox
+//
+// pp_final_kernel evaluates the three final channel maps of a tile per pixel and -- fused -- does the ultralytics
+// predictor preprocess on them (LetterBox half-pixel bilinear resize with cv2's double-precision source coordinates,
+// pad 114, channel reversal, /255) straight into the 16-bit NHWC(4) model input.  The fp32 HWC chain image never exists
+// in HBM (it was a 3 MB write + 3 MB read per 512^2 tile); tests that want it ask for the optional `chain_out`.
+// One CTA walks bands of `band_h` output rows of its tile: the input rows a band needs (band_h * Ty / new_h + 2) are
+// evaluated once into shared memory (fp32 x 3), then every output pixel interpolates from shared memory.
+// emit_only: bands are input rows, the evaluated rows are written to chain_out as they are (parity surface and the
+// path of tiles whose bands do not fit shared memory, which then go through pp_resize_kernel).
+struct FinalParams {
+    PPParams p;
+    void* out16;         // [B,Sh,Sw,4] bf16 / fp16
+    float* out_f32;      // optional [B,3,Sh,Sw]
+    int Sh, Sw, new_h, new_w, top, left;
+    double scale_y, scale_x;   // 1 / (dst/src), as cv2.resize computes it
+    int band_h, rows_cap, nbands;
+    int f16, emit_only;
+};
+
+__device__ __forceinline__ void eval3(const TileFinal& tf, float xf, float* o) {
+    const double x = (double)xf;
+    const double v0 = in_zero_x(tf.cc[0], xf) ? 0.0 : eval_fast(tf.cc[0], tf.ch[0], tf.he, x);
+    const double v1 = tf.same01 ? v0 : (in_zero_x(tf.cc[1], xf) ? 0.0 : eval_fast(tf.cc[1], tf.ch[1], tf.he, x));
+    const double v2 = tf.same02 ? v0
+                                : (tf.same12 ? v1 : (in_zero_x(tf.cc[2], xf) ? 0.0 : eval_fast(tf.cc[2], tf.ch[2], tf.he, x)));
+    o[0] = (float)v0;
+    o[1] = (float)v1;
+    o[2] = (float)v2;
+}
+
+// source row / column of cv2.resize INTER_LINEAR for destination index d: i0, i1 and the weight of i1
+__device__ __forceinline__ void src_coord(int d, double scale, int n, int& i0, int& i1, float& w) {
+    const double f = ((double)d + 0.5) * scale - 0.5;
+    i0 = (int)floor(f);
+    w = (float)(f - (double)i0);
+    if (i0 < 0) { i0 = 0; w = 0.f; }
+    if (i0 >= n - 1) { i0 = n - 1; w = 0.f; }
+    i1 = min(i0 + 1, n - 1);
+}
+
+static constexpr int kFinThreads = 512;
+
+__global__ void __launch_bounds__(kFinThreads) pp_final_kernel(const __grid_constant__ FinalParams r) {
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    TileFinal& tf = *reinterpret_cast<TileFinal*>(fin_smem);
+    int* xi0 = reinterpret_cast<int*>(fin_smem + sizeof(TileFinal));           // [Sw] source column of tap 0
+    int* xi1 = xi0 + r.Sw;                                                      // [Sw] source column of tap 1 (-1: padding)
+    float* xw = reinterpret_cast<float*>(xi1 + r.Sw);                           // [Sw]
+    float* vals = reinterpret_cast<float*>(fin_smem + sizeof(TileFinal) + (((size_t)r.Sw * 12 + 15) & ~(size_t)15));
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const PPParams& p = r.p;
+    const int Ty = p.Ty, Tx = p.Tx;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&p.fin[b]);
+        uint4* dst = reinterpret_cast<uint4*>(&tf);
+        // the histogram-equalisation tables are the bulk of the state: skip them when no channel uses them
+        const int n_head = (int)(offsetof(TileFinal, he) / 16), n_all = (int)(sizeof(TileFinal) / 16);
+        const int n_tail0 = (int)((offsetof(TileFinal, he) + sizeof(HistEq)) / 16);
+        for (int i = tid; i < n_head; i += kFinThreads) dst[i] = src[i];
+        for (int i = n_tail0 + tid; i < n_all; i += kFinThreads) dst[i] = src[i];
+        __syncthreads();
+        if (tf.status == 0 && tf.use_he)
+            for (int i = n_head + tid; i < n_tail0; i += kFinThreads) dst[i] = src[i];
+        if (!r.emit_only)
+            for (int ox = tid; ox < r.Sw; ox += kFinThreads) {
+                const int rx = ox - r.left;
+                int a = -1, c = -1;
+                float w = 0.f;
+                if (rx >= 0 && rx < r.new_w) src_coord(rx, r.scale_x, Tx, a, c, w);
+                xi0[ox] = a;
+                xi1[ox] = c;
+                xw[ox] = w;
+            }
+        __syncthreads();
+    }
+    const bool ok = tf.status == 0;
+    float* chain = p.chain_out ? p.chain_out + (long long)b * Ty * Tx * 3 : nullptr;
+    for (int band = blockIdx.y; band < r.nbands; band += gridDim.y) {
+        int yin0, nrows, oy0 = 0, oy1 = 0;
+        if (r.emit_only) {
+            yin0 = band * r.band_h;
+            nrows = min(Ty, yin0 + r.band_h) - yin0;
+        } else {
+            oy0 = band * r.band_h;
+            oy1 = min(r.Sh, oy0 + r.band_h);
+            const int ry0 = max(oy0 - r.top, 0), ry1 = min(oy1 - r.top, r.new_h);   // resized-image rows [ry0, ry1)
+            yin0 = 0;
+            nrows = 0;
+            if (ry0 < ry1) {
+                int a0, a1, c0, c1;
+                float w;
+                src_coord(ry0, r.scale_y, Ty, a0, a1, w);
+                src_coord(ry1 - 1, r.scale_y, Ty, c0, c1, w);
+                yin0 = a0;
+                nrows = c1 - a0 + 1;
+            }
+        }
+        // evaluate the input rows of the band once
+        for (int i = tid; i < nrows * Tx; i += kFinThreads) {
+            float o[3] = {0.f, 0.f, 0.f};
+            if (ok) eval3(tf, load_pixel(p, b, yin0 * Tx + i), o);
+            vals[3 * i + 0] = o[0];
+            vals[3 * i + 1] = o[1];
+            vals[3 * i + 2] = o[2];
+        }
+        __syncthreads();
+        if (r.emit_only) {
+            if (chain)
+                for (int i = tid; i < nrows * Tx * 3; i += kFinThreads) chain[(long long)yin0 * Tx * 3 + i] = vals[i];
+        } else {
+            const int nout = (oy1 - oy0) * r.Sw;
+            for (int o = tid; o < nout; o += kFinThreads) {
+                const int dy = o / r.Sw, ox = o - dy * r.Sw, oy = oy0 + dy;
+                float v[3] = {114.f, 114.f, 114.f};   // cv2.copyMakeBorder value
+                const int ry = oy - r.top;
+                const int x0 = xi0[ox];
+                if (ry >= 0 && ry < r.new_h && x0 >= 0) {
+                    int y0, y1;
+                    float wy;
+                    src_coord(ry, r.scale_y, Ty, y0, y1, wy);
+                    const int x1 = xi1[ox];
+                    const float wx = xw[ox];
+                    const float* p00 = vals + ((y0 - yin0) * Tx + x0) * 3;
+                    const float* p01 = vals + ((y0 - yin0) * Tx + x1) * 3;
+                    const float* p10 = vals + ((y1 - yin0) * Tx + x0) * 3;
+                    const float* p11 = vals + ((y1 - yin0) * Tx + x1) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float t0 = p00[c] * (1.f - wx) + p01[c] * wx;
+                        const float t1 = p10[c] * (1.f - wx) + p11[c] * wx;
+                        v[c] = t0 * (1.f - wy) + t1 * wy;
+                    }
+                }
+                // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
+                const float m0 = v[2] / 255.f, m1 = v[1] / 255.f, m2 = v[0] / 255.f;
+                const long long idx = ((long long)b * r.Sh + oy) * r.Sw + ox;
+                uint2 pk;
+                pk.x = pack_h2(m0, m1, r.f16);
+                pk.y = pack_h2(m2, 0.f, r.f16);
+                *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(r.out16) + idx * 4) = pk;
+                if (r.out_f32) {
+                    const long long plane = (long long)r.Sh * r.Sw;
+                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)oy * r.Sw + ox;
+                    of[0] = m0;
+                    of[plane] = m1;
+                    of[2 * plane] = m2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ letterbox resize of an HWC image
+
 
 struct ResizeParams {
     const float* chain;  // [B,Ty,Tx,3]
@@ -1236,6 +1407,7 @@ struct ResizeParams {
     int B, Ty, Tx, Sh, Sw;
     int new_h, new_w, top, left;
     double scale_y, scale_x;  // 1 / (dst/src), as cv2.resize computes it
+    int f16;                  // 16-bit output format: 0 bf16, 1 fp16
 };
 
 __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
@@ -1272,9 +1444,8 @@ __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
     // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
     const float m0 = v[2] / 255.f, m1 = v[1] / 255.f, m2 = v[0] / 255.f;
     uint2 pk;
-    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-    p2[0] = __floats2bfloat162_rn(m0, m1);
-    p2[1] = __floats2bfloat162_rn(m2, 0.f);
+    pk.x = pack_h2(m0, m1, r.f16);
+    pk.y = pack_h2(m2, 0.f, r.f16);
     *reinterpret_cast<uint2*>(r.out + idx * 4) = pk;
     if (r.out_f32) {
         const long long plane = (long long)r.Sh * r.Sw;
@@ -1297,10 +1468,60 @@ extern "C" int cy_sort_set_debug(void* dev_buf) {
     return CY_OK;
 }
 
+// Letterbox geometry shared by the fused final kernel and cy_letterbox_resize (ultralytics LetterBox, App. A.4).
+struct LbGeom {
+    int Sh, Sw, new_h, new_w, top, left;
+    double scale_y, scale_x;
+};
+static int lb_geometry(int Ty, int Tx, int imgsz, LbGeom* g) {
+    cy_letterbox lb;
+    int rc = cy_letterbox_shape(Ty, Tx, imgsz, &g->Sh, &g->Sw, &lb);
+    if (rc) return rc;
+    const double rr = fmin((double)imgsz / Ty, (double)imgsz / Tx);
+    g->new_w = (int)nearbyint(Tx * rr);
+    g->new_h = (int)nearbyint(Ty * rr);
+    g->top = (int)nearbyint(((imgsz - g->new_h) % 32) / 2.0 - 0.1);
+    g->left = (int)nearbyint(((imgsz - g->new_w) % 32) / 2.0 - 0.1);
+    g->scale_x = 1.0 / ((double)g->new_w / (double)Tx);
+    g->scale_y = 1.0 / ((double)g->new_h / (double)Ty);
+    return CY_OK;
+}
+// host copy of the kernel's source-coordinate rule
+static void src_coord_host(int d, double scale, int n, int* i0, int* i1) {
+    const double f = ((double)d + 0.5) * scale - 0.5;
+    int a = (int)floor(f);
+    if (a < 0) a = 0;
+    if (a >= n - 1) a = n - 1;
+    *i0 = a;
+    *i1 = a + 1 < n - 1 ? a + 1 : n - 1;
+}
+static constexpr int kFinBandH = 8;            // output rows per band of the fused final kernel
+static constexpr size_t kFinSmemMax = 100 * 1024;   // two CTAs per SM
+
+static size_t fin_smem_bytes(int Sw, int rows, int Tx) {
+    return sizeof(cy::TileFinal) + (((size_t)Sw * 12 + 15) & ~(size_t)15) + (size_t)rows * Tx * 12;
+}
+// rows of shared memory the fused bands need (0: does not fit -> chain_out + pp_resize_kernel path)
+static int fin_rows_cap(const LbGeom& g, int Ty, int Tx) {
+    int cap = 1;
+    for (int oy0 = 0; oy0 < g.Sh; oy0 += kFinBandH) {
+        const int oy1 = oy0 + kFinBandH < g.Sh ? oy0 + kFinBandH : g.Sh;
+        const int ry0 = oy0 - g.top > 0 ? oy0 - g.top : 0, ry1 = oy1 - g.top < g.new_h ? oy1 - g.top : g.new_h;
+        if (ry0 >= ry1) continue;
+        int a0, a1, c0, c1;
+        src_coord_host(ry0, g.scale_y, Ty, &a0, &a1);
+        src_coord_host(ry1 - 1, g.scale_y, Ty, &c0, &c1);
+        if (c1 - a0 + 1 > cap) cap = c1 - a0 + 1;
+    }
+    return fin_smem_bytes(g.Sw, cap, Tx) <= kFinSmemMax ? cap : 0;
+}
+
 extern "C" size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg, int B, int Ty, int Tx) {
     const size_t N = (size_t)Ty * Tx;
     const int nbuf = 3 + ((cfg && cfg->enabled && cfg->subtract_bkg && cfg->use_box_mask_in_bkg) ? 1 : 0);
-    return (size_t)nbuf * align256((size_t)B * N * 4) + 2 * align256((size_t)B * 4) + 256;
+    // + the per-tile final maps + (tiles too large for the fused final kernel) the fp32 HWC chain image
+    return (size_t)nbuf * align256((size_t)B * N * 4) + 2 * align256((size_t)B * 4) + align256((size_t)B * sizeof(cy::TileFinal)) +
+           align256((size_t)B * N * 12) + 256;
 }
 
 extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long row_stride, int big_endian,
@@ -1308,10 +1529,12 @@ extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long
                              float* chain_out, void* model_in, float* model_in_f32, int32_t* status, void* scratch,
                              uintptr_t stream) {
     using namespace cy;
-    if (!cfg || !img || !tile_x0 || !tile_y0 || !chain_out || !status || !scratch)
+    if (!cfg || !img || !tile_x0 || !tile_y0 || !status || !scratch)
         return set_error(CY_ERR_INVALID, "cy_preprocess: null argument");
+    if (!chain_out && !model_in) return set_error(CY_ERR_INVALID, "cy_preprocess: no output requested");
     if (B <= 0 || Ty <= 0 || Tx <= 0) return set_error(CY_ERR_INVALID, "cy_preprocess: invalid shape");
     if ((long long)Ty * Tx >= (1ll << 30)) return set_error(CY_ERR_INVALID, "cy_preprocess: tile too large");
+    if (B > 65535) return set_error(CY_ERR_INVALID, "cy_preprocess: at most 65535 tiles per call");
     if (cfg->enabled) {
         if (cfg->nchannels != 1 && cfg->nchannels != 3)
             return set_error(CY_ERR_INVALID, "nchannels must be 1 or 3 (the model takes 3-channel images)");
@@ -1340,44 +1563,92 @@ extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long
         s += buf;
     }
     p.nlive = (int*)s; s += align256((size_t)B * 4);
-    p.nbox = (int*)s;
+    p.nbox = (int*)s; s += align256((size_t)B * 4);
+    p.fin = (TileFinal*)s; s += align256((size_t)B * sizeof(TileFinal));
+    float* chain_scratch = (float*)s;
     p.chain_out = chain_out;
     p.status = status;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (first_use_on_device(attr_done)) {
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
-        attr_done = true;
+        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemMax));
     }
     pp_sort_kernel<<<B, kSortThreads, sizeof(SortSmem), st>>>(p);
     pp_chain_kernel<<<B, kPPThreads, sizeof(Shared), st>>>(p);
     CY_CUDA_CHECK(cudaGetLastError());
-    if (model_in) return cy_letterbox_resize(chain_out, B, Ty, Tx, imgsz, model_in, model_in_f32, stream);
+
+    LbGeom g;
+    int rc = lb_geometry(Ty, Tx, imgsz, &g);
+    if (rc) return rc;
+    FinalParams r;
+    r.p = p;
+    r.out16 = model_in;
+    r.out_f32 = model_in_f32;
+    r.Sh = g.Sh; r.Sw = g.Sw; r.new_h = g.new_h; r.new_w = g.new_w; r.top = g.top; r.left = g.left;
+    r.scale_y = g.scale_y; r.scale_x = g.scale_x;
+    r.f16 = cfg->out_f16 ? 1 : 0;
+    const int sms = current_device_sms();
+    const int cap = model_in ? fin_rows_cap(g, Ty, Tx) : 0;
+    auto emit_chain = [&](float* dst) -> int {   // evaluated maps as an fp32 HWC image (parity output / resize input)
+        FinalParams e = r;
+        e.p.chain_out = dst;
+        e.emit_only = 1;
+        const int rows_fit = (int)((kFinSmemMax - sizeof(TileFinal) - 64) / ((size_t)Tx * 12));
+        if (rows_fit < 1) return set_error(CY_ERR_INVALID, "cy_preprocess: tile rows of %d pixels do not fit shared memory", Tx);
+        e.band_h = rows_fit < 8 ? rows_fit : 8;
+        e.rows_cap = e.band_h;
+        e.nbands = (Ty + e.band_h - 1) / e.band_h;
+        e.Sw = 0;
+        int chunks = (2 * sms + B - 1) / B;
+        chunks = chunks < 1 ? 1 : (chunks > e.nbands ? e.nbands : chunks);
+        pp_final_kernel<<<dim3((unsigned)B, (unsigned)chunks), kFinThreads, fin_smem_bytes(0, e.band_h, Tx), st>>>(e);
+        return CY_OK;
+    };
+    if (chain_out && (rc = emit_chain(chain_out))) return rc;
+    if (model_in) {
+        if (cap > 0) {
+            r.emit_only = 0;
+            r.band_h = kFinBandH;
+            r.rows_cap = cap;
+            r.nbands = (g.Sh + kFinBandH - 1) / kFinBandH;
+            int chunks = (2 * sms + B - 1) / B;
+            chunks = chunks < 1 ? 1 : (chunks > r.nbands ? r.nbands : chunks);
+            pp_final_kernel<<<dim3((unsigned)B, (unsigned)chunks), kFinThreads, fin_smem_bytes(g.Sw, cap, Tx), st>>>(r);
+        } else {
+            // bands of this tile shape do not fit shared memory: materialise the fp32 HWC image once, then resize it
+            float* hwc = chain_out ? chain_out : chain_scratch;
+            if (!chain_out && (rc = emit_chain(hwc))) return rc;
+            rc = cy_letterbox_resize_fmt(hwc, B, Ty, Tx, imgsz, model_in, model_in_f32, r.f16, stream);
+            if (rc) return rc;
+        }
+    }
+    CY_CUDA_CHECK(cudaGetLastError());
     return CY_OK;
 }
 
 extern "C" int cy_letterbox_resize(const float* chain, int B, int Ty, int Tx, int imgsz, void* model_in,
                                    float* model_in_f32, uintptr_t stream) {
+    return cy_letterbox_resize_fmt(chain, B, Ty, Tx, imgsz, model_in, model_in_f32, 0, stream);
+}
+
+extern "C" int cy_letterbox_resize_fmt(const float* chain, int B, int Ty, int Tx, int imgsz, void* model_in,
+                                       float* model_in_f32, int out_f16, uintptr_t stream) {
     using namespace cy;
     if (!chain || !model_in || B <= 0) return set_error(CY_ERR_INVALID, "cy_letterbox_resize: invalid argument");
-    int Sh, Sw;
-    cy_letterbox lb;
-    int rc = cy_letterbox_shape(Ty, Tx, imgsz, &Sh, &Sw, &lb);
+    LbGeom g;
+    int rc = lb_geometry(Ty, Tx, imgsz, &g);
     if (rc) return rc;
     ResizeParams r;
     r.chain = chain;
     r.out = (__nv_bfloat16*)model_in;
     r.out_f32 = model_in_f32;
-    r.B = B; r.Ty = Ty; r.Tx = Tx; r.Sh = Sh; r.Sw = Sw;
-    const double rr = fmin((double)imgsz / Ty, (double)imgsz / Tx);
-    r.new_w = (int)nearbyint(Tx * rr);
-    r.new_h = (int)nearbyint(Ty * rr);
-    r.top = (int)nearbyint(((imgsz - r.new_h) % 32) / 2.0 - 0.1);
-    r.left = (int)nearbyint(((imgsz - r.new_w) % 32) / 2.0 - 0.1);
-    r.scale_x = 1.0 / ((double)r.new_w / (double)Tx);
-    r.scale_y = 1.0 / ((double)r.new_h / (double)Ty);
-    if (Sh > 65535 || B > 65535) return set_error(CY_ERR_INVALID, "cy_letterbox_resize: batch or image too large");
-    pp_resize_kernel<<<dim3((unsigned)((Sw + 255) / 256), (unsigned)Sh, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(r);
+    r.B = B; r.Ty = Ty; r.Tx = Tx; r.Sh = g.Sh; r.Sw = g.Sw;
+    r.new_w = g.new_w; r.new_h = g.new_h; r.top = g.top; r.left = g.left;
+    r.scale_x = g.scale_x; r.scale_y = g.scale_y;
+    r.f16 = out_f16 ? 1 : 0;
+    if (g.Sh > 65535 || B > 65535) return set_error(CY_ERR_INVALID, "cy_letterbox_resize: batch or image too large");
+    pp_resize_kernel<<<dim3((unsigned)((g.Sw + 255) / 256), (unsigned)g.Sh, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(r);
     CY_CUDA_CHECK(cudaGetLastError());
     return CY_OK;
 }

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "half16.cuh"
 #include <stdint.h>
 
 namespace cy {
@@ -210,9 +212,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
     uint64_t sbo = (8ull * row_bytes) >> 4;
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
-// bf16 x bf16 -> f32, A and B K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// bf16 x bf16 -> f32 (f16 != 0: fp16 x fp16 -> f32: A / B format fields 0 instead of 1; same kind::f16 instruction and
+// rate), A and B K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int f16 = 0) {
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ bool elect_one() {

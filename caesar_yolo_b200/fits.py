@@ -52,8 +52,8 @@ class FitsImage(object):
                         self.header[key] = _value(card[10:])
         h = self.header
         naxis = h.get("NAXIS", 0)
-        if naxis not in (2, 3, 4):
-            raise ValueError("unsupported NAXIS=%s in %s" % (naxis, path))
+        if naxis not in (2, 4):   # read_fits / read_fits_crop accept 2-D images and 4-D cubes only (utils.py:207-216,378-386)
+            raise ValueError("Invalid/unsupported number of channels found in file %s (nchan=%s)" % (path, naxis))
         self.nx, self.ny = int(h["NAXIS1"]), int(h["NAXIS2"])
         self.bitpix = int(h["BITPIX"])
         self.offset = off

@@ -77,7 +77,8 @@ class SFinder(object):
                                  score_thr=self.config['score_thr'], iou_thr=self.config['iou_thr'],
                                  thr_soft=self.config['merge_overlap_iou_thr_soft'],
                                  thr_hard=self.config['merge_overlap_iou_thr_hard'], device=dev,
-                                 batch_tiles=self.config.get('batch_tiles', 296))
+                                 batch_tiles=self.config.get('batch_tiles', 296),
+                                 precision=self.config.get('precision'))
         return self.engine
 
     def set_img_size_params(self):
@@ -194,7 +195,8 @@ class SFinder(object):
             # evaluation.py:171-176 (bug-compatible: image[i] is ROW i): a constant row 0..2 rejects the image
             if any(cube[i].min() == cube[i].max() for i in range(min(3, H))):
                 status[0] = -1
-            x, _ = ops.letterbox_resize(torch.from_numpy(cube).to(eng.device).unsqueeze(0), eng.imgsz)
+            x, _ = ops.letterbox_resize(torch.from_numpy(cube).to(eng.device).unsqueeze(0), eng.imgsz,
+                                        dtype=eng.model.dtype)
             Sh, Sw, lb = ops.letterbox_shape(H, W, eng.imgsz)
             eng._run_batch(x, status, torch.zeros(1, dtype=torch.int32, device=eng.device), H, W, Sh, Sw, lb)
         packed, n = eng.finish()
@@ -223,7 +225,7 @@ class SFinder(object):
                          ntasks_max, c['max_ntasks_per_worker'])
             return -1
         eng = self._engine()
-        img = self.fits.raw if self.fits.is_raw_f32 else self.fits.rows(0, self.fits.ny)
+        img = self.fits   # raw big-endian float32 rows are read from the file into pinned staging (pipeline._RowSource)
         # per-tile debug files (inference.py:218-229): every rank writes the files of its own tiles
         hook = None
         eng.collect_tile_status = bool(self.save_tile_json or self.save_tile_regions)

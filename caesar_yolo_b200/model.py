@@ -27,8 +27,10 @@ class Results(object):
 
 
 class YOLO(object):
-    def __init__(self, weights, device=None):
-        """weights: path of a caesar_yolo_b200 weight file (weights.py) or an already loaded weight dict."""
+    def __init__(self, weights, device=None, precision=None):
+        """weights: path of a caesar_yolo_b200 weight file (weights.py) or an already loaded weight dict.
+        precision: 'fp16' / 'bf16' storage of weights and activations (None: ops.DEFAULT_PRECISION)."""
+        self.precision = precision
         self.weights = W.load_weights(weights) if isinstance(weights, str) else weights
         self.names = dict(self.weights['names'])
         self._models = {}
@@ -38,7 +40,7 @@ class YOLO(object):
         dev = torch.cuda.current_device()
         m = self._models.get(dev)
         if m is None:
-            m = ops.DeviceModel(self.weights)
+            m = ops.DeviceModel(self.weights, precision=self.precision)
             self._models[dev] = m
         return m
 
@@ -55,9 +57,9 @@ class YOLO(object):
         dev = torch.device('cuda:%d' % torch.cuda.current_device())
         H, Wd = a.shape[:2]
         chain = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev).unsqueeze(0)
-        x, _ = ops.letterbox_resize(chain, imgsz)
-        Sh, Sw, lb = ops.letterbox_shape(H, Wd, imgsz)
         m = self.device_model()
+        x, _ = ops.letterbox_resize(chain, imgsz, dtype=m.dtype)
+        Sh, Sw, lb = ops.letterbox_shape(H, Wd, imgsz)
         heads = m.forward(x)
         dets, nd = ops.postprocess(heads, 1, Sh, Sw, m.nc, conf, iou, ops.letterbox_array([lb], dev), dev)
         n = int(nd[0].item())

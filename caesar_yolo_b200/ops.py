@@ -1,6 +1,7 @@
 """Thin Python handles on the C-ABI stage kernels (torch used only for device memory + streams).
 Every function here calls libcaesar_b200.so; there is no CPU or torch fallback."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -61,17 +62,36 @@ def letterbox_shape(Ty, Tx, imgsz):
     return sh.value, sw.value, lb
 
 
+# 16-bit storage format of weights / activations.  fp16 and bf16 run on the same tcgen05 kind::f16 instruction at the same
+# rate with fp32 accumulation; fp16 keeps 11 significand bits instead of 8, which is what decides how closely the
+# catalogs follow the reference's fp32 arithmetic (matched fraction 0.986 vs 0.919 on the same mosaic;
+# the reference's own TF32 GPU path reaches 0.993), and it is the type ultralytics' `half=True` uses.
+DEFAULT_PRECISION = os.environ.get('CY_PRECISION', 'fp16')
+
+
+def storage_dtype(precision):
+    """torch dtype of the 16-bit storage format: 'fp16' or 'bf16' (None: DEFAULT_PRECISION)."""
+    if precision is None:
+        precision = DEFAULT_PRECISION
+    if precision in ('bf16', 0, False):
+        return torch.bfloat16
+    if precision in ('fp16', 'f16', 'half', 1, True):
+        return torch.float16
+    raise ValueError("precision must be 'bf16' or 'fp16' (got %r)" % (precision,))
+
+
 def preprocess(cfg, img, row_stride, big_endian, tile_x0, tile_y0, Ty, Tx, imgsz, want_f32=False, scratch=None,
-               chain_out=None, model_in=None, status=None):
+               chain_out=None, model_in=None, status=None, want_chain=True):
     """cy_preprocess.  img: device tensor (any dtype of 4-byte elements); tile_x0/y0: int32 device tensors [B].
-    Returns (chain_out [B,Ty,Tx,3] f32, model_in [B,Sh,Sw,4] bf16, model_in_f32 or None, status [B] i32)."""
+    Returns (chain_out [B,Ty,Tx,3] f32 or None, model_in [B,Sh,Sw,4] bf16 / fp16 (cfg.out_f16), model_in_f32 or None,
+    status [B] i32).  want_chain=False skips the fp32 chain image (the production path: it only exists for parity)."""
     B = tile_x0.numel()
     dev = img.device
     Sh, Sw, _ = letterbox_shape(Ty, Tx, imgsz)
-    if chain_out is None:
+    if chain_out is None and want_chain:
         chain_out = torch.empty((B, Ty, Tx, 3), dtype=torch.float32, device=dev)
     if model_in is None:
-        model_in = torch.empty((B, Sh, Sw, 4), dtype=torch.bfloat16, device=dev)
+        model_in = torch.empty((B, Sh, Sw, 4), dtype=torch.float16 if cfg.out_f16 else torch.bfloat16, device=dev)
     f32 = torch.empty((B, 3, Sh, Sw), dtype=torch.float32, device=dev) if want_f32 else None
     if status is None:
         status = torch.empty((B,), dtype=torch.int32, device=dev)
@@ -84,14 +104,14 @@ def preprocess(cfg, img, row_stride, big_endian, tile_x0, tile_y0, Ty, Tx, imgsz
     return chain_out, model_in, f32, status
 
 
-def letterbox_resize(chain, imgsz, want_f32=False):
-    """chain: [B,Ty,Tx,3] f32 device -> model_in [B,Sh,Sw,4] bf16 (+ optional f32 NCHW)."""
+def letterbox_resize(chain, imgsz, want_f32=False, dtype=torch.bfloat16):
+    """chain: [B,Ty,Tx,3] f32 device -> model_in [B,Sh,Sw,4] bf16 / fp16 (+ optional f32 NCHW)."""
     B, Ty, Tx, _ = chain.shape
     Sh, Sw, _ = letterbox_shape(Ty, Tx, imgsz)
-    model_in = torch.empty((B, Sh, Sw, 4), dtype=torch.bfloat16, device=chain.device)
+    model_in = torch.empty((B, Sh, Sw, 4), dtype=dtype, device=chain.device)
     f32 = torch.empty((B, 3, Sh, Sw), dtype=torch.float32, device=chain.device) if want_f32 else None
-    check(lib.cy_letterbox_resize(ptr(chain), c_int(B), c_int(Ty), c_int(Tx), c_int(imgsz), ptr(model_in), ptr(f32),
-                                  cur_stream()))
+    check(lib.cy_letterbox_resize_fmt(ptr(chain), c_int(B), c_int(Ty), c_int(Tx), c_int(imgsz), ptr(model_in),
+                                      ptr(f32), c_int(1 if dtype == torch.float16 else 0), cur_stream()))
     return model_in, f32
 
 
@@ -142,13 +162,16 @@ def stem_conv(x, w_oihw, bias, act=1):
 class DeviceModel(object):
     """YOLOv8 DetectionModel resident on the current CUDA device (cy_model_*)."""
 
-    def __init__(self, weights):
+    def __init__(self, weights, precision=None):
         self.variant = weights['variant']
         self.nc = int(weights['nc'])
         self.names = dict(weights['names'])
+        self.dtype = storage_dtype(precision)
+        self.precision = 'fp16' if self.dtype == torch.float16 else 'bf16'
         h = c_void_p(0)
         check(lib.cy_model_create(self.variant.encode(), c_int(self.nc), ctypes.byref(h)))
         self._h = h
+        check(lib.cy_model_set_precision(self._h, c_int(1 if self.dtype == torch.float16 else 0)))
         for k, v in weights['state_dict'].items():
             if '.dfl.' in k:
                 continue
@@ -157,9 +180,12 @@ class DeviceModel(object):
         check(lib.cy_model_finalize(self._h))
 
     def forward(self, x):
-        """x: [B,Sh,Sw,4] bf16 NHWC -> three raw head maps [B,h,w,80] f32 (views of model-owned buffers)."""
+        """x: [B,Sh,Sw,4] NHWC in the model's storage format (bf16 / fp16) -> three raw head maps [B,h,w,80] f32 (views
+        of model-owned buffers)."""
         B, Sh, Sw, C = x.shape
-        assert C == 4 and x.dtype == torch.bfloat16 and x.is_contiguous()
+        if x.dtype != self.dtype:
+            raise CaesarB200Error("model input is %s but the model stores %s" % (x.dtype, self.dtype))
+        assert C == 4 and x.is_contiguous()
         heads = (c_void_p * 3)()
         check(lib.cy_model_forward(self._h, ptr(x), c_int(B), c_int(Sh), c_int(Sw), heads, cur_stream()))
         return [int(heads[l]) for l in range(3)]
@@ -181,6 +207,14 @@ class DeviceModel(object):
         check(lib.cy_model_info(self._h, c_int(B), c_int(Sh), c_int(Sw), a))
         keys = ('nparams', 'flops', 'launches', 'act_bytes', 'c3', 'c4', 'c5', 'nconv')
         return dict(zip(keys, [float(v) for v in a]))
+
+    def plan_summary(self, B, Sh, Sw):
+        """What the planner chose for this shape: launches by kind (cy_model_plan_summary)."""
+        a = (c_int * 8)()
+        check(lib.cy_model_plan_summary(self._h, c_int(B), c_int(Sh), c_int(Sw), a))
+        keys = ('conv_launches', 'pair_launches', 'mode0_launches', 'mode1_launches', 'mode2_launches',
+                'mode3_launches', 'wide_launches', 'two_half_launches')
+        return dict(zip(keys, [int(v) for v in a]))
 
     def conv_bytes(self, B, Sh, Sw):
         """(algorithmic HBM bytes of all conv launches of one forward, number of conv launches)."""
@@ -280,10 +314,11 @@ def make_records(dets, keep_idx, nkeep, status, tiles_dev, tile_ids, recs, nrec)
                               ptr(tile_ids), c_int(B), ptr(recs), ptr(nrec), cur_stream()))
 
 
-def compact_records(slots, counts, T, slot_stride, out, total):
+def compact_records(slots, counts, T, slot_stride, out, total, scratch=None):
     dev = slots.device
     need = int(lib.cy_compact_scratch_bytes(c_int(T)))
-    scratch = torch.empty((need,), dtype=torch.uint8, device=dev)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((need,), dtype=torch.uint8, device=dev)
     check(lib.cy_compact_records(ptr(slots), ptr(counts), c_int(T), c_int(slot_stride), ptr(out), ptr(total),
                                  ptr(scratch), cur_stream()))
 

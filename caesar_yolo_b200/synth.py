@@ -79,3 +79,25 @@ def write_fits(filename, data, extra_cards=None):
         pad = (-nbytes) % 2880
         if pad:
             f.write(b"\0" * pad)
+
+
+def write_fits_raw_be(filename, payload_be):
+    """Like write_fits, for a payload that already is in FITS byte order: `payload_be` is a 2-D array of 4-byte words
+    holding big-endian float32 pixels (what bench.py keeps in pinned memory); written byte for byte."""
+    a = np.asarray(payload_be)
+    ny, nx = a.shape
+    assert a.dtype.itemsize == 4
+    cards = [("SIMPLE", "T"), ("BITPIX", "-32"), ("NAXIS", "2"), ("NAXIS1", str(nx)), ("NAXIS2", str(ny))]
+    txt = "".join(("%-8s= %20s" % (k, v)).ljust(80) for k, v in cards) + "END".ljust(80)
+    txt = txt.ljust((len(txt) + 2879) // 2880 * 2880)
+    with open(filename, "wb") as f:
+        f.write(txt.encode("ascii"))
+        rows = max(1, (1 << 26) // (nx * 4))
+        nbytes = 0
+        for y0 in range(0, ny, rows):
+            blk = np.ascontiguousarray(a[y0:y0 + rows])
+            f.write(memoryview(blk).cast('B'))
+            nbytes += blk.nbytes
+        pad = (-nbytes) % 2880
+        if pad:
+            f.write(b"\0" * pad)

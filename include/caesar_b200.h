@@ -49,6 +49,7 @@ typedef struct {
     int32_t chan3_preproc;       double sigma_clip_baseline;
     int32_t normalize_minmax;    double norm_min, norm_max;
     int32_t enabled;             /* --preprocessing: 0 => the whole chain is skipped (dp = None) */
+    int32_t out_f16;             /* model_in format: 0 = bf16, 1 = fp16 (must match cy_model_set_precision) */
 } cy_pp_config;
 
 const char* cy_last_error(void);
@@ -76,8 +77,11 @@ int cy_tile_neighbors(const cy_tile* tiles_host, int T, int* nb_off_host, int* n
  * img: fp32 image in device memory, row-major with row_stride elements per row; big_endian != 0 means raw FITS
  * byte order (byte-swapped on load); non-finite pixels become 0 (utils.py:219,394).  Tile b covers
  * img[tile_y0[b] .. +Ty, tile_x0[b] .. +Tx].
- * chain_out  [B,Ty,Tx,3] fp32  : chain output before the resize (parity entry; also the resize input)
- * model_in   [B,Sh,Sw,4] bf16  : letterboxed, channel-reversed, /255, NHWC (4th channel 0) — cy_model_forward input
+ * chain_out  [B,Ty,Tx,3] fp32  : OPTIONAL (NULL: skipped) chain output before the resize — the parity surface; the
+ *                                production path never materialises it (the final maps are evaluated per pixel inside
+ *                                the fused letterbox kernel)
+ * model_in   [B,Sh,Sw,4] bf16  : OPTIONAL letterboxed, channel-reversed, /255, NHWC (4th channel 0) — cy_model_forward
+ *                                input (fp16 when cfg->out_f16)
  * model_in_f32 (optional) [B,3,Sh,Sw] fp32 NCHW: the same before bf16 rounding (parity entry)
  * status [B]: 0 ok, -1 tile rejected like the reference (preprocess returned None / constant rows,
  *             evaluation.py:164-176), -3 degenerate statistics (empty clip set). */
@@ -91,6 +95,9 @@ int cy_preprocess(const cy_pp_config* cfg_host, const void* img, long long row_s
  * `model(image, imgsz=...)` call of the reference does before the forward (caesar_yolo/evaluation.py:181-193). */
 int cy_letterbox_resize(const float* chain, int B, int Ty, int Tx, int imgsz, void* model_in, float* model_in_f32,
                         uintptr_t stream);
+/* Same with the 16-bit output format selectable: out_f16 = 0 bf16, 1 fp16. */
+int cy_letterbox_resize_fmt(const float* chain, int B, int Ty, int Tx, int imgsz, void* model_in, float* model_in_f32,
+                            int out_f16, uintptr_t stream);
 
 /* ------------------------------------------------------------------------------------------------ convolution
  * Layer primitive (ultralytics Conv = Conv2d+BN+SiLU fused; reference model call at
@@ -127,7 +134,14 @@ int cy_stem_conv_nhwc4(const void* in, int B, int H, int W, const float* w_host,
  * [B, Sh/s, Sw/s, 80] fp32, s = 8,16,32: 64 DFL logits + nc class logits per anchor. */
 int cy_model_create(const char* variant, int nc, void** model_host);
 int cy_model_set_tensor(void* model, const char* name, const float* data_host, long long numel);
+/* Storage format of weights and activations (call before cy_model_finalize): 0 = bf16 (default), 1 = fp16.  Both run
+ * on the same tcgen05 kind::f16 instruction at the same rate with fp32 accumulation; fp16 keeps 11 significand bits
+ * instead of 8 (ultralytics' own `half=True` inference type).  The model input (cy_preprocess out_f16) must match. */
+int cy_model_set_precision(void* model, int fp16);
 int cy_model_finalize(void* model);
+/* info_host[0..7] of the plan for (B,Sh,Sw): conv launches, CTA-pair launches, launches in tap modes 0..3,
+ * 256-wide-tile launches, two-half-tile launches (what the planner chose; parity tests assert on it). */
+int cy_model_plan_summary(void* model, int B, int Sh, int Sw, int* info_host);
 int cy_model_forward(void* model, const void* in, int B, int Sh, int Sw, const float** heads_host, uintptr_t stream);
 /* info_host[0..7] = nparams, flops per forward of the last planned shape, #kernel launches per forward,
  * activation bytes, c3, c4, c5, #convs */

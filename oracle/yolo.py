@@ -34,17 +34,33 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def _fp16(x):
+    return x.to(torch.float16).to(torch.float32)
+
+
+def _tf32(x):
+    """Round to TF32 (10 explicit mantissa bits, round-to-nearest, ties away: cvt.rna.tf32.f32) — what cuDNN's default
+    `allow_tf32` convolution path of the reference's own --devices=cuda run feeds the tensor cores."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 class OracleYolo(object):
     """YOLOv8 DetectionModel with Conv+BN fused (ultralytics fuse()), fp32 on CPU.  emulate_bf16=True rounds
     weights and every layer output to bf16 (what the B200 path stores) to separate quantisation from kernel
     bugs; the default is the reference's fp32."""
 
     def __init__(self, weights, emulate_bf16=False):
+        # emulate_bf16: False (fp32), True / 'bf16' (weights + every stored activation rounded to bf16), 'tf32' (conv
+        # operands rounded to TF32, fp32 storage: the reference's own GPU arithmetic), 'perm' (fp32 with the input
+        # channels of every conv visited in reverse order: same math, different accumulation order)
         self.variant = weights['variant']
         self.nc = weights['nc']
         self.names = dict(weights['names'])
         self.a = arch(self.variant) if not str(self.variant).startswith('11') else None
-        self.emu = emulate_bf16
+        self.mode = emulate_bf16 if isinstance(emulate_bf16, str) else ('bf16' if emulate_bf16 else 'fp32')
+        self.emu = self.mode in ('bf16', 'fp16')
+        self._rnd = _fp16 if self.mode == 'fp16' else _bf16
         sd = weights['state_dict']
         self.w = {}
         for k in sd:
@@ -56,16 +72,20 @@ class OracleYolo(object):
                 s = gamma / torch.sqrt(var + 1e-3)
                 wf = w * s.view(-1, 1, 1, 1)
                 bf = beta - mean * s
-                self.w[p] = (_bf16(wf) if self.emu else wf, bf)
+                self.w[p] = (self._rnd(wf) if self.emu else wf, bf)
             elif k.endswith('.2.weight') and '.cv' in k:
                 p = k[:-len('.weight')]
-                self.w[p] = (_bf16(sd[k].float()) if self.emu else sd[k].float(), sd[p + '.bias'].float())
+                self.w[p] = (self._rnd(sd[k].float()) if self.emu else sd[k].float(), sd[p + '.bias'].float())
 
     def _q(self, x):
-        return _bf16(x) if self.emu else x
+        return self._rnd(x) if self.emu else x
 
     def conv(self, x, p, k, s, act=True):
         w, b = self.w[p]
+        if self.mode == 'tf32':
+            x, w = _tf32(x), _tf32(w)
+        elif self.mode == 'perm':
+            x, w = x.flip(1).contiguous(), w.flip(1).contiguous()
         y = F.conv2d(x, w, b, stride=s, padding=k // 2)
         if act:
             y = F.silu(y)

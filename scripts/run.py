@@ -65,6 +65,8 @@ def parse_args(argv=None):
     p.add_argument('--save_tile_catalog', dest='save_tile_catalog', action='store_true')
     p.add_argument('--save_tile_region', dest='save_tile_region', action='store_true')
     p.add_argument('--save_tile_img', dest='save_tile_img', action='store_true')
+    p.add_argument('--precision', required=False, type=str, default=None, choices=['fp16', 'bf16'],
+                   help='B200 build only: 16-bit storage of weights/activations (default fp16; same tensor-core rate)')
     p.add_argument('--detect_outfile', required=False, type=str, default="")
     p.add_argument('--detect_outfile_json', required=False, type=str, default="")
     return p.parse_args(argv)
@@ -159,9 +161,9 @@ def main(argv=None):
         'outfile_json': args.detect_outfile_json, 'draw_plot': args.draw_plots,
         'draw_class_label_in_caption': args.draw_class_label_in_caption, 'save_plot': args.save_plots,
         'save_tile_catalog': args.save_tile_catalog, 'save_tile_region': args.save_tile_region,
-        'save_tile_img': args.save_tile_img,
+        'save_tile_img': args.save_tile_img, 'precision': args.precision,
     })
-    model = YOLO(args.weights)
+    model = YOLO(args.weights, precision=args.precision)
     sfinder = SFinder(model, CONFIG)
     status = sfinder.run_parallel() if args.split_img_in_tiles else sfinder.run()
     if status < 0:

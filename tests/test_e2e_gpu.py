@@ -70,7 +70,7 @@ def _config(path, outdir, dp, split, **kw):
     return cfg
 
 
-def _run_ours(weights, path, outdir, split, **kw):
+def _run_ours(weights, path, outdir, split, precision=None, **kw):
     from caesar_yolo_b200.inference import SFinder
     from caesar_yolo_b200.model import YOLO
     from caesar_yolo_b200.preprocessing import (BkgSubtractor, SigmaClipper, ChanResizer, ZScaleTransformer,
@@ -79,7 +79,7 @@ def _run_ours(weights, path, outdir, split, **kw):
                            ZScaleTransformer(contrasts=[.25, .25, .25]),
                            Chan3Trasformer(sigma_clip_baseline=0, sigma_clip_low=10, sigma_clip_up=10, zscale_contrast=.25),
                            MinMaxNormalizer(norm_min=0, norm_max=255.)])
-    sf = SFinder(YOLO(weights), _config(path, outdir, dp, split, **kw))
+    sf = SFinder(YOLO(weights, precision=precision), _config(path, outdir, dp, split, **kw))
     rc = sf.run_parallel() if split else sf.run()
     assert rc == 0
     return sf
@@ -94,8 +94,8 @@ def _run_oracle(weights, path, outdir, split, emulate_bf16, **kw):
     return sf
 
 
-@pytest.mark.parametrize("step", [1.0, 0.5])
-def test_tiled_mosaic_catalog_matches_oracle(tmp_path, step):
+@pytest.mark.parametrize("step,precision", [(1.0, 'fp16'), (0.5, 'fp16'), (1.0, 'bf16'), (0.5, 'bf16')])
+def test_tiled_mosaic_catalog_matches_oracle(tmp_path, step, precision):
     from caesar_yolo_b200 import synth, weights as W
     ny, nx = 1536, 2048
     mosaic = synth.make_mosaic(ny, nx, seed=31, nan_border_frac=0.0)
@@ -105,20 +105,25 @@ def test_tiled_mosaic_catalog_matches_oracle(tmp_path, step):
     synth.write_fits(path, mosaic)
     w = W.make_random_weights('n', 5, seed=0, cls_bias=-12.0)
     kw = dict(tile_xstep=step, tile_ystep=step)
-    ours = _run_ours(w, path, str(tmp_path), True, **kw)
+    ours = _run_ours(w, path, str(tmp_path), True, precision=precision, **kw)
     got = json.load(open(str(tmp_path / "catalog_mosaic.json")))['sources']
     assert os.path.exists(str(tmp_path / "ds9_mosaic.reg"))
     os.rename(str(tmp_path / "catalog_mosaic.json"), str(tmp_path / "ours.json"))
-    emu = _run_oracle(w, path, str(tmp_path), True, True, **kw).sources['sources']
+    emu = _run_oracle(w, path, str(tmp_path), True, precision, **kw).sources['sources']
     f32 = _run_oracle(w, path, str(tmp_path), True, False, **kw).sources['sources']
     assert len(emu) >= 15, "threshold too high: the test would be vacuous"
     m_emu, m_f32 = match_fraction(got, emu), match_fraction(got, f32)
     m_ref = match_fraction(emu, f32)   # how much of the disagreement is bf16 quantisation itself
-    print("step %.1f: ours %d, oracle(bf16-emulated) %d, oracle(fp32) %d sources; matched@IoU0.9: vs emu %.4f, vs fp32 "
-          "%.4f (emu vs fp32 %.4f)" % (step, len(got), len(emu), len(f32), m_emu, m_f32, m_ref))
-    slack = 0.05 + 2.0 / max(len(emu), 1)     # small catalogs: one flipped source is a large fraction
-    assert m_emu >= 0.90 - slack, m_emu
-    assert m_f32 >= min(0.995, m_ref) - slack, (m_f32, m_ref)
+    print("step %.1f %s: ours %d, oracle(%s-emulated) %d, oracle(fp32) %d sources; matched@IoU0.9: vs emu %.4f, vs fp32 "
+          "%.4f (emu vs fp32 %.4f)" % (step, precision, len(got), precision, len(emu), len(f32), m_emu, m_f32, m_ref))
+    # The storage precision decides how many near-tie decisions of a RANDOM-INIT network flip (the
+    # reference's own TF32 GPU arithmetic reaches 0.993 against its fp32 CPU path on such a mosaic, fp16 storage 0.986,
+    # bf16 storage 0.919); everything downstream of the head maps is bit-exact (tests/test_parity_gpu.py).  The bounds
+    # are the measured levels minus one flipped source on a small catalog.
+    slack = 2.0 / max(len(emu), 1)
+    floor = {'fp16': 0.955, 'bf16': 0.87}[precision]
+    assert m_emu >= floor - slack, m_emu
+    assert m_f32 >= min(floor, m_ref - 0.02) - slack, (m_f32, m_ref)
     assert abs(len(got) - len(f32)) <= 0.1 * len(f32) + 3
     # catalog format
     keys = {'class_id', 'class_name', 'edge', 'merged', 'name', 'score', 'x1', 'x2', 'y1', 'y2'}
@@ -160,7 +165,7 @@ def test_single_image_galaxy0001(tmp_path):
     x = oy.preprocess(img, 640)
     xin = torch.zeros(1, x.shape[2], x.shape[3], 4, dtype=torch.bfloat16)
     xin[..., :3] = x[0].permute(1, 2, 0).to(torch.bfloat16)
-    heads = [h.cpu() for h in ops.DeviceModel(w).forward_tensors(xin.to('cuda:0'))]
+    heads = [h.cpu() for h in ops.DeviceModel(w, precision='bf16').forward_tensors(xin.to('cuda:0'))]
     with torch.no_grad():
         he = oy.OracleYolo(w, emulate_bf16=True).forward_heads(x)
         hf = oy.OracleYolo(w, emulate_bf16=False).forward_heads(x)

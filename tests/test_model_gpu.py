@@ -29,7 +29,7 @@ def _to_nhwc4(x):
 def model_n():
     from caesar_yolo_b200 import ops, weights as W
     w = W.make_random_weights('n', 5, seed=0)
-    return w, ops.DeviceModel(w)
+    return w, ops.DeviceModel(w, precision='bf16')
 
 
 @pytest.mark.parametrize("B,Sh,Sw", [(1, 640, 640), (2, 640, 320), (3, 320, 320)])
@@ -58,7 +58,7 @@ def test_forward_v8n_matches_oracle(model_n, B, Sh, Sw):
 def test_forward_v8l_small(model_n):
     from caesar_yolo_b200 import ops, weights as W
     w = W.make_random_weights('l', 5, seed=0)
-    dm = ops.DeviceModel(w)
+    dm = ops.DeviceModel(w, precision='bf16')
     x = _input(2, 320, 320, seed=7)
     heads = dm.forward_tensors(_to_nhwc4(x).to(DEV))
     torch.cuda.synchronize()
@@ -138,7 +138,7 @@ def test_forward_yolo11_matches_oracle(variant, B, Sh, Sw):
     depthwise-conv and attention kernels vs the oracle restatement (bf16-emulated and fp32)."""
     from caesar_yolo_b200 import ops, weights as W
     w = W.make_random_weights(variant, 5, seed=0)
-    dm = ops.DeviceModel(w)
+    dm = ops.DeviceModel(w, precision='bf16')
     x = _input(B, Sh, Sw, seed=B + Sh)
     heads = dm.forward_tensors(_to_nhwc4(x).to(DEV))
     torch.cuda.synchronize()
@@ -164,7 +164,7 @@ def test_yolo11_attention_kernels_agree(monkeypatch):
     rounding of P (fp32 softmax weights there, bf16 here)."""
     from caesar_yolo_b200 import ops, weights as W
     w = W.make_random_weights('11s', 5, seed=0)
-    dm = ops.DeviceModel(w)
+    dm = ops.DeviceModel(w, precision='bf16')
     x = _to_nhwc4(_input(2, 640, 320, seed=5)).to(DEV)
     a = [h.clone() for h in dm.forward_tensors(x)]
     torch.cuda.synchronize()

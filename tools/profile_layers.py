@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_device(dev)
     w = W.make_random_weights(a.variant, 5, seed=0, cls_bias=-16.0)
     m = ops.DeviceModel(w)
-    x = torch.rand((a.batch, a.imgsz, a.imgsz, 4), device=dev).to(torch.bfloat16)
+    x = torch.rand((a.batch, a.imgsz, a.imgsz, 4), device=dev).to(m.dtype)
     best = None
     for _ in range(a.reps):
         prof = m.profile(x)
