@@ -224,7 +224,7 @@ class Engine(object):
         """Compacts the per-tile record slots -> (packed uint8 tensor of n cy_det_record, n) in tile-id order.
         Synchronises (n is read on the host); the exchange path below does not use it."""
         packed = self._compact_local()
-        n = int(self._buf['total'].item())
+        n = int(self._buf['total'][0].item())
         return packed[:n * 32], n
 
     def _compact_local(self):
