@@ -44,6 +44,24 @@ class PPConfig(ctypes.Structure):
     ]
 
 
+class PPStage(ctypes.Structure):
+    """cy_pp_stage."""
+    _fields_ = [("type", ctypes.c_int32), ("chid", ctypes.c_int32), ("flag", ctypes.c_int32), ("n", ctypes.c_int32),
+                ("p", c_double * 8)]
+
+
+PP_MAX_STAGES = 16
+(PP_BKG_SUB, PP_CLIP_SHIFT, PP_SIGMA_CLIP, PP_CHAN_RESIZE, PP_ZSCALE, PP_CHAN3, PP_MINMAX, PP_ABS_MINMAX, PP_MAX_SCALE,
+ PP_ABS_MAX_SCALE, PP_CHAN_MAX_SCALE, PP_MIN_SHIFT, PP_SHIFT, PP_STANDARDIZE, PP_NEG_FIX, PP_LOG_STRETCH, PP_BORDER_MASK,
+ PP_HISTEQ) = range(1, 19)
+
+
+class PPChain(ctypes.Structure):
+    """cy_pp_chain: general stage list."""
+    _fields_ = [("nstages", ctypes.c_int32), ("out_f16", ctypes.c_int32), ("reject_all", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("st", PPStage * PP_MAX_STAGES)]
+
+
 class Letterbox(ctypes.Structure):
     """cy_letterbox."""
     _fields_ = [("gain", c_float), ("pad_x", c_float), ("pad_y", c_float), ("w0", ctypes.c_int32),
@@ -54,7 +72,8 @@ class Letterbox(ctypes.Structure):
 SYMBOLS = [
     "cy_last_error", "cy_version", "cy_device_check", "cy_memcpy_d2d", "cy_generate_tiles", "cy_tile_neighbors",
     "cy_letterbox_shape", "cy_preprocess_scratch_bytes", "cy_preprocess", "cy_letterbox_resize", "cy_conv_block_n", "cy_conv2d_nhwc",
-    "cy_conv_set_debug", "cy_conv_plan_info", "cy_sort_set_debug",
+    "cy_conv_set_debug", "cy_conv_plan_info", "cy_pp_chain_from_config", "cy_pp_chain_validate",
+    "cy_preprocess_chain_scratch_bytes", "cy_preprocess_chain",
     "cy_model_create", "cy_model_set_tensor", "cy_model_set_precision", "cy_model_plan_summary", "cy_letterbox_resize_fmt", "cy_model_finalize", "cy_model_forward", "cy_model_info",
     "cy_stem_conv_nhwc4", "cy_model_profile", "cy_model_conv_bytes", "cy_model_destroy", "cy_num_anchors", "cy_decode_pred", "cy_postprocess_scratch_bytes",
     "cy_postprocess", "cy_nms_scratch_bytes", "cy_nms_batched", "cy_merge_tile", "cy_make_records",
@@ -62,7 +81,7 @@ SYMBOLS = [
 ]
 
 lib.cy_last_error.restype = ctypes.c_char_p
-for _n in ("cy_preprocess_scratch_bytes", "cy_postprocess_scratch_bytes", "cy_nms_scratch_bytes",
+for _n in ("cy_preprocess_scratch_bytes", "cy_preprocess_chain_scratch_bytes", "cy_postprocess_scratch_bytes", "cy_nms_scratch_bytes",
            "cy_compact_scratch_bytes"):
     getattr(lib, _n).restype = ctypes.c_size_t
 

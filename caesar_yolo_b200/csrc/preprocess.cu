@@ -1,67 +1,81 @@
-// Preprocessing chain on the device: tile cut-out (FITS byte order, NaN -> 0), the run.py stage list of
+// Preprocessing chain on the device: tile cut-out (FITS byte order, NaN -> 0), the stage list of
 // caesar_yolo/preprocessing.py, and the ultralytics predictor preprocess (letterbox resize, channel flip, /255).
 //
-// Reference: BkgSubtractor (caesar_yolo/preprocessing.py:591-658), SigmaClipShifter (:664-717), SigmaClipper
-// (:723-771), ChanResizer (:1077-1133), ZScaleTransformer (:934-971), Chan3Trasformer (:1020-1072), HistEqualizer
-// (:977-1012), MinMaxNormalizer (:75-111), stage order scripts/run.py:272-293, Analyzer.predict front part
-// (caesar_yolo/evaluation.py:146-176); astropy sigma_clip / ZScaleInterval, skimage equalize_hist and the
-// ultralytics LetterBox semantics are restated in SURVEY.md App. A.1-A.4.
+// Reference: DataPreprocessor (caesar_yolo/preprocessing.py:47-67), BkgSubtractor (:591-658), SigmaClipShifter (:664-717),
+// SigmaClipper (:723-771), ChanResizer (:1077-1133), ZScaleTransformer (:934-971), Chan3Trasformer (:1020-1072),
+// HistEqualizer (:977-1012), MinMaxNormalizer (:75-111), AbsMinMaxNormalizer (:116-146), MaxScaler (:152-176),
+// AbsMaxScaler (:182-226), ChanMaxScaler (:232-288), MinShifter (:294-327), Shifter (:333-363), Standardizer (:369-402),
+// NegativeDataFixer (:408-440), LogStretcher (:480-538), BorderMasker (:544-586); stage order of scripts/run.py:272-293;
+// Analyzer.predict front part (caesar_yolo/evaluation.py:146-176); astropy sigma_clip / ZScaleInterval, skimage
+// equalize_hist and the ultralytics LetterBox semantics are restated in SURVEY.md App. A.1-A.4.
 //
-// Design.  Every stage of the chain is a monotone non-decreasing scalar map of the pixel value, and "0 means masked"
-// is sticky.  So each channel is represented by a short op list (scalars only) applied to the ORIGINAL pixel value
-// in fp64, never by a materialised fp64 image:
-//   kernel 1 (pp_sort_kernel):   one CTA per tile; cut-out + byte swap + NaN->0 into a native fp32 tile buffer, then
-//                                an in-L2 LSD radix sort of the non-masked pixels (order-preserving keys).
-//   kernel 2 (pp_chain_kernel):  one CTA per tile; runs the stage list.  Order statistics (medians, clip bounds,
-//                                histogram edges) are O(log n) lookups in the sorted array through the monotone op
-//                                list; means/standard deviations are two-pass fp64 block reductions (numpy's
-//                                definition) with warp-shuffle trees; zscale sorts its 1000 positional samples in
-//                                shared memory and does the iterative line fit in fp64.  Writes the chain output
-//                                (fp32 HWC) with one fused evaluation of the final op lists.
-//   kernel 3 (pp_resize_kernel): half-pixel bilinear letterbox resize (double-precision source coordinates like
-//                                cv2.resize on float64), pad 114, channel reversal, /255, bf16 NHWC(4) store.
+// Design.  Every stage is a monotone non-decreasing scalar map of the pixel value, and "0 means masked" is sticky.  So a
+// channel is a short op list (scalars only) applied to the ORIGINAL pixel value in fp64; no intermediate image exists.
+// What the stages need from the pixels are order statistics (medians of shrinking value intervals), ranks of thresholds,
+// moment sums over value intervals and min / max -- none of which needs the full sorted order (the first version sorted
+// every tile with a 4-pass radix sort).  Three kernels, the tile is read from HBM twice and nothing else of its size is
+// written except the 16-bit model input:
+//   pp_bucket_kernel: one CTA per tile.  A 1024-sample sort fixes a robust centre / scale of the tile; the pixels then
+//       stream through shared memory in chunks of 16384 (TMA 2-D boxes of the mosaic, byte swap + NaN -> 0 on the
+//       shared-memory read) and every chunk is counting-sorted into 1024 value bins (linear over +-8 robust sigma,
+//       logarithmic tails; optionally split in "inside / outside the central box"): chunk-local bucketed values,
+//       per-chunk bin offsets, and per-bin count / min / max / fp64 moment sums about a pivot.
+//   pp_chain_kernel: one CTA per tile, runs the stage list on the bin tables.  A rank query is a scan of the 1024 bin
+//       maxima + a count inside ONE bin; an order statistic is a gather + sort of ONE bin (cached); moment sums of a
+//       clipped interval come from the per-bin sums in closed form (the maps are affine + clamp) + exact sums over
+//       the few bins a boundary cuts.  zscale sorts its 1000 positional samples in shared memory and runs the <= 5 line
+//       fits in fp64; histogram equalisation bins whole value bins at once.  Exact zeros (= masked) are tracked as value
+//       intervals so masks match the reference bit for bit.
+//   pp_final_kernel: evaluates the three final channel maps per pixel and, fused, does the letterbox bilinear resize
+//       (cv2's double-precision source coordinates), pad 114, channel reversal, /255 into the bf16 / fp16 NHWC(4) model
+//       input.  The fp32 HWC chain image is an optional parity output.
 #include "common.h"
 #include "half16.cuh"
-#include <stddef.h>
-#include <cuda_bf16.h>
+#include "ptx.cuh"
+#include <cudaTypedefs.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace cy {
 
-static constexpr int kPPThreads = 512;    // two CTAs (tiles) per SM: the kernels are latency-bound, the second CTA
-                                          // fills the first one's barrier and dependent-load stalls
+static constexpr int kPPThreads = 512;     // chain kernel: latency-bound, several CTAs (tiles) per SM
 static constexpr int kPPWarps = kPPThreads / 32;
-static constexpr int kSortThreads = 1024;  // the sort is instruction-bound: one full-width CTA per SM
-static constexpr int kSortWarps = kSortThreads / 32;
+static constexpr int kBkThreads = 1024;    // bucket kernel: one full-width CTA per SM
+static constexpr int kNB = 1024;           // logical value bins
+static constexpr int kChunk = 16384;       // pixels per bucketing chunk (16 per thread)
+static constexpr int kGather = 4096;       // largest bin that is gathered + sorted in shared memory
 static constexpr int kMaxOps = 12;
 static constexpr int kMaxZero = 8;
 
-enum OpKind { OP_SUB = 1, OP_SHIFT = 2, OP_CLAMP = 3, OP_ZSCALE = 4, OP_HISTEQ = 5, OP_MINMAX = 6 };
+enum OpKind { OP_SUB = 1, OP_SHIFT = 2, OP_CLAMP = 3, OP_ZSCALE = 4, OP_HISTEQ = 5, OP_MINMAX = 6, OP_DIV = 7,
+              OP_STD = 8, OP_LOG = 9 };
 
 struct Chan {
     int nops;
     int hid;  // history id: channels with equal hid hold identical data
     int kind[kMaxOps];
     double p0[kMaxOps], p1[kMaxOps], p2[kMaxOps], p3[kMaxOps];
-    int nz;  // zero (masked) index ranges in the sorted array, sorted + merged
+    int nz;  // zero (masked) sets, sorted + merged: rank ranges [z0, z1) of the all-pixels view = value intervals
     int z0[kMaxZero], z1[kMaxZero];
+    float zx0[kMaxZero], zx1[kMaxZero];   // [zx0, zx1] of the ORIGINAL pixel value (closed)
 };
 
-// Compiled form of a channel's op list for the full passes: every op except HISTEQ is affine + clamp with a positive
-// slope, so the composition collapses to v = clamp(a*x + b, l, h) (one optional HISTEQ in the middle splits it into
-// A and B).  Differs from the sequential fp64 evaluation only by rounding (~1e-16 relative); exact-zero (= masked)
-// decisions never come from it: they are the index ranges Chan::z0/z1 of the sorted array, i.e. x intervals.
+// Compiled form of a channel's op list for the full passes: every op except HISTEQ / LOG is affine + clamp with a
+// positive slope, so the composition collapses to v = clamp(a*x + b, l, h) (one optional HISTEQ in the middle splits it
+// into A and B).  Differs from the sequential fp64 evaluation only by rounding (~1e-16 relative); exact-zero (= masked)
+// decisions never come from it: they are the value intervals of the channel.
 struct Comp {
     double a0, b0, l0, h0;
     double a1, b1, l1, h1;
     int has_he;
-    int ok;                      // 0: not representable (non-finite / non-positive slope) -> interpreter
+    int ok;                      // 0: not representable (non-finite / non-positive slope, LOG) -> interpreter
     int nzx;
-    float zx0[8], zx1[8];        // zero intervals [zx0, zx1] of the ORIGINAL pixel value
+    float zx0[kMaxZero], zx1[kMaxZero];
 };
 
-struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per chain: Chan3 channel 2)
+struct HistEq {  // skimage.exposure.equalize_hist tables (one histogram equalisation per chain)
     double edges[257];
     double cdf[256];
     double center[256];   // (edges[k] + edges[k+1]) / 2
@@ -69,35 +83,58 @@ struct HistEq {  // skimage.exposure.equalize_hist tables (one HistEqualizer per
     double inv_step;      // 255 / (center[255] - center[0]) (0 when the range is empty): bracket guess of the fast lookup
 };
 
-struct TileFinal;
+// Final state of a tile's chain: what pp_final_kernel needs to evaluate the three channel maps per pixel.
+struct TileFinal {
+    Comp cc[3];
+    Chan ch[3];       // op lists: interpreter fallback for maps the compiled form cannot represent (cc.ok == 0)
+    HistEq he;        // valid when use_he
+    int same01, same02, same12;
+    int use_he;
+    int status;       // 0 ok, < 0: tile rejected
+    int valid;        // maps are valid (a rejected tile whose chain ran still has its chain image, evaluation.py:171-176)
+    int pad_[2];
+};
+static_assert(sizeof(TileFinal) % 16 == 0 && offsetof(TileFinal, he) % 16 == 0 && sizeof(HistEq) % 16 == 0,
+              "TileFinal is copied in 16-byte words");
+
+struct TileHdr {      // written by pp_bucket_kernel
+    int n;            // live (non-masked) pixels
+    int n_sub[2];     // live pixels outside / inside the box (nsub == 2)
+    float c, inv_s;   // binning centre and 1 / scale
+    int pad_;
+    double pivot;     // pivot of the per-bin moment sums
+};
+
 struct PPParams {
-    cy_pp_config cfg;
+    cy_pp_chain chain;
     const uint32_t* img;
     long long row_stride;
     int big_endian;
     const int* x0;
     const int* y0;
     int B, Ty, Tx;
-    float* tilebuf;     // [B][N] native fp32, non-finite -> 0
-    uint32_t* keysA;    // [B][N] sorted live values (fp32 bits after the sort kernel)
-    uint32_t* keysB;    // [B][N] ping-pong
-    uint32_t* keysC;    // [B][N] sorted live values outside the bkg box (only when use_box_mask_in_bkg)
-    int* nlive;         // [B]
-    int* nbox;          // [B]
-    float* chain_out;   // [B][N][3] (optional parity output, written by pp_final_kernel)
-    int* status;        // [B]
-    struct TileFinal* fin;   // [B] final per-channel maps of every tile (chain kernel -> final kernel)
+    // bucketing geometry
+    int nsub;               // 1, or 2: every value bin split into (outside, inside) the central box
+    int bx0, bx1, by0, by1; // the box [by0,by1) x [bx0,bx1) (BkgSubtractor / AbsMaxScaler / BorderMasker geometry)
+    int border_mask;        // 1: pixels outside the box read as 0 (leading BorderMasker)
+    int rows_per_chunk, nchunks, nbs;   // nbs = kNB * nsub sub-bins
+    int use_tma, pw, npanels;           // TMA path: boxes of pw columns x rows_per_chunk rows
+    // scratch (per tile: index b)
+    TileHdr* hdr;
+    float* vals;            // [B][N] bucketed live values, chunk-major
+    unsigned short* off;    // [B][nchunks][nbs + 1] chunk-local start offsets of the sub-bins
+    int* cbase;             // [B][nchunks + 1] start of every chunk inside vals
+    int* cnt;               // [B][nbs]
+    float* bmin;            // [B][nbs]
+    float* bmax;            // [B][nbs]
+    double* m1;             // [B][nbs] sum (x - pivot)
+    double* m2;             // [B][nbs] sum (x - pivot)^2
+    TileFinal* fin;         // [B]
+    float* chain_out;       // [B][N][3] (optional parity output, written by pp_final_kernel)
+    int* status;            // [B]
 };
 
 // ------------------------------------------------------------------------------------------ small device helpers
-
-__device__ __forceinline__ uint32_t f2key(float f) {
-    const uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key2f(uint32_t k) {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -164,6 +201,318 @@ __device__ void block_minmax(double& mn, double& mx, double* red) {
     mx = red[97];
 }
 
+// ascending bitonic sort of n (power of two) floats in shared memory by NT threads; ends with a barrier
+template <int NT>
+__device__ void bitonic_sort_f(float* a, int n) {
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int e = threadIdx.x; e < n; e += NT) {
+                const int q = e ^ j;
+                if (q > e) {
+                    const float x = a[e], y = a[q];
+                    const bool asc = ((e & k) == 0);
+                    if (asc ? (x > y) : (x < y)) {
+                        a[e] = y;
+                        a[q] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// Value bin of pixel value x: linear bins of 1/48 robust sigma over [-8, 8) sigma around the tile's robust centre
+// (bins 128..895), 8 logarithmic bins per octave beyond (0..127 below, 896..1023 above).  Monotone non-decreasing in x.
+__device__ __forceinline__ int value_bin(float x, float c, float inv_s) {
+    const float t = (x - c) * inv_s;
+    if (t >= 8.f) {
+        const uint32_t k = (__float_as_uint(t * 0.125f) - 0x3F800000u) >> 20;
+        return 896 + (int)min(k, 127u);
+    }
+    if (t <= -8.f) {
+        const uint32_t k = (__float_as_uint(-t * 0.125f) - 0x3F800000u) >> 20;
+        return 127 - (int)min(k, 127u);
+    }
+    const int b = 128 + (int)floorf((t + 8.f) * 48.f);
+    return min(max(b, 128), 895);
+}
+
+__device__ __forceinline__ float decode_pixel(uint32_t raw, int big_endian) {
+    if (big_endian) raw = __byte_perm(raw, 0, 0x0123);
+    const float f = __uint_as_float(raw);
+    return isfinite(f) ? f : 0.0f;  // utils.py:219,394
+}
+__device__ __forceinline__ bool in_box(const PPParams& p, int y, int x) {
+    return y >= p.by0 && y < p.by1 && x >= p.bx0 && x < p.bx1;
+}
+// pixel (y, x) of tile b as the chain sees it
+__device__ __forceinline__ float load_pixel_yx(const PPParams& p, int b, int y, int x) {
+    const float f = decode_pixel(p.img[(long long)(p.y0[b] + y) * p.row_stride + p.x0[b] + x], p.big_endian);
+    return (p.border_mask && !in_box(p, y, x)) ? 0.0f : f;
+}
+__device__ __forceinline__ float load_pixel(const PPParams& p, int b, int idx) {
+    const int y = idx / p.Tx;
+    return load_pixel_yx(p, b, y, idx - y * p.Tx);
+}
+
+// ------------------------------------------------------------------------------------------ kernel 1: bucketing
+
+struct BkSmem {
+    uint32_t raw[kChunk];        // chunk as it lies in the mosaic (TMA destination; panels of pw columns)
+    float srt[kChunk];           // chunk in sub-bin order
+    int hist[2 * kNB];           // sub-bin counts of the chunk
+    int hoff[2 * kNB + 1];       // exclusive scan of hist
+    int tot[2 * kNB];
+    float bmin[2 * kNB], bmax[2 * kNB];
+    double m1[2 * kNB], m2[2 * kNB];
+    int wsum[32];
+    unsigned long long mbar;
+    float c, inv_s;
+    int nsamp;
+};
+
+__global__ void __launch_bounds__(kBkThreads, 1)
+pp_bucket_kernel(const __grid_constant__ PPParams p, const __grid_constant__ CUtensorMap tm) {
+    extern __shared__ __align__(128) unsigned char bk_smem_raw[];
+    BkSmem& sm = *reinterpret_cast<BkSmem*>(bk_smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Ty = p.Ty, Tx = p.Tx, N = Ty * Tx;
+    const int nbs = p.nbs, R = p.rows_per_chunk;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(&sm.mbar);
+    const int tx0 = p.x0[b], ty0 = p.y0[b];
+
+    auto issue_tma = [&](int ch) {   // one elected thread: boxes of the chunk's rows
+        const uint32_t bytes = (uint32_t)R * Tx * 4u;
+        mbar_arrive_expect_tx(mbar, bytes);
+        for (int q = 0; q < p.npanels; ++q)
+            tma_load_2d(&sm.raw[q * R * p.pw], &tm, mbar, tx0 + q * p.pw, ty0 + ch * R);
+    };
+    const int full_chunks = p.use_tma ? Ty / R : 0;     // chunks loaded by TMA (a partial last chunk is read directly)
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < nbs; i += kBkThreads) {
+        sm.hist[i] = 0;
+        sm.tot[i] = 0;
+        sm.bmin[i] = INFINITY;
+        sm.bmax[i] = -INFINITY;
+        sm.m1[i] = 0.0;
+        sm.m2[i] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0 && full_chunks > 0) issue_tma(0);      // overlaps the sample sort below
+
+    // ---- robust centre / scale from <= 1024 positional samples (sorted in srt[0..1024))
+    {
+        const int stride = max(1, N / 1024);
+        const int ns = min(1024, (N + stride - 1) / stride);
+        float v = INFINITY;
+        if (tid < ns) {
+            v = load_pixel(p, b, tid * stride);
+            if (v == 0.0f) v = INFINITY;
+        }
+        sm.srt[tid] = v;
+        const int live = __syncthreads_count(v != INFINITY);
+        bitonic_sort_f<kBkThreads>(sm.srt, 1024);
+        if (tid == 0) {
+            float c = 0.f, s = 0.f;
+            if (live > 0) {
+                c = sm.srt[live / 2];
+                s = 0.5f * (sm.srt[min(live - 1, (int)(0.84f * live))] - sm.srt[(int)(0.16f * live)]);
+                if (!(s > 0.f)) s = (sm.srt[live - 1] - sm.srt[0]) * 0.0625f;
+            }
+            if (!(s > 0.f) || !isfinite(s)) s = fmaxf(fabsf(c) * 1e-3f, 1e-30f);
+            float inv = 1.0f / s;
+            if (!isfinite(inv) || !(inv > 0.f)) inv = 1.0f;
+            sm.c = c;
+            sm.inv_s = inv;
+        }
+        __syncthreads();
+    }
+    const float bc = sm.c, binv = sm.inv_s;
+    const double pivot = (double)bc;
+
+    int gbase = 0;               // live pixels written so far
+    int nsub0 = 0, nsub1 = 0;
+    float* vals = p.vals + (long long)b * N;
+    unsigned short* off = p.off + (long long)b * p.nchunks * (nbs + 1);
+    int* cbase = p.cbase + (long long)b * (p.nchunks + 1);
+    uint32_t phase = 0;
+    for (int ch = 0; ch < p.nchunks; ++ch) {
+        const int r0 = ch * R, rows = min(R, Ty - r0), len = rows * Tx;
+        const bool via_tma = ch < full_chunks;
+        if (via_tma) {
+            mbar_wait(mbar, phase);
+            phase ^= 1;
+        } else {
+            // direct coalesced reads of the chunk's rows into the same buffer (panel layout with pw = Tx)
+            for (int i = tid; i < len; i += kBkThreads) {
+                const int y = i / Tx, x = i - y * Tx;
+                sm.raw[i] = p.img[(long long)(ty0 + r0 + y) * p.row_stride + tx0 + x];
+            }
+            __syncthreads();
+        }
+        // ---- registers <- shared memory (byte swap, NaN -> 0), sub-bin of every live pixel
+        const int pw = via_tma ? p.pw : Tx, rpw = R * pw;
+        float xv[kChunk / kBkThreads];
+        int sb[kChunk / kBkThreads];
+#pragma unroll
+        for (int k = 0; k < kChunk / kBkThreads; ++k) {
+            const int i = tid + k * kBkThreads;
+            sb[k] = -1;
+            xv[k] = 0.f;
+            if (i < len) {
+                int y, x;
+                if (via_tma) {
+                    const int q = i / rpw, rem = i - q * rpw;
+                    y = rem / pw;
+                    x = q * pw + (rem - y * pw);
+                } else {
+                    y = i / Tx;
+                    x = i - y * Tx;
+                }
+                float f = decode_pixel(sm.raw[i], p.big_endian);
+                const bool inb = in_box(p, r0 + y, x);
+                if (p.border_mask && !inb) f = 0.0f;
+                if (f != 0.0f) {
+                    xv[k] = f;
+                    const int vb = value_bin(f, bc, binv);
+                    sb[k] = p.nsub == 2 ? 2 * vb + (inb ? 1 : 0) : vb;
+                }
+            }
+        }
+        __syncthreads();                                   // every thread has its pixels: the raw buffer is free
+        if (tid == 0 && ch + 1 < full_chunks) {
+            fence_proxy_async_smem();
+            issue_tma(ch + 1);                             // the next chunk lands while this one is bucketed
+        }
+        // ---- slot inside the sub-bin (shared-memory atomics), then chunk-local counting sort
+#pragma unroll
+        for (int k = 0; k < kChunk / kBkThreads; ++k)
+            if (sb[k] >= 0) sb[k] |= atomicAdd(&sm.hist[sb[k]], 1) << 12;     // nbs <= 2048 < 2^12, slot < 2^15
+        __syncthreads();
+        {   // exclusive scan of hist[0..nbs) -> hoff: thread t owns entries [t*e, (t+1)*e), e = nbs / 1024
+            const int e = nbs / kBkThreads;
+            int loc[2], s = 0;
+            for (int q = 0; q < e; ++q) {
+                loc[q] = sm.hist[tid * e + q];
+                s += loc[q];
+            }
+            int inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            if (lane == 31) sm.wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                int w = sm.wsum[lane], wi = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (lane >= o) wi += y;
+                }
+                sm.wsum[lane] = wi - w;
+            }
+            __syncthreads();
+            int run = sm.wsum[warp] + inc - s;
+            for (int q = 0; q < e; ++q) {
+                sm.hoff[tid * e + q] = run;
+                run += loc[q];
+            }
+            if (tid == kBkThreads - 1) sm.hoff[nbs] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kChunk / kBkThreads; ++k)
+            if (sb[k] >= 0) sm.srt[sm.hoff[sb[k] & 0xfff] + (sb[k] >> 12)] = xv[k];
+        __syncthreads();
+        const int nlive = sm.hoff[nbs];
+        // ---- per sub-bin statistics of the chunk (thread per sub-bin, no atomics) + write-out
+        for (int j = tid; j < nbs; j += kBkThreads) {
+            const int s = sm.hoff[j], e = sm.hoff[j + 1];
+            if (e > s) {
+                float mn = sm.bmin[j], mx = sm.bmax[j];
+                double a1 = 0.0, a2 = 0.0;
+                for (int i = s; i < e; ++i) {
+                    const float x = sm.srt[i];
+                    mn = fminf(mn, x);
+                    mx = fmaxf(mx, x);
+                    const double d = (double)x - pivot;
+                    a1 += d;
+                    a2 = fma(d, d, a2);
+                }
+                sm.bmin[j] = mn;
+                sm.bmax[j] = mx;
+                sm.m1[j] += a1;
+                sm.m2[j] += a2;
+                sm.tot[j] += e - s;
+            }
+        }
+        for (int i = tid; i < nlive; i += kBkThreads) vals[gbase + i] = sm.srt[i];
+        unsigned short* offc = off + (long long)ch * (nbs + 1);
+        for (int j = tid; j <= nbs; j += kBkThreads) offc[j] = (unsigned short)sm.hoff[j];
+        if (tid == 0) cbase[ch] = gbase;
+        gbase += nlive;
+        __syncthreads();
+        for (int i = tid; i < nbs; i += kBkThreads) sm.hist[i] = 0;
+        __syncthreads();
+    }
+    // ---- per-tile tables
+    {
+        int* cnt = p.cnt + (long long)b * nbs;
+        float* bmin = p.bmin + (long long)b * nbs;
+        float* bmax = p.bmax + (long long)b * nbs;
+        double* m1 = p.m1 + (long long)b * nbs;
+        double* m2 = p.m2 + (long long)b * nbs;
+        int s0 = 0, s1 = 0;
+        for (int j = tid; j < nbs; j += kBkThreads) {
+            cnt[j] = sm.tot[j];
+            bmin[j] = sm.bmin[j];
+            bmax[j] = sm.bmax[j];
+            m1[j] = sm.m1[j];
+            m2[j] = sm.m2[j];
+            if (p.nsub == 2) {
+                if (j & 1) s1 += sm.tot[j];
+                else s0 += sm.tot[j];
+            }
+        }
+        if (p.nsub == 2) {
+            // block totals of the two subsets
+            s0 = __reduce_add_sync(0xffffffffu, s0);
+            s1 = __reduce_add_sync(0xffffffffu, s1);
+            __syncthreads();
+            if (lane == 0) {
+                sm.wsum[warp] = s0;
+                sm.hist[warp] = s1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 0; w < 32; ++w) {
+                    nsub0 += sm.wsum[w];
+                    nsub1 += sm.hist[w];
+                }
+            }
+        }
+        if (tid == 0) {
+            cbase[p.nchunks] = gbase;
+            TileHdr h;
+            h.n = gbase;
+            h.n_sub[0] = nsub0;
+            h.n_sub[1] = nsub1;
+            h.c = bc;
+            h.inv_s = binv;
+            h.pad_ = 0;
+            h.pivot = pivot;
+            p.hdr[b] = h;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ op lists
+
 // np.interp(v, centers, cdf) with centers = (edges[:-1] + edges[1:]) / 2 (skimage equalize_hist, App. A.3)
 __device__ double histeq_interp(const HistEq& h, double v) {
     const double c0 = (h.edges[0] + h.edges[1]) / 2.0, c255 = (h.edges[255] + h.edges[256]) / 2.0;
@@ -182,7 +531,7 @@ __device__ double histeq_interp(const HistEq& h, double v) {
 
 // Apply the first `nops` ops of channel c to the original pixel value x (fp64, reference operation order, no FMA
 // contraction).  STICKY: a value that is (or becomes) exactly 0 stays 0 — the reference's `out[~cond] = 0`.
-// !STICKY: the plain monotone composition (used to locate index ranges among live elements).
+// !STICKY: the plain monotone composition (used to locate ranks among live elements).
 template <bool STICKY>
 __device__ double eval_ops(const Chan& c, int nops, const HistEq& he, double v) {
     for (int k = 0; k < nops; ++k) {
@@ -206,22 +555,16 @@ __device__ double eval_ops(const Chan& c, int nops, const HistEq& he, double v) 
             case OP_MINMAX:
                 v = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(v, c.p0[k]), c.p1[k]), c.p2[k]), c.p3[k]);
                 break;
+            case OP_DIV: v = __ddiv_rn(v, c.p0[k]); break;
+            case OP_STD: v = __ddiv_rn(__dsub_rn(v, c.p0[k]), c.p1[k]); break;
+            case OP_LOG:   // LogStretcher with minmaxnorm: log10 of positive pixels, others at the smallest log
+                v = v > 0.0 ? log10(v) : c.p0[k];
+                v = __ddiv_rn(__dsub_rn(v, c.p1[k]), c.p2[k]);
+                if (c.p3[k] != 0.0 && v < 0.0) v = 0.0;
+                break;
         }
     }
     return v;
-}
-
-// first index i in [a,b) with f*(S[i]) >= t (STRICT: > t); b if none.  Executed redundantly by every thread.
-template <bool STRICT>
-__device__ int lower_index(const Chan& c, int nops, const HistEq& he, const float* S, int a, int b, double t) {
-    int lo = a, hi = b;
-    while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        const double v = eval_ops<false>(c, nops, he, (double)S[m]);
-        const bool ok = STRICT ? (v > t) : (v >= t);
-        if (ok) hi = m; else lo = m + 1;
-    }
-    return lo;
 }
 
 // np.interp on the uniform histogram centres with an O(1) bracket (same interpolation arithmetic as histeq_interp).
@@ -236,7 +579,7 @@ __device__ __forceinline__ double histeq_interp_fast(const HistEq& h, double v) 
     return __dadd_rn(__dmul_rn(h.slope[lo], __dsub_rn(v, h.center[lo])), h.cdf[lo]);
 }
 
-// Value of a NON-masked pixel through the compiled op list (callers decide masking by index / x interval).
+// Value of a NON-masked pixel through the compiled op list (callers decide masking by value interval).
 __device__ __forceinline__ double eval_fast(const Comp& cc, const Chan& c, const HistEq& he, double x) {
     if (!cc.ok) return eval_ops<true>(c, c.nops, he, x);
     double v = fmin(fmax(fma(cc.a0, x, cc.b0), cc.l0), cc.h0);
@@ -246,19 +589,15 @@ __device__ __forceinline__ double eval_fast(const Comp& cc, const Chan& c, const
     }
     return v;
 }
-__device__ __forceinline__ bool in_zero_x(const Comp& cc, float x) {
-    bool z = (x == 0.0f);
-    for (int k = 0; k < cc.nzx; ++k) z = z || (x >= cc.zx0[k] && x <= cc.zx1[k]);
-    return z;
-}
-__device__ __forceinline__ bool in_zero_idx(const Chan& c, int i) {
-    bool z = false;
-    for (int k = 0; k < c.nz; ++k) z = z || (i >= c.z0[k] && i < c.z1[k]);
-    return z;
+template <class Z>
+__device__ __forceinline__ bool in_zero_x(const Z& z, int nz, float x) {
+    bool m = false;
+    for (int k = 0; k < nz; ++k) m = m || (x >= z.zx0[k] && x <= z.zx1[k]);
+    return m;
 }
 
-// (thread 0) rebuild the compiled form of channel c after its op list / zero ranges changed
-__device__ void compile_chan(const Chan& c, Comp& cc, const float* S) {
+// (thread 0) rebuild the compiled form of channel c after its op list / zero sets changed
+__device__ void compile_chan(const Chan& c, Comp& cc) {
     double a = 1.0, b = 0.0, l = -INFINITY, h = INFINITY;
     cc.has_he = 0;
     cc.ok = 1;
@@ -291,6 +630,18 @@ __device__ void compile_chan(const Chan& c, Comp& cc, const float* S) {
                 h = (h - c.p0[k]) * sc + c.p3[k];
                 break;
             }
+            case OP_DIV: {
+                const double sc = 1.0 / c.p0[k];
+                if (!(sc > 0.0) || !isfinite(sc)) cc.ok = 0;
+                a *= sc; b *= sc; l *= sc; h *= sc;
+                break;
+            }
+            case OP_STD: {
+                const double sc = 1.0 / c.p1[k];
+                if (!(sc > 0.0) || !isfinite(sc)) cc.ok = 0;
+                a *= sc; b = (b - c.p0[k]) * sc; l = (l - c.p0[k]) * sc; h = (h - c.p0[k]) * sc;
+                break;
+            }
             case OP_HISTEQ:
                 if (cc.has_he) cc.ok = 0;
                 cc.a0 = a; cc.b0 = b; cc.l0 = l; cc.h0 = h;
@@ -309,33 +660,35 @@ __device__ void compile_chan(const Chan& c, Comp& cc, const float* S) {
     if (!isfinite(a) || !isfinite(b) || !isfinite(cc.a0) || !isfinite(cc.b0) || isnan(l) || isnan(h)) cc.ok = 0;
     cc.nzx = c.nz;
     for (int k = 0; k < c.nz; ++k) {
-        cc.zx0[k] = S[c.z0[k]];
-        cc.zx1[k] = S[c.z1[k] - 1];
+        cc.zx0[k] = c.zx0[k];
+        cc.zx1[k] = c.zx1[k];
     }
 }
 
-__device__ void add_zero_range(Chan& c, int h0, int h1) {  // single thread
+// (single thread) add the zero set [h0, h1) = [x0, x1] to channel c: insertion sort + merge of ranks and values
+__device__ void add_zero_range(Chan& c, int h0, int h1, float x0, float x1) {
     if (h1 <= h0) return;
     int n = c.nz;
     if (n < kMaxZero) {
-        c.z0[n] = h0;
-        c.z1[n] = h1;
+        c.z0[n] = h0; c.z1[n] = h1; c.zx0[n] = x0; c.zx1[n] = x1;
         ++n;
+    } else {  // table full: widen the last set (never expected: every stage adds at most one contiguous set)
+        if (h1 > c.z1[n - 1]) { c.z1[n - 1] = h1; c.zx1[n - 1] = x1; }
+        if (h0 < c.z0[n - 1]) { c.z0[n - 1] = h0; c.zx0[n - 1] = x0; }
     }
-    // insertion sort + merge
     for (int i = n - 1; i > 0 && c.z0[i] < c.z0[i - 1]; --i) {
         const int t0 = c.z0[i], t1 = c.z1[i];
-        c.z0[i] = c.z0[i - 1]; c.z1[i] = c.z1[i - 1];
-        c.z0[i - 1] = t0; c.z1[i - 1] = t1;
+        const float u0 = c.zx0[i], u1 = c.zx1[i];
+        c.z0[i] = c.z0[i - 1]; c.z1[i] = c.z1[i - 1]; c.zx0[i] = c.zx0[i - 1]; c.zx1[i] = c.zx1[i - 1];
+        c.z0[i - 1] = t0; c.z1[i - 1] = t1; c.zx0[i - 1] = u0; c.zx1[i - 1] = u1;
     }
     int m = 0;
     for (int i = 1; i < n; ++i) {
         if (c.z0[i] <= c.z1[m]) {
-            if (c.z1[i] > c.z1[m]) c.z1[m] = c.z1[i];
+            if (c.z1[i] > c.z1[m]) { c.z1[m] = c.z1[i]; c.zx1[m] = c.zx1[i]; }
         } else {
             ++m;
-            c.z0[m] = c.z0[i];
-            c.z1[m] = c.z1[i];
+            c.z0[m] = c.z0[i]; c.z1[m] = c.z1[i]; c.zx0[m] = c.zx0[i]; c.zx1[m] = c.zx1[i];
         }
     }
     c.nz = n ? m + 1 : 0;
@@ -348,7 +701,7 @@ __device__ int live_count(const Chan& c, int a, int b) {
     }
     return n;
 }
-// index of the k-th (0-based) live element at or after a
+// rank of the k-th (0-based) live element at or after rank a
 __device__ int kth_live(const Chan& c, int a, int k) {
     int pos = a;
     for (int i = 0; i < c.nz; ++i) {
@@ -365,9 +718,12 @@ __device__ int kth_live(const Chan& c, int a, int k) {
     return pos + k;
 }
 
+// ------------------------------------------------------------------------------------------ bin-table view of a tile
+
 struct Shared {
     Chan ch[3];
     Comp cc[3];
+    Chan tmp;                // channel with its zero sets re-ranked for a subset view
     HistEq he;
     double red[3 * 32 + 4];
     double zs[1024];         // zscale samples / flat residuals
@@ -377,133 +733,306 @@ struct Shared {
     int next_hid;
     int fail;                // tile status
     int sidx;                // block-wide search scratch
+    int he_used;             // a histogram equalisation owns `he`
+    // active view of the bucketed tile: -1 all pixels, 0 / 1 = outside / inside the box
+    int view, n;
+    int prefix[kNB + 1];     // rank of the first element of every logical bin
+    float bmin[kNB], bmax[kNB];
+    float gath[kGather];     // sorted elements of bin gath_bin
+    int gath_bin, gath_n;
+    int plist[kNB], nplist;  // bins a query has to walk element by element
+    int wtmp[32];
+    float fres[4];
 };
 
-// Final state of a tile's chain: what pp_final_kernel needs to evaluate the three channel maps per pixel.
-struct TileFinal {
-    Comp cc[3];
-    Chan ch[3];       // op lists: interpreter fallback for maps the compiled form cannot represent (cc.ok == 0)
-    HistEq he;        // valid when use_he
-    int same01, same02, same12;
-    int use_he;
-    int status;       // 0 ok, < 0: tile rejected (model input zero-filled)
-    int pad_[3];
+struct TileView {            // global tables of one tile
+    const float* vals;
+    const unsigned short* off;
+    const int* cbase;
+    const int* cnt;
+    const float* bmin;
+    const float* bmax;
+    const double* m1;
+    const double* m2;
+    int nchunks, nbs, nsub;
+    double pivot;
 };
-static_assert(sizeof(TileFinal) % 16 == 0 && offsetof(TileFinal, he) % 16 == 0 && sizeof(HistEq) % 16 == 0,
-              "TileFinal is copied in 16-byte words");
-
-// Block-cooperative version of lower_index (all threads call it with the same arguments): every round probes
-// kPPThreads equally spaced elements at once, so 2^18 elements need two rounds of one load each instead of 18
-// dependent loads per thread.
-template <bool STRICT>
-__device__ int lower_index_coop(Shared& sh, const Chan& c, int nops, const float* S, int a, int b, double t) {
-    int lo = a, hi = b;
-    while (hi > lo) {
-        const int len = hi - lo;
-        const int step = (len + kPPThreads - 1) / kPPThreads;
-        const long long mi = (long long)lo + (long long)threadIdx.x * step;
-        bool ok = true;  // probes at or beyond hi count as "true"
-        if (mi < hi) {
-            const double v = eval_ops<false>(c, nops, sh.he, (double)S[mi]);
-            ok = STRICT ? (v > t) : (v >= t);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) sh.sidx = kPPThreads;
-        __syncthreads();
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        if ((threadIdx.x & 31) == 0 && bal) atomicMin(&sh.sidx, (int)(threadIdx.x & ~31u) + __ffs(bal) - 1);
-        __syncthreads();
-        const int T = sh.sidx;  // first probing thread whose predicate holds (kPPThreads: none)
-        const long long mT = (long long)lo + (long long)T * step;
-        const int nhi = (int)(mT < hi ? mT : hi);
-        const int nlo = T == 0 ? lo : (int)(mT - step + 1 < hi ? mT - step + 1 : hi);
-        if (step == 1 || T == 0) return nhi;
-        lo = nlo;
-        hi = nhi;
+__device__ __forceinline__ TileView tile_view(const PPParams& p, int b) {
+    TileView v;
+    const long long N = (long long)p.Ty * p.Tx;
+    v.vals = p.vals + b * N;
+    v.off = p.off + (long long)b * p.nchunks * (p.nbs + 1);
+    v.cbase = p.cbase + (long long)b * (p.nchunks + 1);
+    v.cnt = p.cnt + (long long)b * p.nbs;
+    v.bmin = p.bmin + (long long)b * p.nbs;
+    v.bmax = p.bmax + (long long)b * p.nbs;
+    v.m1 = p.m1 + (long long)b * p.nbs;
+    v.m2 = p.m2 + (long long)b * p.nbs;
+    v.nchunks = p.nchunks;
+    v.nbs = p.nbs;
+    v.nsub = p.nsub;
+    v.pivot = p.hdr[b].pivot;
+    return v;
+}
+// sub-bin range [s0, s1) of logical bin j in the active view
+__device__ __forceinline__ void sub_range(const TileView& tv, int view, int j, int& s0, int& s1) {
+    if (tv.nsub == 1) { s0 = j; s1 = j + 1; }
+    else if (view < 0) { s0 = 2 * j; s1 = 2 * j + 2; }
+    else { s0 = 2 * j + view; s1 = s0 + 1; }
+}
+// Visits every element of logical bin j: warp w walks chunks w, w + 16, ...; lanes stride over the chunk's segment.
+template <class F>
+__device__ __forceinline__ void for_bin_elements(const TileView& tv, int view, int j, F f) {
+    int s0, s1;
+    sub_range(tv, view, j, s0, s1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < tv.nchunks; c += kPPWarps) {
+        const unsigned short* oc = tv.off + (long long)c * (tv.nbs + 1);
+        const int base = tv.cbase[c];
+        const int a = base + oc[s0], e = base + oc[s1];
+        for (int i = a + lane; i < e; i += 32) f(tv.vals[i]);
     }
-    return lo;
 }
 
-// Pivoted moment sums of the live values f(S[i]), i in [a,b) U [a2,b2):  n, sum(v-p), sum((v-p)^2)   (fp64).
-// Values come from the compiled op list; masked elements are the zero index ranges of the channel, so each input
-// range is cut into its live segments once and the element loop carries no mask test.
-__device__ void range_sums(const Chan& c, const Comp& cc, const HistEq& he, const float* S, int a, int b, int a2,
-                           int b2, double p, double* red, double& s0, double& s1, double& s2) {
-    double n = 0.0, u = 0.0, q = 0.0;
-    const bool simple = cc.ok && !cc.has_he;
-    const double bp = cc.b0 - p, lp = cc.l0 - p, hp = cc.h0 - p;   // clamp(a*x + b, l, h) - p
-    for (int part = 0; part < 2; ++part) {
-        int pos = part ? a2 : a;
-        const int end = part ? b2 : b;
-        int zi = 0;
-        while (pos < end) {
-            // next live segment [pos, seg_end)
-            while (zi < c.nz && c.z1[zi] <= pos) ++zi;
-            if (zi < c.nz && c.z0[zi] <= pos) {
-                pos = c.z1[zi];
-                continue;
-            }
-            const int seg_end = (zi < c.nz && c.z0[zi] < end) ? c.z0[zi] : end;
-            if (threadIdx.x == 0) n += (double)(seg_end - pos);
-            if (simple) {
-                // two independent accumulator pairs: the DADD / DFMA dependency chains were the stall of this loop
-                double u1 = 0.0, q1 = 0.0;
-                int i = pos + threadIdx.x;
-                for (; i + kPPThreads < seg_end; i += 2 * kPPThreads) {
-                    const float x0 = S[i], x1 = S[i + kPPThreads];
-                    const double d0 = fmin(fmax(fma(cc.a0, (double)x0, bp), lp), hp);
-                    const double d1 = fmin(fmax(fma(cc.a0, (double)x1, bp), lp), hp);
-                    u += d0;
-                    q = fma(d0, d0, q);
-                    u1 += d1;
-                    q1 = fma(d1, d1, q1);
-                }
-                if (i < seg_end) {
-                    const double d = fmin(fmax(fma(cc.a0, (double)S[i], bp), lp), hp);
-                    u += d;
-                    q = fma(d, d, q);
-                }
-                u += u1;
-                q += q1;
-            } else {
-#pragma unroll 2
-                for (int i = pos + threadIdx.x; i < seg_end; i += kPPThreads) {
-                    const double d = eval_fast(cc, c, he, (double)S[i]) - p;
-                    u += d;
-                    q = fma(d, d, q);
-                }
-            }
-            pos = seg_end;
+// (all threads) make `view` the active view: logical-bin counts -> prefix ranks, minima / maxima
+__device__ void set_view(Shared& sh, const TileView& tv, int view) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    __syncthreads();
+    int c2[2];
+    for (int q = 0; q < 2; ++q) {    // thread t owns logical bins 2t, 2t + 1
+        const int j = 2 * t + q;
+        int s0, s1;
+        sub_range(tv, view, j, s0, s1);
+        int cn = 0;
+        float mn = INFINITY, mx = -INFINITY;
+        for (int s = s0; s < s1; ++s) {
+            cn += tv.cnt[s];
+            mn = fminf(mn, tv.bmin[s]);
+            mx = fmaxf(mx, tv.bmax[s]);
+        }
+        c2[q] = cn;
+        sh.bmin[j] = mn;
+        sh.bmax[j] = mx;
+    }
+    const int s = c2[0] + c2[1];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) sh.wtmp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < kPPWarps ? sh.wtmp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        if (lane < kPPWarps) sh.wtmp[lane] = wi - w;
+    }
+    __syncthreads();
+    const int run = sh.wtmp[warp] + inc - s;
+    sh.prefix[2 * t] = run;
+    sh.prefix[2 * t + 1] = run + c2[0];
+    if (t == kPPThreads - 1) {
+        sh.prefix[kNB] = run + s;
+        sh.n = run + s;
+        sh.view = view;
+        sh.gath_bin = -1;
+    }
+    __syncthreads();
+}
+
+// Value at rank r of the active view (exact order statistic): the elements of r's bin are gathered and sorted in shared
+// memory (kept until another bin is asked for); bins larger than kGather take a 4-pass radix selection instead.
+__device__ float value_at(Shared& sh, const TileView& tv, int r) {
+    // bin of rank r: largest j with prefix[j] <= r (uniform binary search in shared memory)
+    int lo = 0, hi = kNB;
+    while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (sh.prefix[m] <= r) lo = m; else hi = m;
+    }
+    const int j = lo, k = r - sh.prefix[j], m = sh.prefix[j + 1] - sh.prefix[j];
+    __syncthreads();
+    if (sh.gath_bin == j) return sh.gath[k];
+    if (m <= kGather) {
+        if (threadIdx.x == 0) sh.gath_n = 0;
+        int np2 = 32;
+        while (np2 < m) np2 <<= 1;
+        for (int i = threadIdx.x; i < np2; i += kPPThreads) sh.gath[i] = INFINITY;
+        __syncthreads();
+        for_bin_elements(tv, sh.view, j, [&](float x) { sh.gath[atomicAdd(&sh.gath_n, 1)] = x; });
+        __syncthreads();
+        bitonic_sort_f<kPPThreads>(sh.gath, np2);
+        if (threadIdx.x == 0) sh.gath_bin = j;
+        __syncthreads();
+        return sh.gath[k];
+    }
+    // radix selection on the order-preserving key, most significant byte first
+    uint32_t prefix_key = 0, mask = 0;
+    int kk = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.hist[i] = 0;
+        __syncthreads();
+        for_bin_elements(tv, sh.view, j, [&](float x) {
+            const uint32_t u = __float_as_uint(x);
+            const uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            if ((key & mask) == prefix_key) atomicAdd(&sh.hist[(key >> shift) & 255u], 1);
+        });
+        __syncthreads();
+        int d = 0, acc = 0;
+        for (; d < 256; ++d) {      // every thread walks the same 256 counters
+            const int h = sh.hist[d];
+            if (kk < acc + h) break;
+            acc += h;
+        }
+        kk -= acc;
+        prefix_key |= (uint32_t)d << shift;
+        mask |= 0xffu << shift;
+        __syncthreads();
+    }
+    const uint32_t u = (prefix_key & 0x80000000u) ? (prefix_key & 0x7fffffffu) : ~prefix_key;
+    return __uint_as_float(u);
+}
+
+// First rank r in [a, b) of the active view with P(x) true, P(x) = f(x) >= t (STRICT: f(x) > t), f = the first nops ops
+// of c (plain composition, monotone); b if none.  *xbelow / *xabove: largest pixel value with !P / smallest with P over
+// the whole view (-inf / +inf if none) -- the value form of the rank boundary.
+template <bool STRICT>
+__device__ int lower_index(Shared& sh, const TileView& tv, const Chan& c, int nops, int a, int b, double t,
+                           float* xbelow, float* xabove) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.sidx = kNB;
+    __syncthreads();
+    for (int j = threadIdx.x; j < kNB; j += kPPThreads) {
+        if (sh.prefix[j + 1] > sh.prefix[j]) {
+            const double v = eval_ops<false>(c, nops, sh.he, (double)sh.bmax[j]);
+            if (STRICT ? (v > t) : (v >= t)) atomicMin(&sh.sidx, j);
         }
     }
-    block_sum3(n, u, q, red);
+    __syncthreads();
+    const int jb = sh.sidx;
+    int r;
+    float xb = -INFINITY, xa = INFINITY;
+    if (jb == kNB) {
+        r = sh.n;
+    } else {
+        int cntb = 0;
+        float mxb = -INFINITY, mna = INFINITY;
+        for_bin_elements(tv, sh.view, jb, [&](float x) {
+            const double v = eval_ops<false>(c, nops, sh.he, (double)x);
+            if (STRICT ? (v > t) : (v >= t)) mna = fminf(mna, x);
+            else { ++cntb; mxb = fmaxf(mxb, x); }
+        });
+        double d0 = (double)cntb, d1 = 0.0, d2 = 0.0, mn = (double)mna, mx = (double)mxb;
+        block_sum3(d0, d1, d2, sh.red);
+        block_minmax(mn, mx, sh.red);
+        r = sh.prefix[jb] + (int)d0;
+        xb = (float)mx;
+        xa = (float)mn;
+    }
+    if (xb == -INFINITY) {   // nothing below inside bin jb: the largest element of the previous non-empty bin
+        for (int j = min(jb, kNB) - 1; j >= 0; --j)
+            if (sh.prefix[j + 1] > sh.prefix[j]) {
+                xb = sh.bmax[j];
+                break;
+            }
+    }
+    if (xbelow) *xbelow = xb;
+    if (xabove) *xabove = xa;
+    return min(max(r, a), b);
+}
+
+// Moment sums of the live values f(x) over the pixels with xa <= x <= xb of the active view:  n, sum(v-p), sum((v-p)^2)
+// in fp64.  Bins entirely inside the interval whose map is affine (or constant) over the bin come from the per-bin
+// sums in closed form; bins cut by an interval end, a masked interval or a clamp bound are walked element by element.
+__device__ void range_sums(Shared& sh, const TileView& tv, const Chan& c, const Comp& cc, float xa, float xb, double pv,
+                           double& s0, double& s1, double& s2) {
+    double n = 0.0, u = 0.0, q = 0.0;
+    const bool simple = cc.ok && !cc.has_he;
+    __syncthreads();
+    if (threadIdx.x == 0) sh.nplist = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < kNB; j += kPPThreads) {
+        const int cn = sh.prefix[j + 1] - sh.prefix[j];
+        if (cn == 0) continue;
+        const float lo = sh.bmin[j], hi = sh.bmax[j];
+        if (hi < xa || lo > xb) continue;
+        bool partial = !(lo >= xa && hi <= xb) || !simple;
+        bool masked = false;
+        for (int k = 0; k < c.nz; ++k) {
+            if (hi < c.zx0[k] || lo > c.zx1[k]) continue;
+            if (lo >= c.zx0[k] && hi <= c.zx1[k]) masked = true; else partial = true;
+        }
+        if (masked) continue;
+        if (!partial) {
+            const double flo = fma(cc.a0, (double)lo, cc.b0), fhi = fma(cc.a0, (double)hi, cc.b0);
+            if (flo >= cc.l0 && fhi <= cc.h0) {
+                int q0, q1;
+                sub_range(tv, sh.view, j, q0, q1);
+                double m1 = 0.0, m2 = 0.0;
+                for (int s = q0; s < q1; ++s) {
+                    m1 += tv.m1[s];
+                    m2 += tv.m2[s];
+                }
+                const double off = fma(cc.a0, tv.pivot, cc.b0) - pv;     // f(x) - p = a (x - pivot) + off
+                n += (double)cn;
+                u += cc.a0 * m1 + (double)cn * off;
+                q += cc.a0 * cc.a0 * m2 + 2.0 * cc.a0 * off * m1 + (double)cn * off * off;
+            } else if (fhi <= cc.l0 || flo >= cc.h0) {
+                const double d = (fhi <= cc.l0 ? cc.l0 : cc.h0) - pv;
+                n += (double)cn;
+                u += (double)cn * d;
+                q += (double)cn * d * d;
+            } else {
+                partial = true;
+            }
+        }
+        if (partial) sh.plist[atomicAdd(&sh.nplist, 1)] = j;
+    }
+    __syncthreads();
+    const int np = sh.nplist;
+    for (int i = 0; i < np; ++i) {
+        for_bin_elements(tv, sh.view, sh.plist[i], [&](float x) {
+            if (x < xa || x > xb || in_zero_x(c, c.nz, x)) return;
+            const double d = eval_fast(cc, c, sh.he, (double)x) - pv;
+            n += 1.0;
+            u += d;
+            q = fma(d, d, q);
+        });
+    }
+    block_sum3(n, u, q, sh.red);
     s0 = n;
     s1 = u;
     s2 = q;
 }
 
-__device__ double live_median(const Chan& c, const HistEq& he, const float* S, int a, int cnt) {
+__device__ double live_median(Shared& sh, const TileView& tv, const Chan& c, int a, int cnt) {
     // numpy median: middle element, or mean of the two middle elements
-    if (cnt & 1) return eval_ops<true>(c, c.nops, he, (double)S[kth_live(c, a, cnt >> 1)]);
-    const double x = eval_ops<true>(c, c.nops, he, (double)S[kth_live(c, a, (cnt >> 1) - 1)]);
-    const double y = eval_ops<true>(c, c.nops, he, (double)S[kth_live(c, a, cnt >> 1)]);
+    if (cnt & 1) return eval_ops<true>(c, c.nops, sh.he, (double)value_at(sh, tv, kth_live(c, a, cnt >> 1)));
+    const double x = eval_ops<true>(c, c.nops, sh.he, (double)value_at(sh, tv, kth_live(c, a, (cnt >> 1) - 1)));
+    const double y = eval_ops<true>(c, c.nops, sh.he, (double)value_at(sh, tv, kth_live(c, a, cnt >> 1)));
     return (x + y) / 2.0;
 }
 
-// astropy SigmaClip (axis=None, median/std, maxiters 5; App. A.1) over the live values of channel c in S[0..n).
+// astropy SigmaClip (axis=None, median/std, maxiters 5; App. A.1) over the live values of channel c in the active view.
 // Outputs the bounds of the last iteration and the (mean, std) of the survivors.  Returns false if the set is empty.
-// One full pass builds the moment sums about a pivot (the initial median, so mean-pivot = O(std): no cancellation);
-// every iteration keeps a contiguous index range of the sorted array, so it only subtracts the sums of the clipped
-// tails: mean = p + S1/n, std = sqrt(S2/n - (S1/n)^2)  (== numpy's two-pass definition up to fp64 rounding).
-__device__ bool sigma_clip(Shared& sh, const Chan& c, const Comp& cc, const float* S, int n, double sig_lo,
-                           double sig_hi, double& lo, double& hi, double& mean, double& sd) {
-    int a = 0, b = n;
+// Every iteration keeps a contiguous rank range = value interval [xa, xb]; the moment sums are taken about the initial
+// median (mean-pivot = O(std): no cancellation): mean = p + S1/n, std = sqrt(S2/n - (S1/n)^2)  (== numpy's two-pass
+// definition up to fp64 rounding).
+__device__ bool sigma_clip(Shared& sh, const TileView& tv, const Chan& c, const Comp& cc, double sig_lo, double sig_hi,
+                           double& lo, double& hi, double& mean, double& sd) {
+    int a = 0, b = sh.n;
+    float xa = -INFINITY, xb = INFINITY;
     int cnt = live_count(c, a, b);
     if (cnt <= 0) return false;
-    const double p = live_median(c, sh.he, S, a, cnt);
+    const double p = live_median(sh, tv, c, a, cnt);
     double s0, s1, s2;
-    range_sums(c, cc, sh.he, S, a, b, 0, 0, p, sh.red, s0, s1, s2);
-    if ((int)s0 != cnt) {  // index-range bookkeeping and evaluation disagree: never expected
+    range_sums(sh, tv, c, cc, xa, xb, p, s0, s1, s2);
+    if ((int)s0 != cnt) {  // rank bookkeeping and evaluation disagree: never expected
         if (threadIdx.x == 0) sh.fail = -5;
         cnt = (int)s0;
         if (cnt <= 0) return false;
@@ -513,22 +1042,23 @@ __device__ bool sigma_clip(Shared& sh, const Chan& c, const Comp& cc, const floa
         const double m1 = s1 / s0;
         mean = p + m1;
         sd = sqrt(fmax(s2 / s0 - m1 * m1, 0.0));
-        const double med = live_median(c, sh.he, S, a, cnt);
+        const double med = live_median(sh, tv, c, a, cnt);
         lo = med - sd * sig_lo;
         hi = med + sd * sig_hi;
-        const int na = lower_index_coop<false>(sh, c, c.nops, S, a, b, lo);   // first f >= lo
-        const int nb = lower_index_coop<true>(sh, c, c.nops, S, na, b, hi);   // first f > hi
+        float xbel, xabv;
+        int na = a, nb = b;
+        float nxa = xa, nxb = xb;
+        const int r1 = lower_index<false>(sh, tv, c, c.nops, a, b, lo, &xbel, &xabv);   // first f >= lo
+        if (r1 > a) { na = r1; nxa = xabv; }
+        const int r2 = lower_index<true>(sh, tv, c, c.nops, na, b, hi, &xbel, &xabv);   // first f > hi
+        if (r2 < b) { nb = r2; nxb = xbel; }
         const int ncnt = live_count(c, na, nb);
         if (ncnt == cnt) break;
         if (ncnt <= 0) return false;
-        double t0, t1, t2;
-        range_sums(c, cc, sh.he, S, a, na, nb, b, p, sh.red, t0, t1, t2);  // the clipped tails only
-        s0 -= t0;
-        s1 -= t1;
-        s2 -= t2;
-        a = na;
-        b = nb;
-        cnt = ncnt;
+        a = na; b = nb; xa = nxa; xb = nxb; cnt = ncnt;
+        range_sums(sh, tv, c, cc, xa, xb, p, s0, s1, s2);
+        if ((int)s0 != cnt && threadIdx.x == 0) sh.fail = -5;
+        if (s0 <= 0.0) return false;
     }
     const double m1 = s1 / s0;
     mean = p + m1;
@@ -536,8 +1066,8 @@ __device__ bool sigma_clip(Shared& sh, const Chan& c, const Comp& cc, const floa
     return true;
 }
 
-// Append an op to channel c and register the pixels it newly maps to exactly 0 (they become masked).
-__device__ void push_op(Shared& sh, int ci, const float* S, int n, int kind, double p0, double p1, double p2, double p3) {
+// Append an op to channel ci and register the pixels it newly maps to exactly 0 (they become masked).  View: all.
+__device__ void push_op(Shared& sh, const TileView& tv, int ci, int kind, double p0, double p1, double p2, double p3) {
     Chan& c = sh.ch[ci];
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -551,14 +1081,15 @@ __device__ void push_op(Shared& sh, int ci, const float* S, int n, int kind, dou
         }
     }
     __syncthreads();
-    // zero set of the plain composition is a contiguous index range (monotone): [first >= 0, first > 0)
-    const int h0 = lower_index_coop<false>(sh, c, c.nops, S, 0, n, 0.0);
-    const int h1 = lower_index_coop<true>(sh, c, c.nops, S, h0, n, 0.0);
+    // zero set of the plain composition is a contiguous rank range (monotone): [first f >= 0, first f > 0)
+    float xb0, xa0, xb1, xa1;
+    const int h0 = lower_index<false>(sh, tv, c, c.nops, 0, sh.n, 0.0, &xb0, &xa0);
+    const int h1 = lower_index<true>(sh, tv, c, c.nops, h0, sh.n, 0.0, &xb1, &xa1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        add_zero_range(c, h0, h1);
+        add_zero_range(c, h0, h1, xa0, xb1);
         c.hid = sh.next_hid++;
-        compile_chan(c, sh.cc[ci], S);
+        compile_chan(c, sh.cc[ci]);
     }
     __syncthreads();
 }
@@ -572,11 +1103,41 @@ __device__ void copy_chan(Shared& sh, int dst, int src) {
     __syncthreads();
 }
 
-// astropy ZScaleInterval.get_limits (App. A.2) on channel c (positional samples of the current image, zeros
+// smallest / largest live value of channel c after its ops (NaN-free); false if the channel has no live pixel
+__device__ bool live_min_max(Shared& sh, const TileView& tv, const Chan& c, double& mn, double& mx) {
+    const int nl = live_count(c, 0, sh.n);
+    if (nl <= 0) return false;
+    mn = eval_ops<true>(c, c.nops, sh.he, (double)value_at(sh, tv, kth_live(c, 0, 0)));
+    mx = eval_ops<true>(c, c.nops, sh.he, (double)value_at(sh, tv, kth_live(c, 0, nl - 1)));
+    return true;
+}
+
+// (all threads) channel c with its zero sets expressed in ranks of the active (subset) view -> sh.tmp
+__device__ void rerank_zero_sets(Shared& sh, const TileView& tv, const Chan& c) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.tmp = c;
+    __syncthreads();
+    const int nz = c.nz;
+    for (int k = 0; k < nz; ++k) {
+        const int z0 = lower_index<false>(sh, tv, c, 0, 0, sh.n, (double)c.zx0[k], nullptr, nullptr);
+        const int z1 = lower_index<true>(sh, tv, c, 0, 0, sh.n, (double)c.zx1[k], nullptr, nullptr);
+        if (threadIdx.x == 0) {
+            sh.tmp.z0[k] = z0;
+            sh.tmp.z1[k] = z1;
+        }
+    }
+    __syncthreads();
+}
+static_assert(kNB == 2 * kPPThreads, "set_view: two logical bins per thread");
+
+// ------------------------------------------------------------------------------------------ stages
+
+// astropy ZScaleInterval.get_limits (App. A.2) on channel ci (positional samples of the current image, zeros
 // included), then the OP_ZSCALE op.
-__device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const float* S, int n, double contrast) {
+__device__ void zscale_stage(Shared& sh, const PPParams& p, int b, const TileView& tv, int ci, double contrast) {
     const Chan& c = sh.ch[ci];
     const int t = threadIdx.x;
+    const int N = p.Ty * p.Tx;
     constexpr int kZS = 1024;                     // sample slots (>= the 1000 samples of ZScaleInterval)
     constexpr int kZE = kZS / kPPThreads;         // slots per thread: e = t + q * kPPThreads
     const int stride = (int)fmax(1.0, (double)N / 1000.0);
@@ -586,7 +1147,7 @@ __device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const
 #pragma unroll
     for (int q = 0; q < kZE; ++q) {
         const int e = t + q * kPPThreads;
-        sh.zs[e] = (e < npix) ? eval_ops<true>(c, c.nops, sh.he, (double)tile[(long long)e * stride]) : INFINITY;
+        sh.zs[e] = (e < npix) ? eval_ops<true>(c, c.nops, sh.he, (double)load_pixel(p, b, e * stride)) : INFINITY;
     }
     __syncthreads();
     // bitonic sort ascending, 1024 elements, one compare-exchange per element pair
@@ -595,13 +1156,13 @@ __device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const
 #pragma unroll
             for (int q = 0; q < kZE; ++q) {
                 const int e = t + q * kPPThreads;
-                const int p = e ^ j;
-                if (p > e) {
-                    const double x = sh.zs[e], y = sh.zs[p];
+                const int pp = e ^ j;
+                if (pp > e) {
+                    const double x = sh.zs[e], y = sh.zs[pp];
                     const bool asc = ((e & k) == 0);
                     if (asc ? (x > y) : (x < y)) {
                         sh.zs[e] = y;
-                        sh.zs[p] = x;
+                        sh.zs[pp] = x;
                     }
                 }
             }
@@ -704,22 +1265,36 @@ __device__ void zscale_stage(Shared& sh, int ci, const float* tile, int N, const
         vmin = fmax(vmin, med - (double)(center - 1) * sl);
         vmax = fmin(vmax, med + (double)(npix - center) * sl);
     }
-    push_op(sh, ci, S, n, OP_ZSCALE, vmin, vmax - vmin, 0.0, 0.0);
+    push_op(sh, tv, ci, OP_ZSCALE, vmin, vmax - vmin, 0.0, 0.0);
 }
 
-// skimage equalize_hist (App. A.3) on channel c: 256-bin histogram over [min,max] of ALL pixels (masked zeros
-// included), CDF, then OP_HISTEQ.  The channel is a monotone map of the sorted array, so min / max are its first / last
-// live element (and 0 if any pixel is masked) and the bin counts are differences of 257 binary searches at the bin
-// edges (numpy assigns v to the bin with edges[k] <= v < edges[k+1], last bin closed) -- no pass over the pixels.
-__device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const float* S, int n) {
+// histogram bin of value v among the 256 bins of sh.he.edges (numpy: edges[k] <= v < edges[k+1], last bin closed);
+// -1 below the first edge
+__device__ __forceinline__ int he_bin(const HistEq& h, double v) {
+    if (v < h.edges[0]) return -1;
+    int lo = 0, hi = 256;   // invariant: edges[lo] <= v, (hi == 256 or v < edges[hi])
+    while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (h.edges[m] <= v) lo = m; else hi = m;
+    }
+    return min(lo, 255);
+}
+
+// skimage equalize_hist (App. A.3) on channel ci: 256-bin histogram over [min,max] of ALL pixels (masked zeros
+// included), CDF, then OP_HISTEQ.  The channel is a monotone map of the pixel value, so min / max are its first / last
+// live element (and 0 if any pixel is masked); value bins that fall into ONE histogram bin are counted at once, the
+// bins a histogram edge (or a masked interval) cuts are walked element by element.
+__device__ bool histeq_stage(Shared& sh, const PPParams& p, const TileView& tv, int ci) {
     const Chan& c = sh.ch[ci];
-    const int nlive = live_count(c, 0, n);
+    const int N = p.Ty * p.Tx;
+    if (sh.he_used) {   // one table per chain
+        if (threadIdx.x == 0) sh.fail = -6;
+        return false;
+    }
+    const int nlive = live_count(c, 0, sh.n);
     const int nzero = N - nlive;
     double mn = INFINITY, mx = -INFINITY;
-    if (nlive > 0) {
-        mn = eval_ops<true>(c, c.nops, sh.he, (double)S[kth_live(c, 0, 0)]);
-        mx = eval_ops<true>(c, c.nops, sh.he, (double)S[kth_live(c, 0, nlive - 1)]);
-    }
+    if (nlive > 0) live_min_max(sh, tv, c, mn, mx);
     if (nzero > 0) {
         mn = fmin(mn, 0.0);
         mx = fmax(mx, 0.0);
@@ -734,13 +1309,39 @@ __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const
     const double step = (last - first) / 256.0;
     for (int i = threadIdx.x; i < 257; i += kPPThreads)
         sh.he.edges[i] = i == 256 ? last : __dadd_rn(__dmul_rn((double)i, step), first);
+    for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.hist[i] = 0;
+    if (threadIdx.x == 0) sh.nplist = 0;
     __syncthreads();
-    // cum[k] = number of live elements with value < edges[k]  (k = 256: all of them, the last bin is closed)
-    int* cum = reinterpret_cast<int*>(sh.zs);
-    for (int k = threadIdx.x; k < 257; k += kPPThreads)
-        cum[k] = k == 256 ? nlive : live_count(c, 0, lower_index<false>(c, c.nops, sh.he, S, 0, n, sh.he.edges[k]));
+    for (int j = threadIdx.x; j < kNB; j += kPPThreads) {
+        const int cn = sh.prefix[j + 1] - sh.prefix[j];
+        if (cn == 0) continue;
+        const float lo = sh.bmin[j], hi = sh.bmax[j];
+        bool partial = false, masked = false;
+        for (int k = 0; k < c.nz; ++k) {
+            if (hi < c.zx0[k] || lo > c.zx1[k]) continue;
+            if (lo >= c.zx0[k] && hi <= c.zx1[k]) masked = true; else partial = true;
+        }
+        if (masked) continue;
+        if (!partial) {
+            const int b0 = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)lo));
+            const int b1 = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)hi));
+            if (b0 == b1) {
+                if (b0 >= 0) atomicAdd(&sh.hist[b0], cn);
+            } else {
+                partial = true;
+            }
+        }
+        if (partial) sh.plist[atomicAdd(&sh.nplist, 1)] = j;
+    }
     __syncthreads();
-    for (int k = threadIdx.x; k < 256; k += kPPThreads) sh.hist[k] = cum[k + 1] - cum[k];
+    const int np = sh.nplist;
+    for (int i = 0; i < np; ++i) {
+        for_bin_elements(tv, sh.view, sh.plist[i], [&](float x) {
+            if (in_zero_x(c, c.nz, x)) return;
+            const int hb = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)x));
+            if (hb >= 0) atomicAdd(&sh.hist[hb], 1);
+        });
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (nzero > 0) {  // the masked pixels (value 0): numpy histogram fast path for uniform bins
@@ -761,6 +1362,7 @@ __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const
         }
         const double tot = (double)run;
         for (int i = 0; i < 256; ++i) sh.he.cdf[i] = sh.he.cdf[i] / tot;
+        sh.he_used = 1;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.he.center[i] = (sh.he.edges[i] + sh.he.edges[i + 1]) / 2.0;
@@ -770,286 +1372,42 @@ __device__ void histeq_stage(Shared& sh, int ci, const float* tile, int N, const
                                             __dsub_rn(sh.he.center[i + 1], sh.he.center[i]))
                                  : 0.0;
     if (threadIdx.x == 0) {
-        const double step = (sh.he.center[255] - sh.he.center[0]) / 255.0;
-        sh.he.inv_step = step > 0.0 ? 1.0 / step : 0.0;
+        const double st = (sh.he.center[255] - sh.he.center[0]) / 255.0;
+        sh.he.inv_step = st > 0.0 ? 1.0 / st : 0.0;
     }
     __syncthreads();
-    push_op(sh, ci, S, n, OP_HISTEQ, 0.0, 0.0, 0.0, 0.0);
-}
-
-// SigmaClipper._clip (preprocessing.py:735-751) on channel ci
-__device__ bool sigma_clipper_stage(Shared& sh, int ci, const float* S, int n, double s_lo, double s_hi) {
-    // astropy: sigma_lower = sigma_lower or sigma(=3.0): a falsy 0 falls back to 3 (App. A.1 / B#1)
-    const double slo = s_lo != 0.0 ? s_lo : 3.0, shi = s_hi != 0.0 ? s_hi : 3.0;
-    double lo, hi, mean, sd;
-    if (!sigma_clip(sh, sh.ch[ci], sh.cc[ci], S, n, slo, shi, lo, hi, mean, sd)) return false;
-    push_op(sh, ci, S, n, OP_CLAMP, lo, hi, 0.0, 0.0);
+    push_op(sh, tv, ci, OP_HISTEQ, 0.0, 0.0, 0.0, 0.0);
     return true;
 }
 
-// ------------------------------------------------------------------------------------------ kernel 1: cut-out + sort
-
-__device__ __forceinline__ float load_pixel(const PPParams& p, int b, int idx) {
-    const int y = idx / p.Tx, x = idx - y * p.Tx;
-    uint32_t raw = p.img[(long long)(p.y0[b] + y) * p.row_stride + p.x0[b] + x];
-    if (p.big_endian) raw = __byte_perm(raw, 0, 0x0123);
-    const float f = __uint_as_float(raw);
-    return isfinite(f) ? f : 0.0f;  // utils.py:219,394
+// SigmaClipper._clip (preprocessing.py:735-751) on channel ci
+__device__ bool sigma_clipper_stage(Shared& sh, const TileView& tv, int ci, double s_lo, double s_hi) {
+    // astropy: sigma_lower = sigma_lower or sigma(=3.0): a falsy 0 falls back to 3 (App. A.1 / B#1)
+    const double slo = s_lo != 0.0 ? s_lo : 3.0, shi = s_hi != 0.0 ? s_hi : 3.0;
+    double lo, hi, mean, sd;
+    if (!sigma_clip(sh, tv, sh.ch[ci], sh.cc[ci], slo, shi, lo, hi, mean, sd)) return false;
+    push_op(sh, tv, ci, OP_CLAMP, lo, hi, 0.0, 0.0);
+    return true;
 }
 
-// LSD radix sort (4 x 8 bit) of `n` keys in global memory with one CTA.  Every pass streams the keys in chunks of 8 keys per thread
-// through shared memory: warp-striped loads, stable ranks inside the chunk from __match_any_sync + per-warp digit
-// counters, a counting sort of the chunk in shared memory, then a write-out in which consecutive threads carry
-// consecutive keys of one digit to consecutive addresses (full-sector stores; the direct per-key scatter this replaces
-// wrote 4 bytes per 32-byte sector).  The histogram of the NEXT digit is built during the write-out, so a pass reads
-// and writes every key once; passes whose digit is the same for all keys are skipped.
-static constexpr int kSortChunk = 8 * kSortThreads;   // 8 keys per thread, warp-striped
-struct SortSmem {
-    int hist[256][kSortWarps + 1];  // [digit][warp] counters -> exclusive warp bases inside the chunk (+1: bank skew)
-    uint32_t sorted[kSortChunk];  // the chunk in digit order
-    int dtot[256], dbase[256], gcur[256];
-    int nh[2][256];               // digit histograms of the whole array (current / next pass)
-    int flag;
-};
-
-// lanes of `msk` whose 8-bit digit equals mine (eight independent ballots; MATCH.ANY is far slower than this)
-__device__ __forceinline__ uint32_t digit_peers(uint32_t msk, uint32_t d) {
-    uint32_t peers = msk;
-#pragma unroll
-    for (int bit = 0; bit < 8; ++bit) {
-        const bool on = (d >> bit) & 1u;
-        const uint32_t b = __ballot_sync(msk, on);
-        peers &= on ? b : ~b;
-    }
-    return peers;
+// sigma clipping of channel ci over the pixels outside (sub 0) / inside (sub 1) the box: the view is switched, the
+// channel's masked sets are re-ranked for it, and the all-pixels view is restored
+__device__ bool sigma_clip_subset(Shared& sh, const TileView& tv, int ci, int sub, double sig, double& mean, double& sd) {
+    set_view(sh, tv, sub);
+    rerank_zero_sets(sh, tv, sh.ch[ci]);
+    double lo, hi;
+    const bool ok = sigma_clip(sh, tv, sh.tmp, sh.cc[ci], sig, sig, lo, hi, mean, sd);
+    set_view(sh, tv, -1);
+    return ok;
 }
-
-// exclusive scan of a[0..256) into out[0..256) by warp 0 (8 entries per lane); returns nothing
-__device__ __forceinline__ void scan256_warp0(const int* a, int* out) {
-    const int lane = threadIdx.x & 31;
-    int v[8], s = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        v[q] = a[lane * 8 + q];
-        s += v[q];
-    }
-    int inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += y;
-    }
-    int run = inc - s;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        out[lane * 8 + q] = run;
-        run += v[q];
-    }
-}
-
-__device__ long long* g_sort_dbg = nullptr;   // optional phase timing (clock64 sums of thread 0 of block 0), tools only
-#define SORT_T(k) do { if (dbg) { const long long _c = clock64(); dbg[k] += _c - tprev; tprev = _c; } } while (0)
-
-// Returns the buffer (a or b) that holds the sorted keys.  *as_float is set when the top-digit pass moved the keys (it
-// then wrote them back as fp32 bit patterns, key2f fused into its write-out: no separate conversion pass).
-__device__ uint32_t* block_radix_sort(uint32_t* a, uint32_t* b, int n, SortSmem& sm, bool* as_float) {
-    *as_float = false;
-    long long* dbg = (g_sort_dbg && blockIdx.x == 0 && threadIdx.x == 0) ? g_sort_dbg : nullptr;
-    long long tprev = dbg ? clock64() : 0;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    uint32_t* src = a;
-    uint32_t* dst = b;
-    for (int i = t; i < 512; i += kSortThreads) (&sm.nh[0][0])[i] = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += 4 * kSortThreads) {
-        uint32_t k[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int i = i0 + q * kSortThreads + t;
-            k[q] = i < n ? src[i] : 0xffffffffu;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (i0 + q * kSortThreads + t < n) atomicAdd(&sm.nh[0][k[q] & 255u], 1);
-    }
-    __syncthreads();
-    SORT_T(0);
-    int cur = 0;
-    for (int shift = 0; shift < 32; shift += 8, cur ^= 1) {
-        int* nh = sm.nh[cur];
-        int* nh_next = sm.nh[cur ^ 1];
-        if (t < 32) {
-            scan256_warp0(nh, sm.gcur);
-            int one = 0;
-            for (int q = 0; q < 8; ++q) one |= (nh[lane * 8 + q] == n);
-            one = __any_sync(0xffffffffu, one);
-            if (lane == 0) sm.flag = one;
-        }
-        for (int i = t; i < 256; i += kSortThreads) nh_next[i] = 0;
-        __syncthreads();
-        const bool trivial = sm.flag != 0;
-        const bool more = shift < 24;
-        if (trivial) {  // nothing moves; only the next digit's histogram is needed
-            if (more)
-                for (int i = t; i < n; i += kSortThreads) atomicAdd(&nh_next[(src[i] >> (shift + 8)) & 255u], 1);
-            __syncthreads();
-            continue;
-        }
-        for (int c0 = 0; c0 < n; c0 += kSortChunk) {
-            const int m = min(kSortChunk, n - c0);
-            for (int i = t; i < 256 * (kSortWarps + 1); i += kSortThreads) (&sm.hist[0][0])[i] = 0;
-            uint32_t key[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {  // independent loads first
-                const int li = w * 256 + j * 32 + lane;
-                key[j] = li < m ? src[c0 + li] : 0u;
-            }
-            __syncthreads();
-            SORT_T(1);
-            int rnk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int li = w * 256 + j * 32 + lane;
-                const bool v = li < m;
-                rnk[j] = -1;
-                const uint32_t msk = __ballot_sync(0xffffffffu, v);
-                if (v) {
-                    const uint32_t d = (key[j] >> shift) & 255u;
-                    const uint32_t peers = digit_peers(msk, d);
-                    const int r = __popc(peers & ((1u << lane) - 1u));
-                    const int pre = sm.hist[d][w];
-                    __syncwarp(msk);
-                    if (r == 0) sm.hist[d][w] = pre + __popc(peers);
-                    rnk[j] = pre + r;
-                }
-                __syncwarp();
-            }
-            __syncthreads();
-            SORT_T(2);
-            // per digit: exclusive scan over the warps' counters (one warp per digit, 256 / kSortWarps digits per warp)
-#pragma unroll
-            for (int q = 0; q < 256 / kSortWarps; ++q) {
-                const int d = w * (256 / kSortWarps) + q;
-                const int v = lane < kSortWarps ? sm.hist[d][lane] : 0;
-                int inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
-                }
-                if (lane < kSortWarps) sm.hist[d][lane] = inc - v;
-                if (lane == 31) sm.dtot[d] = inc;
-            }
-            __syncthreads();
-            SORT_T(3);
-            if (t < 32) scan256_warp0(sm.dtot, sm.dbase);
-            __syncthreads();
-            SORT_T(4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (rnk[j] >= 0) {
-                    const uint32_t d = (key[j] >> shift) & 255u;
-                    sm.sorted[sm.dbase[d] + sm.hist[d][w] + rnk[j]] = key[j];
-                }
-            __syncthreads();
-            SORT_T(5);
-#pragma unroll
-            for (int q = 0; q < kSortChunk / kSortThreads; ++q) {
-                const int j = q * kSortThreads + t;
-                if (j < m) {
-                    const uint32_t k = sm.sorted[j];
-                    const uint32_t d = (k >> shift) & 255u;
-                    dst[sm.gcur[d] + (j - sm.dbase[d])] = more ? k : __float_as_uint(key2f(k));
-                    if (more) atomicAdd(&nh_next[(k >> (shift + 8)) & 255u], 1);
-                }
-            }
-            __syncthreads();
-            SORT_T(6);
-            if (t < 256) sm.gcur[t] += sm.dtot[t];
-        }
-        if (!more) *as_float = true;
-        __syncthreads();
-        uint32_t* x = src;
-        src = dst;
-        dst = x;
-    }
-    return src;
-}
-
-__global__ void __launch_bounds__(kSortThreads, 2) pp_sort_kernel(const __grid_constant__ PPParams p) {
-    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
-    SortSmem& sm = *reinterpret_cast<SortSmem*>(sort_smem_raw);
-    __shared__ int s_n, s_nb;
-    const int b = blockIdx.x;
-    const int N = p.Ty * p.Tx;
-    float* tile = p.tilebuf + (long long)b * N;
-    uint32_t* A = p.keysA + (long long)b * N;
-    uint32_t* Bk = p.keysB + (long long)b * N;
-    uint32_t* C = p.keysC ? p.keysC + (long long)b * N : nullptr;
-    if (threadIdx.x == 0) {
-        s_n = 0;
-        s_nb = 0;
-    }
-    __syncthreads();
-    // box of BkgSubtractor (preprocessing.py:610-621)
-    const int xc = p.Tx / 2, yc = p.Ty / 2;
-    const int dy = (int)(p.Ty * p.cfg.bkg_box_mask_fract / 2.0), dx = (int)(p.Tx * p.cfg.bkg_box_mask_fract / 2.0);
-    const int lane = threadIdx.x & 31;
-    for (int i00 = 0; i00 < N; i00 += 4 * kSortThreads) {
-        float fq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {  // four independent loads in flight per thread
-            const int i = i00 + q * kSortThreads + threadIdx.x;
-            fq[q] = i < N ? load_pixel(p, b, i) : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int i = i00 + q * kSortThreads + threadIdx.x;
-            const float f = fq[q];
-            if (i < N) tile[i] = f;
-            const bool live = (i < N) && (f != 0.0f);
-            const uint32_t m = __ballot_sync(0xffffffffu, live);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (live) A[base + __popc(m & ((1u << lane) - 1u))] = f2key(f);
-            if (C) {
-                const int y = i / p.Tx, x = i - y * p.Tx;
-                const bool inbox = (y >= yc - dy && y < yc + dy && x >= xc - dx && x < xc + dx);
-                const bool lb = live && !inbox;
-                const uint32_t m2 = __ballot_sync(0xffffffffu, lb);
-                int base2 = 0;
-                if (lane == 0 && m2) base2 = atomicAdd(&s_nb, __popc(m2));
-                base2 = __shfl_sync(0xffffffffu, base2, 0);
-                if (lb) C[base2 + __popc(m2 & ((1u << lane) - 1u))] = f2key(f);
-            }
-        }
-    }
-    __syncthreads();
-    const int n = s_n, nb = s_nb;
-    // sorted keys -> fp32 values in `out`; usually nothing is left to do (four moving passes end in `out`, already
-    // converted by the last one)
-    auto finish = [&](const uint32_t* r, bool as_float, uint32_t* out, int cnt) {
-        if (as_float && r == out) return;
-        for (int i = threadIdx.x; i < cnt; i += kSortThreads) {
-            const uint32_t k = r[i];
-            out[i] = as_float ? k : __float_as_uint(key2f(k));
-        }
-    };
-    bool as_float;
-    {
-        const uint32_t* r = block_radix_sort(A, Bk, n, sm, &as_float);
-        finish(r, as_float, A, n);
-    }
-    if (C) {
-        __syncthreads();
-        const uint32_t* r = block_radix_sort(C, Bk, nb, sm, &as_float);
-        finish(r, as_float, C, nb);
-    }
-    if (threadIdx.x == 0) {
-        p.nlive[b] = n;
-        p.nbox[b] = nb;
-    }
+// largest live value of channel ci inside the box (AbsMaxScaler / ChanMaxScaler with use_mask_box)
+__device__ bool box_max(Shared& sh, const TileView& tv, int ci, double& mx) {
+    set_view(sh, tv, 1);
+    rerank_zero_sets(sh, tv, sh.ch[ci]);
+    double mn;
+    const bool ok = live_min_max(sh, tv, sh.tmp, mn, mx);
+    set_view(sh, tv, -1);
+    return ok;
 }
 
 // ------------------------------------------------------------------------------------------ kernel 2: the chain
@@ -1060,12 +1418,10 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
     const int b = blockIdx.x;
-    const int N = p.Ty * p.Tx;
-    const float* tile = p.tilebuf + (long long)b * N;
-    const float* S = reinterpret_cast<const float*>(p.keysA + (long long)b * N);
-    const float* Sbox = p.keysC ? reinterpret_cast<const float*>(p.keysC + (long long)b * N) : nullptr;
-    const int n = p.nlive[b];
-    const cy_pp_config& cfg = p.cfg;
+    const cy_pp_chain& chain = p.chain;
+    TileView tv;
+    memset(&tv, 0, sizeof(tv));
+    if (chain.nstages > 0) tv = tile_view(p, b);
     if (threadIdx.x == 0) {
         for (int c = 0; c < 3; ++c) {
             sh.ch[c].nops = 0;
@@ -1074,10 +1430,15 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
         }
         sh.next_hid = 1;
         sh.fail = 0;
-        for (int c = 0; c < 3; ++c) compile_chan(sh.ch[c], sh.cc[c], S);
+        sh.he_used = 0;
+        sh.n = 0;
+        sh.view = -1;
+        sh.gath_bin = -1;
+        for (int c = 0; c < 3; ++c) compile_chan(sh.ch[c], sh.cc[c]);
     }
     __syncthreads();
-    bool ok = true;  // uniform across the block
+    if (chain.nstages > 0) set_view(sh, tv, -1);
+    bool ok = chain.reject_all == 0;  // uniform across the block
 
     // Channel de-duplication: a stage applied with equal parameters to channels that hold identical data (equal
     // history id) gives identical results, so it is computed once and the channel state is copied.  `in_hid[c]` is
@@ -1089,122 +1450,276 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
         return -1;
     };
 
-    if (cfg.enabled) {
-        // ---- BkgSubtractor (preprocessing.py:591-658): x - clipped mean
-        if (cfg.subtract_bkg) {
-            in_hid[0] = in_hid[1] = in_hid[2] = -1;
-            for (int c = 0; c < 3 && ok; ++c) {
-                if (!chan_selected(cfg.bkg_chid, c)) continue;
-                const int q = find_same(c), hid = sh.ch[c].hid;
-                if (q >= 0) {
-                    copy_chan(sh, c, q);
-                } else {
-                    double lo, hi, mean, sd;
-                    const float* Sb = cfg.use_box_mask_in_bkg ? Sbox : S;
-                    const int nb = cfg.use_box_mask_in_bkg ? p.nbox[b] : n;
-                    const double sg = cfg.sigma_bkg != 0 ? cfg.sigma_bkg : 3.0;
-                    ok = sigma_clip(sh, sh.ch[c], sh.cc[c], Sb, nb, sg, sg, lo, hi, mean, sd);
-                    if (ok) push_op(sh, c, S, n, OP_SUB, mean, 0, 0, 0);
-                }
-                in_hid[c] = hid;
-            }
-        }
-        // ---- SigmaClipShifter (preprocessing.py:664-717): x - (clipmean + sigma*std), negatives -> 0
-        if (cfg.clip_shift_data && ok) {
-            in_hid[0] = in_hid[1] = in_hid[2] = -1;
-            for (int c = 0; c < 3 && ok; ++c) {
-                if (!chan_selected(cfg.clip_chid, c)) continue;
-                const int q = find_same(c), hid = sh.ch[c].hid;
-                if (q >= 0) {
-                    copy_chan(sh, c, q);
-                } else {
-                    double lo, hi, mean, sd;
-                    const double sg = cfg.sigma_clip != 0 ? cfg.sigma_clip : 3.0;
-                    ok = sigma_clip(sh, sh.ch[c], sh.cc[c], S, n, sg, sg, lo, hi, mean, sd);
-                    if (ok) push_op(sh, c, S, n, OP_SHIFT, mean + cfg.sigma_clip * sd, 0, 0, 0);
-                }
-                in_hid[c] = hid;
-            }
-        }
-        // ---- SigmaClipper (preprocessing.py:723-771)
-        if (cfg.clip_data && ok) {
-            in_hid[0] = in_hid[1] = in_hid[2] = -1;
-            for (int c = 0; c < 3 && ok; ++c) {
-                if (!chan_selected(cfg.clip_chid, c)) continue;
-                const int q = find_same(c), hid = sh.ch[c].hid;
-                if (q >= 0) copy_chan(sh, c, q);
-                else ok = sigma_clipper_stage(sh, c, S, n, cfg.sigma_clip_low, cfg.sigma_clip_up);
-                in_hid[c] = hid;
-            }
-        }
-        // ---- ChanResizer: the cube already has 3 channels (evaluation.py:146-154) -> no-op for nchannels 1 or 3
-        // ---- ZScaleTransformer (preprocessing.py:934-971)
-        if (cfg.zscale_stretch && ok) {
-            in_hid[0] = in_hid[1] = in_hid[2] = -1;
-            for (int c = 0; c < 3; ++c) {
-                int q = -1;
-                for (int k = 0; k < c; ++k)
-                    if (in_hid[k] == sh.ch[c].hid && cfg.zscale_contrasts[k] == cfg.zscale_contrasts[c]) q = k;
-                const int hid = sh.ch[c].hid;
-                if (q >= 0) copy_chan(sh, c, q);
-                else zscale_stage(sh, c, tile, N, S, n, cfg.zscale_contrasts[c]);
-                in_hid[c] = hid;
-            }
-        }
-        // ---- Chan3Trasformer (preprocessing.py:1020-1072)
-        if (cfg.chan3_preproc && ok) {
-            const int hid0 = sh.ch[0].hid, hid1 = sh.ch[1].hid;
-            ok = sigma_clipper_stage(sh, 0, S, n, cfg.sigma_clip_baseline, cfg.sigma_clip_up);
-            if (ok) zscale_stage(sh, 0, tile, N, S, n, cfg.zscale_contrasts[0]);
-            if (ok) {
-                const double blo = cfg.sigma_clip_baseline != 0.0 ? cfg.sigma_clip_baseline : 3.0;
-                const double llo = cfg.sigma_clip_low != 0.0 ? cfg.sigma_clip_low : 3.0;
-                if (hid0 == hid1 && blo == llo) {
-                    copy_chan(sh, 1, 0);
-                } else {
-                    ok = sigma_clipper_stage(sh, 1, S, n, cfg.sigma_clip_low, cfg.sigma_clip_up);
-                    if (ok) zscale_stage(sh, 1, tile, N, S, n, cfg.zscale_contrasts[0]);
-                }
-            }
-            if (ok) histeq_stage(sh, 2, tile, N, S, n);
-        }
-        // ---- MinMaxNormalizer (preprocessing.py:75-111)
-        if (cfg.normalize_minmax && ok) {
-            in_hid[0] = in_hid[1] = in_hid[2] = -1;
-            for (int c = 0; c < 3 && ok; ++c) {
-                const int q = find_same(c), hid = sh.ch[c].hid;
-                if (q >= 0) {
-                    copy_chan(sh, c, q);
-                } else {
-                    // min / max over the non-zero pixels = first / last live element of the sorted array
-                    const Chan& ch = sh.ch[c];
-                    double mn = INFINITY, mx = -INFINITY;
-                    const int nl = live_count(ch, 0, n);
-                    if (nl > 0) {
-                        mn = eval_ops<true>(ch, ch.nops, sh.he, (double)S[kth_live(ch, 0, 0)]);
-                        mx = eval_ops<true>(ch, ch.nops, sh.he, (double)S[kth_live(ch, 0, nl - 1)]);
+    for (int si = 0; si < chain.nstages && ok; ++si) {
+        const cy_pp_stage& st = chain.st[si];
+        in_hid[0] = in_hid[1] = in_hid[2] = -1;
+        switch (st.type) {
+            case CY_PP_BKG_SUB:      // x - clipped mean (preprocessing.py:591-658)
+                for (int c = 0; c < 3 && ok; ++c) {
+                    if (!chan_selected(st.chid, c)) continue;
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) {
+                        copy_chan(sh, c, q);
+                    } else {
+                        double lo, hi, mean, sd;
+                        const double sg = st.p[0] != 0 ? st.p[0] : 3.0;
+                        if (st.flag) ok = sigma_clip_subset(sh, tv, c, 0, sg, mean, sd);
+                        else ok = sigma_clip(sh, tv, sh.ch[c], sh.cc[c], sg, sg, lo, hi, mean, sd);
+                        if (ok) push_op(sh, tv, c, OP_SUB, mean, 0, 0, 0);
                     }
-                    if (!(mn <= mx)) ok = false;  // no non-zero pixel -> None (preprocessing.py:101-103)
-                    else push_op(sh, c, S, n, OP_MINMAX, mn, mx - mn, cfg.norm_max - cfg.norm_min, cfg.norm_min);
+                    in_hid[c] = hid;
                 }
-                in_hid[c] = hid;
+                break;
+            case CY_PP_CLIP_SHIFT:   // x - (clipmean + sigma*std), negatives -> 0 (preprocessing.py:664-717)
+                for (int c = 0; c < 3 && ok; ++c) {
+                    if (!chan_selected(st.chid, c)) continue;
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) {
+                        copy_chan(sh, c, q);
+                    } else {
+                        double lo, hi, mean, sd;
+                        const double sg = st.p[0] != 0 ? st.p[0] : 3.0;
+                        ok = sigma_clip(sh, tv, sh.ch[c], sh.cc[c], sg, sg, lo, hi, mean, sd);
+                        if (ok) push_op(sh, tv, c, OP_SHIFT, mean + st.p[0] * sd, 0, 0, 0);
+                    }
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_SIGMA_CLIP:   // preprocessing.py:723-771
+                for (int c = 0; c < 3 && ok; ++c) {
+                    if (!chan_selected(st.chid, c)) continue;
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) copy_chan(sh, c, q);
+                    else ok = sigma_clipper_stage(sh, tv, c, st.p[0], st.p[1]);
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_CHAN_RESIZE:  // the cube already has 3 channels (evaluation.py:146-154): no-op for 1 or 3
+                break;
+            case CY_PP_ZSCALE:       // preprocessing.py:934-971
+                for (int c = 0; c < 3; ++c) {
+                    int q = -1;
+                    for (int k = 0; k < c; ++k)
+                        if (in_hid[k] == sh.ch[c].hid && st.p[k] == st.p[c]) q = k;
+                    const int hid = sh.ch[c].hid;
+                    if (q >= 0) copy_chan(sh, c, q);
+                    else zscale_stage(sh, p, b, tv, c, st.p[c]);
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_CHAN3: {      // preprocessing.py:1020-1072: p0 baseline, p1 low, p2 up, p3 contrast
+                const int hid0 = sh.ch[0].hid, hid1 = sh.ch[1].hid;
+                ok = sigma_clipper_stage(sh, tv, 0, st.p[0], st.p[2]);
+                if (ok) zscale_stage(sh, p, b, tv, 0, st.p[3]);
+                if (ok) {
+                    const double blo = st.p[0] != 0.0 ? st.p[0] : 3.0;
+                    const double llo = st.p[1] != 0.0 ? st.p[1] : 3.0;
+                    if (hid0 == hid1 && blo == llo) {
+                        copy_chan(sh, 1, 0);
+                    } else {
+                        ok = sigma_clipper_stage(sh, tv, 1, st.p[1], st.p[2]);
+                        if (ok) zscale_stage(sh, p, b, tv, 1, st.p[3]);
+                    }
+                }
+                if (ok) ok = histeq_stage(sh, p, tv, 2);
+                break;
             }
+            case CY_PP_HISTEQ: {     // preprocessing.py:977-1012: every channel; one table: channels must be identical
+                const int hid0 = sh.ch[0].hid;
+                if (sh.ch[1].hid != hid0 || sh.ch[2].hid != hid0) {
+                    if (threadIdx.x == 0) sh.fail = -6;
+                    ok = false;
+                    break;
+                }
+                ok = histeq_stage(sh, p, tv, 0);
+                if (ok) {
+                    copy_chan(sh, 1, 0);
+                    copy_chan(sh, 2, 0);
+                }
+                break;
+            }
+            case CY_PP_MINMAX:       // preprocessing.py:75-111
+                for (int c = 0; c < 3 && ok; ++c) {
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) {
+                        copy_chan(sh, c, q);
+                    } else {
+                        double mn, mx;
+                        if (!live_min_max(sh, tv, sh.ch[c], mn, mx)) ok = false;  // no non-zero pixel -> None (:101-103)
+                        else push_op(sh, tv, c, OP_MINMAX, mn, mx - mn, st.p[1] - st.p[0], st.p[0]);
+                    }
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_ABS_MINMAX: { // preprocessing.py:116-146: one min / max over all channels
+                double mn = INFINITY, mx = -INFINITY;
+                bool any = false;
+                for (int c = 0; c < 3; ++c) {
+                    double a, z;
+                    if (c > 0 && sh.ch[c].hid == sh.ch[c - 1].hid) continue;
+                    if (live_min_max(sh, tv, sh.ch[c], a, z)) {
+                        mn = fmin(mn, a);
+                        mx = fmax(mx, z);
+                        any = true;
+                    }
+                }
+                if (!any) break;     // everything masked: the output stays all zero
+                for (int c = 0; c < 3; ++c) {
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) copy_chan(sh, c, q);
+                    else push_op(sh, tv, c, OP_MINMAX, mn, mx - mn, st.p[1] - st.p[0], st.p[0]);
+                    in_hid[c] = hid;
+                }
+                break;
+            }
+            case CY_PP_MAX_SCALE:    // preprocessing.py:152-176: x / max of the channel
+                for (int c = 0; c < 3 && ok; ++c) {
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) {
+                        copy_chan(sh, c, q);
+                    } else {
+                        double mn, mx;
+                        if (!live_min_max(sh, tv, sh.ch[c], mn, mx)) { in_hid[c] = hid; continue; }  // all masked: stays 0
+                        if (!(mx > 0.0)) {   // order-reversing division: not representable as a monotone map
+                            if (threadIdx.x == 0) sh.fail = -6;
+                            ok = false;
+                        } else {
+                            push_op(sh, tv, c, OP_DIV, mx, 0, 0, 0);
+                        }
+                    }
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_ABS_MAX_SCALE:      // preprocessing.py:182-226: x / max over all channels (inside the box)
+            case CY_PP_CHAN_MAX_SCALE: {   // preprocessing.py:232-288: x / max of channel chref; None if a channel max <= 0
+                double mxs[3];
+                bool have[3];
+                for (int c = 0; c < 3; ++c) {
+                    if (c > 0 && sh.ch[c].hid == sh.ch[c - 1].hid) {
+                        mxs[c] = mxs[c - 1];
+                        have[c] = have[c - 1];
+                        continue;
+                    }
+                    double mn;
+                    have[c] = st.flag ? box_max(sh, tv, c, mxs[c]) : live_min_max(sh, tv, sh.ch[c], mn, mxs[c]);
+                }
+                double d;
+                if (st.type == CY_PP_ABS_MAX_SCALE) {
+                    d = -INFINITY;
+                    bool any = false;
+                    for (int c = 0; c < 3; ++c)
+                        if (have[c]) {
+                            d = fmax(d, mxs[c]);
+                            any = true;
+                        }
+                    if (!any) break;
+                } else {
+                    for (int c = 0; c < 3; ++c)
+                        if (!have[c] || !(mxs[c] > 0.0) || !isfinite(mxs[c])) ok = false;   // returns None (:276-279)
+                    if (!ok) break;
+                    d = mxs[min(max(st.n, 0), 2)];
+                }
+                if (!(d > 0.0)) {
+                    if (threadIdx.x == 0) sh.fail = -6;
+                    ok = false;
+                    break;
+                }
+                for (int c = 0; c < 3; ++c) {
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) copy_chan(sh, c, q);
+                    else push_op(sh, tv, c, OP_DIV, d, 0, 0, 0);
+                    in_hid[c] = hid;
+                }
+                break;
+            }
+            case CY_PP_MIN_SHIFT:    // preprocessing.py:294-327
+            case CY_PP_NEG_FIX:      // preprocessing.py:408-440: the same for channels without a positive pixel
+                for (int c = 0; c < 3 && ok; ++c) {
+                    if (st.type == CY_PP_MIN_SHIFT && !chan_selected(st.chid, c)) continue;
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) {
+                        copy_chan(sh, c, q);
+                    } else {
+                        double mn, mx;
+                        if (live_min_max(sh, tv, sh.ch[c], mn, mx)) {
+                            if (st.type == CY_PP_MIN_SHIFT || !(mx > 0.0)) push_op(sh, tv, c, OP_SUB, mn, 0, 0, 0);
+                        } else {
+                            ok = false;   // numpy: min() of an empty array raises; the reference run dies -> reject
+                        }
+                    }
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_SHIFT:        // preprocessing.py:333-363
+                for (int c = 0; c < 3; ++c) {
+                    int q = -1;
+                    for (int k = 0; k < c; ++k)
+                        if (in_hid[k] == sh.ch[c].hid && st.p[k] == st.p[c]) q = k;
+                    const int hid = sh.ch[c].hid;
+                    if (q >= 0) copy_chan(sh, c, q);
+                    else push_op(sh, tv, c, OP_SUB, st.p[c], 0, 0, 0);
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_STANDARDIZE:  // preprocessing.py:369-402
+                for (int c = 0; c < 3 && ok; ++c) {
+                    if (!(st.p[3 + c] > 0.0)) {
+                        if (threadIdx.x == 0) sh.fail = -6;
+                        ok = false;
+                        break;
+                    }
+                    int q = -1;
+                    for (int k = 0; k < c; ++k)
+                        if (in_hid[k] == sh.ch[c].hid && st.p[k] == st.p[c] && st.p[3 + k] == st.p[3 + c]) q = k;
+                    const int hid = sh.ch[c].hid;
+                    if (q >= 0) copy_chan(sh, c, q);
+                    else push_op(sh, tv, c, OP_STD, st.p[c], st.p[3 + c], 0, 0);
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_LOG_STRETCH:  // preprocessing.py:480-538 (minmaxnorm form): chid = EXCLUDED channel
+                for (int c = 0; c < 3 && ok; ++c) {
+                    if (st.chid != -1 && c == st.chid) continue;
+                    const int q = find_same(c), hid = sh.ch[c].hid;
+                    if (q >= 0) {
+                        copy_chan(sh, c, q);
+                    } else {
+                        const Chan& cch = sh.ch[c];
+                        const int i0 = lower_index<true>(sh, tv, cch, cch.nops, 0, sh.n, 0.0, nullptr, nullptr);
+                        const int npos = live_count(cch, i0, sh.n);
+                        if (npos <= 0) {
+                            ok = false;       // no positive pixel: returns None (:513-516)
+                        } else {
+                            const double vmin = eval_ops<true>(cch, cch.nops, sh.he,
+                                                               (double)value_at(sh, tv, kth_live(cch, i0, 0)));
+                            push_op(sh, tv, c, OP_LOG, log10(vmin), st.p[0], st.p[1] - st.p[0], (st.flag & 2) ? 1.0 : 0.0);
+                        }
+                    }
+                    in_hid[c] = hid;
+                }
+                break;
+            case CY_PP_BORDER_MASK:  // applied when the pixels are read (leading stage only; checked on the host)
+                break;
+            default:
+                if (threadIdx.x == 0) sh.fail = -6;
+                ok = false;
         }
     }
 
     // ---- hand the final per-channel maps to pp_final_kernel (which evaluates them per pixel, fused with the letterbox
     // resize) + the reference's degenerate-image check on rows 0..2 (evaluation.py:171-176)
     TileFinal& tf = p.fin[b];
+    __syncthreads();
     if (!ok) {
         if (threadIdx.x == 0) {
             const int stt = sh.fail ? sh.fail : -1;
             p.status[b] = stt;
             tf.status = stt;
+            tf.valid = 0;
         }
         return;
     }
     {
-        __syncthreads();
         uint32_t* dst = reinterpret_cast<uint32_t*>(&tf);
         const uint32_t* s_cc = reinterpret_cast<const uint32_t*>(&sh.cc[0]);
         const uint32_t* s_ch = reinterpret_cast<const uint32_t*>(&sh.ch[0]);
@@ -1212,21 +1727,21 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
         constexpr int n_cc = sizeof(Comp) * 3 / 4, n_ch = sizeof(Chan) * 3 / 4, n_he = sizeof(HistEq) / 4;
         for (int i = threadIdx.x; i < n_cc; i += kPPThreads) dst[offsetof(TileFinal, cc) / 4 + i] = s_cc[i];
         for (int i = threadIdx.x; i < n_ch; i += kPPThreads) dst[offsetof(TileFinal, ch) / 4 + i] = s_ch[i];
-        const bool any_he = sh.cc[0].has_he || sh.cc[1].has_he || sh.cc[2].has_he || !sh.cc[0].ok || !sh.cc[1].ok || !sh.cc[2].ok;
-        if (any_he)
+        if (sh.he_used)
             for (int i = threadIdx.x; i < n_he; i += kPPThreads) dst[offsetof(TileFinal, he) / 4 + i] = s_he[i];
         if (threadIdx.x == 0) {
             tf.same01 = sh.ch[0].hid == sh.ch[1].hid;
             tf.same02 = sh.ch[0].hid == sh.ch[2].hid;
             tf.same12 = sh.ch[1].hid == sh.ch[2].hid;
-            tf.use_he = any_he ? 1 : 0;
+            tf.use_he = sh.he_used;
+            tf.valid = 1;
         }
     }
     int bad = 0;
     for (int r = 0; r < 3 && r < p.Ty; ++r) {
         double mn = INFINITY, mx = -INFINITY;
         for (int i = threadIdx.x; i < p.Tx; i += kPPThreads) {
-            const double x = (double)tile[r * p.Tx + i];
+            const double x = (double)load_pixel_yx(p, b, r, i);
             for (int c = 0; c < 3; ++c) {
                 const double v = eval_ops<true>(sh.ch[c], sh.ch[c].nops, sh.he, x);
                 mn = fmin(mn, v);
@@ -1249,10 +1764,11 @@ __global__ void __launch_bounds__(kPPThreads, 2) pp_chain_kernel(const __grid_co
 // predictor preprocess on them (LetterBox half-pixel bilinear resize with cv2's double-precision source coordinates,
 // pad 114, channel reversal, /255) straight into the 16-bit NHWC(4) model input.  The fp32 HWC chain image never exists
 // in HBM (it was a 3 MB write + 3 MB read per 512^2 tile); tests that want it ask for the optional `chain_out`.
-// One CTA walks bands of `band_h` output rows of its tile: the input rows a band needs (band_h * Ty / new_h + 2) are
-// evaluated once into shared memory (fp32 x 3), then every output pixel interpolates from shared memory.
-// emit_only: bands are input rows, the evaluated rows are written to chain_out as they are (parity surface and the
-// path of tiles whose bands do not fit shared memory, which then go through pp_resize_kernel).
+// One CTA walks bands of `band_h` output rows of its tile: the raw input rows a band needs (band_h * Ty / new_h + 2)
+// are staged in shared memory once, every DISTINCT channel map is evaluated over them with its parameters in registers
+// (planes of fp32 in shared memory), then every thread interpolates whole output columns from the planes.
+// emit_only: bands are input rows and the planes are written to chain_out as they are (parity surface, and the path of
+// tiles whose bands do not fit shared memory, which then go through pp_resize_kernel).
 struct FinalParams {
     PPParams p;
     void* out16;         // [B,Sh,Sw,4] bf16 / fp16
@@ -1262,17 +1778,6 @@ struct FinalParams {
     int band_h, rows_cap, nbands;
     int f16, emit_only;
 };
-
-__device__ __forceinline__ void eval3(const TileFinal& tf, float xf, float* o) {
-    const double x = (double)xf;
-    const double v0 = in_zero_x(tf.cc[0], xf) ? 0.0 : eval_fast(tf.cc[0], tf.ch[0], tf.he, x);
-    const double v1 = tf.same01 ? v0 : (in_zero_x(tf.cc[1], xf) ? 0.0 : eval_fast(tf.cc[1], tf.ch[1], tf.he, x));
-    const double v2 = tf.same02 ? v0
-                                : (tf.same12 ? v1 : (in_zero_x(tf.cc[2], xf) ? 0.0 : eval_fast(tf.cc[2], tf.ch[2], tf.he, x)));
-    o[0] = (float)v0;
-    o[1] = (float)v1;
-    o[2] = (float)v2;
-}
 
 // source row / column of cv2.resize INTER_LINEAR for destination index d: i0, i1 and the weight of i1
 __device__ __forceinline__ void src_coord(int d, double scale, int n, int& i0, int& i1, float& w) {
@@ -1286,27 +1791,59 @@ __device__ __forceinline__ void src_coord(int d, double scale, int n, int& i0, i
 
 static constexpr int kFinThreads = 512;
 
-__global__ void __launch_bounds__(kFinThreads) pp_final_kernel(const __grid_constant__ FinalParams r) {
+// one channel map over the staged rows: raw[] -> plane[]
+__device__ void eval_plane(const TileFinal& tf, int ci, const float* __restrict__ raw, float* __restrict__ plane, int n) {
+    const Comp& cc = tf.cc[ci];
+    const int nz = cc.nzx;
+    if (cc.ok && !cc.has_he && nz <= 2) {
+        // the common case: affine + clamp with at most two masked intervals, everything in registers
+        const double a = cc.a0, b = cc.b0, l = cc.l0, h = cc.h0;
+        const float z00 = nz > 0 ? cc.zx0[0] : INFINITY, z01 = nz > 0 ? cc.zx1[0] : -INFINITY;
+        const float z10 = nz > 1 ? cc.zx0[1] : INFINITY, z11 = nz > 1 ? cc.zx1[1] : -INFINITY;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n; i += kFinThreads) {
+            const float x = raw[i];
+            const bool masked = (x == 0.0f) || (x >= z00 && x <= z01) || (x >= z10 && x <= z11);
+            const double v = fmin(fmax(fma(a, (double)x, b), l), h);
+            plane[i] = masked ? 0.0f : (float)v;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += kFinThreads) {
+        const float x = raw[i];
+        const bool masked = (x == 0.0f) || in_zero_x(cc, nz, x);
+        plane[i] = masked ? 0.0f : (float)eval_fast(cc, tf.ch[ci], tf.he, (double)x);
+    }
+}
+
+__global__ void __launch_bounds__(kFinThreads, 2) pp_final_kernel(const __grid_constant__ FinalParams r) {
     extern __shared__ __align__(16) unsigned char fin_smem[];
     TileFinal& tf = *reinterpret_cast<TileFinal*>(fin_smem);
-    int* xi0 = reinterpret_cast<int*>(fin_smem + sizeof(TileFinal));           // [Sw] source column of tap 0
-    int* xi1 = xi0 + r.Sw;                                                      // [Sw] source column of tap 1 (-1: padding)
+    int* xi0 = reinterpret_cast<int*>(fin_smem + sizeof(TileFinal));           // [Sw] source column of tap 0 (-1: padding)
+    int* xi1 = xi0 + r.Sw;                                                      // [Sw] source column of tap 1
     float* xw = reinterpret_cast<float*>(xi1 + r.Sw);                           // [Sw]
-    float* vals = reinterpret_cast<float*>(fin_smem + sizeof(TileFinal) + (((size_t)r.Sw * 12 + 15) & ~(size_t)15));
+    int* ry0t = reinterpret_cast<int*>(xw + r.Sw);                              // [16] source rows of the band's output rows
+    int* ry1t = ry0t + 16;
+    float* rwt = reinterpret_cast<float*>(ry1t + 16);
+    float* raw = reinterpret_cast<float*>(fin_smem + sizeof(TileFinal) + (((size_t)r.Sw * 12 + 192 + 15) & ~(size_t)15));
     const int b = blockIdx.x, tid = threadIdx.x;
     const PPParams& p = r.p;
     const int Ty = p.Ty, Tx = p.Tx;
+    const int plane_sz = r.rows_cap * Tx;
+    float* pl0 = raw + plane_sz;
     {
         const uint4* src = reinterpret_cast<const uint4*>(&p.fin[b]);
         uint4* dst = reinterpret_cast<uint4*>(&tf);
         // the histogram-equalisation tables are the bulk of the state: skip them when no channel uses them
         const int n_head = (int)(offsetof(TileFinal, he) / 16), n_all = (int)(sizeof(TileFinal) / 16);
         const int n_tail0 = (int)((offsetof(TileFinal, he) + sizeof(HistEq)) / 16);
-        for (int i = tid; i < n_head; i += kFinThreads) dst[i] = src[i];
         for (int i = n_tail0 + tid; i < n_all; i += kFinThreads) dst[i] = src[i];
         __syncthreads();
-        if (tf.status == 0 && tf.use_he)
-            for (int i = n_head + tid; i < n_tail0; i += kFinThreads) dst[i] = src[i];
+        if (tf.valid) {
+            for (int i = tid; i < n_head; i += kFinThreads) dst[i] = src[i];
+            if (tf.use_he)
+                for (int i = n_head + tid; i < n_tail0; i += kFinThreads) dst[i] = src[i];
+        }
         if (!r.emit_only)
             for (int ox = tid; ox < r.Sw; ox += kFinThreads) {
                 const int rx = ox - r.left;
@@ -1319,8 +1856,15 @@ __global__ void __launch_bounds__(kFinThreads) pp_final_kernel(const __grid_cons
             }
         __syncthreads();
     }
-    const bool ok = tf.status == 0;
+    const bool valid = tf.valid != 0;
+    // distinct planes: channel c reads plane pidx[c]
+    const int pidx1 = tf.same01 ? 0 : 1;
+    const int pidx2 = tf.same02 ? 0 : (tf.same12 ? pidx1 : pidx1 + 1);
+    const float* pc0 = pl0;
+    const float* pc1 = pl0 + pidx1 * plane_sz;
+    const float* pc2 = pl0 + pidx2 * plane_sz;
     float* chain = p.chain_out ? p.chain_out + (long long)b * Ty * Tx * 3 : nullptr;
+    const uint32_t* gimg = p.img + (long long)p.y0[b] * p.row_stride + p.x0[b];
     for (int band = blockIdx.y; band < r.nbands; band += gridDim.y) {
         int yin0, nrows, oy0 = 0, oy1 = 0;
         if (r.emit_only) {
@@ -1341,55 +1885,75 @@ __global__ void __launch_bounds__(kFinThreads) pp_final_kernel(const __grid_cons
                 nrows = c1 - a0 + 1;
             }
         }
-        // evaluate the input rows of the band once
-        for (int i = tid; i < nrows * Tx; i += kFinThreads) {
-            float o[3] = {0.f, 0.f, 0.f};
-            if (ok) eval3(tf, load_pixel(p, b, yin0 * Tx + i), o);
-            vals[3 * i + 0] = o[0];
-            vals[3 * i + 1] = o[1];
-            vals[3 * i + 2] = o[2];
+        const int n = nrows * Tx;
+        if (!r.emit_only && tid < oy1 - oy0) {
+            const int ry = oy0 + tid - r.top;
+            int y0 = -1, y1 = -1;
+            float wy = 0.f;
+            if (ry >= 0 && ry < r.new_h) src_coord(ry, r.scale_y, Ty, y0, y1, wy);
+            ry0t[tid] = y0;
+            ry1t[tid] = y1;
+            rwt[tid] = wy;
+        }
+        // raw rows of the band -> shared memory (byte swap, NaN -> 0, border mask)
+        for (int i = tid; i < n; i += kFinThreads) {
+            const int y = i / Tx, x = i - y * Tx;
+            float f = decode_pixel(gimg[(long long)(yin0 + y) * p.row_stride + x], p.big_endian);
+            if (p.border_mask && !in_box(p, yin0 + y, x)) f = 0.0f;
+            raw[i] = f;
         }
         __syncthreads();
+        if (valid) {
+            eval_plane(tf, 0, raw, pl0, n);
+            if (!tf.same01) eval_plane(tf, 1, raw, pl0 + pidx1 * plane_sz, n);
+            if (!tf.same02 && !tf.same12) eval_plane(tf, 2, raw, pl0 + pidx2 * plane_sz, n);
+        } else {
+            for (int i = tid; i < n; i += kFinThreads) pl0[i] = 0.0f;   // same01 / same02 are garbage: see pc* below
+        }
+        __syncthreads();
+        const float* q0 = pc0;
+        const float* q1 = valid ? pc1 : pc0;
+        const float* q2 = valid ? pc2 : pc0;
         if (r.emit_only) {
             if (chain)
-                for (int i = tid; i < nrows * Tx * 3; i += kFinThreads) chain[(long long)yin0 * Tx * 3 + i] = vals[i];
-        } else {
-            const int nout = (oy1 - oy0) * r.Sw;
-            for (int o = tid; o < nout; o += kFinThreads) {
-                const int dy = o / r.Sw, ox = o - dy * r.Sw, oy = oy0 + dy;
-                float v[3] = {114.f, 114.f, 114.f};   // cv2.copyMakeBorder value
-                const int ry = oy - r.top;
-                const int x0 = xi0[ox];
-                if (ry >= 0 && ry < r.new_h && x0 >= 0) {
-                    int y0, y1;
-                    float wy;
-                    src_coord(ry, r.scale_y, Ty, y0, y1, wy);
-                    const int x1 = xi1[ox];
-                    const float wx = xw[ox];
-                    const float* p00 = vals + ((y0 - yin0) * Tx + x0) * 3;
-                    const float* p01 = vals + ((y0 - yin0) * Tx + x1) * 3;
-                    const float* p10 = vals + ((y1 - yin0) * Tx + x0) * 3;
-                    const float* p11 = vals + ((y1 - yin0) * Tx + x1) * 3;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float t0 = p00[c] * (1.f - wx) + p01[c] * wx;
-                        const float t1 = p10[c] * (1.f - wx) + p11[c] * wx;
-                        v[c] = t0 * (1.f - wy) + t1 * wy;
-                    }
+                for (int i = tid; i < n; i += kFinThreads) {
+                    float* o = chain + ((long long)yin0 * Tx + i) * 3;
+                    o[0] = q0[i];
+                    o[1] = q1[i];
+                    o[2] = q2[i];
                 }
-                // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
-                const float m0 = v[2] / 255.f, m1 = v[1] / 255.f, m2 = v[0] / 255.f;
-                const long long idx = ((long long)b * r.Sh + oy) * r.Sw + ox;
-                uint2 pk;
-                pk.x = pack_h2(m0, m1, r.f16);
-                pk.y = pack_h2(m2, 0.f, r.f16);
-                *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(r.out16) + idx * 4) = pk;
-                if (r.out_f32) {
-                    const long long plane = (long long)r.Sh * r.Sw;
-                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)oy * r.Sw + ox;
-                    of[0] = m0;
-                    of[plane] = m1;
-                    of[2 * plane] = m2;
+        } else {
+            // every thread owns output columns; the row geometry is shared by the whole band
+            for (int ox = tid; ox < r.Sw; ox += kFinThreads) {
+                const int x0 = xi0[ox], x1 = xi1[ox];
+                const float wx = xw[ox], ux = 1.f - wx;
+                for (int oy = oy0; oy < oy1; ++oy) {
+                    float v0 = 114.f, v1 = 114.f, v2 = 114.f;   // cv2.copyMakeBorder value
+                    const int y0 = ry0t[oy - oy0];
+                    if (y0 >= 0 && x0 >= 0) {
+                        const int y1 = ry1t[oy - oy0];
+                        const float wy = rwt[oy - oy0];
+                        const float uy = 1.f - wy;
+                        const int i00 = (y0 - yin0) * Tx + x0, i01 = (y0 - yin0) * Tx + x1;
+                        const int i10 = (y1 - yin0) * Tx + x0, i11 = (y1 - yin0) * Tx + x1;
+                        v0 = (q0[i00] * ux + q0[i01] * wx) * uy + (q0[i10] * ux + q0[i11] * wx) * wy;
+                        v1 = (q1[i00] * ux + q1[i01] * wx) * uy + (q1[i10] * ux + q1[i11] * wx) * wy;
+                        v2 = (q2[i00] * ux + q2[i01] * wx) * uy + (q2[i10] * ux + q2[i11] * wx) * wy;
+                    }
+                    // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
+                    const float m0 = v2 / 255.f, m1 = v1 / 255.f, m2 = v0 / 255.f;
+                    const long long idx = ((long long)b * r.Sh + oy) * r.Sw + ox;
+                    uint2 pk;
+                    pk.x = pack_h2(m0, m1, r.f16);
+                    pk.y = pack_h2(m2, 0.f, r.f16);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(r.out16) + idx * 4) = pk;
+                    if (r.out_f32) {
+                        const long long plane = (long long)r.Sh * r.Sw;
+                        float* of = r.out_f32 + (long long)b * 3 * plane + (long long)oy * r.Sw + ox;
+                        of[0] = m0;
+                        of[plane] = m1;
+                        of[2 * plane] = m2;
+                    }
                 }
             }
         }
@@ -1398,7 +1962,6 @@ __global__ void __launch_bounds__(kFinThreads) pp_final_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------ letterbox resize of an HWC image
-
 
 struct ResizeParams {
     const float* chain;  // [B,Ty,Tx,3]
@@ -1411,7 +1974,7 @@ struct ResizeParams {
 };
 
 __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
-    // grid = (column blocks, output rows, tiles): no 64-bit div/mod per pixel (they were 40 % of this kernel's stalls)
+    // grid = (column blocks, output rows, tiles): no 64-bit div/mod per pixel
     const int ox = blockIdx.x * blockDim.x + threadIdx.x;
     const int oy = blockIdx.y, b = blockIdx.z;
     if (ox >= r.Sw) return;
@@ -1419,16 +1982,10 @@ __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
     float v[3] = {114.f, 114.f, 114.f};  // cv2.copyMakeBorder value
     const int ry = oy - r.top, rx = ox - r.left;
     if (ry >= 0 && ry < r.new_h && rx >= 0 && rx < r.new_w) {
-        // cv2.resize INTER_LINEAR: half-pixel centres, clamp at the borders
-        double fy = ((double)ry + 0.5) * r.scale_y - 0.5;
-        double fx = ((double)rx + 0.5) * r.scale_x - 0.5;
-        int y0 = (int)floor(fy), x0 = (int)floor(fx);
-        float wy = (float)(fy - (double)y0), wx = (float)(fx - (double)x0);
-        if (y0 < 0) { y0 = 0; wy = 0.f; }
-        if (y0 >= r.Ty - 1) { y0 = r.Ty - 1; wy = 0.f; }
-        if (x0 < 0) { x0 = 0; wx = 0.f; }
-        if (x0 >= r.Tx - 1) { x0 = r.Tx - 1; wx = 0.f; }
-        const int y1 = min(y0 + 1, r.Ty - 1), x1 = min(x0 + 1, r.Tx - 1);
+        int y0, y1, x0, x1;
+        float wy, wx;
+        src_coord(ry, r.scale_y, r.Ty, y0, y1, wy);
+        src_coord(rx, r.scale_x, r.Tx, x0, x1, wx);
         const float* base = r.chain + (long long)b * r.Ty * r.Tx * 3;
         const float* p00 = base + ((long long)y0 * r.Tx + x0) * 3;
         const float* p01 = base + ((long long)y0 * r.Tx + x1) * 3;
@@ -1462,9 +2019,107 @@ __global__ void __launch_bounds__(256) pp_resize_kernel(const ResizeParams r) {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" int cy_sort_set_debug(void* dev_buf) {
-    long long* p = (long long*)dev_buf;
-    CY_CUDA_CHECK(cudaMemcpyToSymbol(cy::g_sort_dbg, &p, sizeof(p)));
+static void add_stage(cy_pp_chain* ch, int type, int chid, int flag, int n, double p0 = 0, double p1 = 0, double p2 = 0,
+                      double p3 = 0) {
+    if (ch->nstages >= CY_PP_MAX_STAGES) return;
+    cy_pp_stage& s = ch->st[ch->nstages++];
+    memset(&s, 0, sizeof(s));
+    s.type = type; s.chid = chid; s.flag = flag; s.n = n;
+    s.p[0] = p0; s.p[1] = p1; s.p[2] = p2; s.p[3] = p3;
+}
+
+extern "C" int cy_pp_chain_from_config(const cy_pp_config* cfg, cy_pp_chain* ch) {
+    if (!cfg || !ch) return cy::set_error(CY_ERR_INVALID, "cy_pp_chain_from_config: null argument");
+    memset(ch, 0, sizeof(*ch));
+    ch->out_f16 = cfg->out_f16 ? 1 : 0;
+    if (!cfg->enabled) return CY_OK;
+    // scripts/run.py:272-293
+    if (cfg->subtract_bkg)
+        add_stage(ch, CY_PP_BKG_SUB, cfg->bkg_chid, cfg->use_box_mask_in_bkg ? 1 : 0, 0, cfg->sigma_bkg, cfg->bkg_box_mask_fract);
+    if (cfg->clip_shift_data) add_stage(ch, CY_PP_CLIP_SHIFT, cfg->clip_chid, 0, 0, cfg->sigma_clip);
+    if (cfg->clip_data) add_stage(ch, CY_PP_SIGMA_CLIP, cfg->clip_chid, 0, 0, cfg->sigma_clip_low, cfg->sigma_clip_up);
+    if (cfg->nchannels > 1) add_stage(ch, CY_PP_CHAN_RESIZE, -1, 0, cfg->nchannels);
+    if (cfg->zscale_stretch)
+        add_stage(ch, CY_PP_ZSCALE, -1, 0, 3, cfg->zscale_contrasts[0], cfg->zscale_contrasts[1], cfg->zscale_contrasts[2]);
+    if (cfg->chan3_preproc)
+        add_stage(ch, CY_PP_CHAN3, -1, 0, 0, cfg->sigma_clip_baseline, cfg->sigma_clip_low, cfg->sigma_clip_up,
+                  cfg->zscale_contrasts[0]);
+    if (cfg->normalize_minmax) add_stage(ch, CY_PP_MINMAX, -1, 0, 0, cfg->norm_min, cfg->norm_max);
+    if (cfg->nchannels != 1 && cfg->nchannels != 3)
+        return cy::set_error(CY_ERR_INVALID, "nchannels must be 1 or 3 (the model takes 3-channel images)");
+    if (cfg->chan3_preproc && cfg->nchannels != 3)
+        return cy::set_error(CY_ERR_INVALID, "chan3_preproc requires nchannels == 3 (scripts/run.py:253-256)");
+    return cy_pp_chain_validate(ch);
+}
+
+static bool stage_uses_box_stats(const cy_pp_stage& s) {
+    return (s.type == CY_PP_BKG_SUB || s.type == CY_PP_ABS_MAX_SCALE || s.type == CY_PP_CHAN_MAX_SCALE) && s.flag;
+}
+static double stage_box_fract(const cy_pp_stage& s) {
+    return s.type == CY_PP_BKG_SUB ? s.p[1] : s.p[0];
+}
+
+extern "C" int cy_pp_chain_validate(cy_pp_chain* ch) {
+    using namespace cy;
+    if (!ch) return set_error(CY_ERR_INVALID, "cy_pp_chain_validate: null argument");
+    if (ch->nstages < 0 || ch->nstages > CY_PP_MAX_STAGES)
+        return set_error(CY_ERR_INVALID, "a chain holds at most %d stages", CY_PP_MAX_STAGES);
+    ch->reject_all = 0;
+    bool have_box = false, stats_seen = false;
+    double fract = 0;
+    int nhe = 0;
+    for (int i = 0; i < ch->nstages; ++i) {
+        const cy_pp_stage& s = ch->st[i];
+        if (s.chid < -1 || s.chid > 2) return set_error(CY_ERR_INVALID, "stage %d: chid must be -1, 0, 1 or 2", i);
+        const bool box_stage = stage_uses_box_stats(s) || s.type == CY_PP_BORDER_MASK;
+        if (box_stage) {
+            const double f = stage_box_fract(s);
+            if (have_box && f != fract)
+                return set_error(CY_ERR_INVALID, "stage %d: one box geometry (mask_fract) per chain in this build", i);
+            have_box = true;
+            fract = f;
+        }
+        switch (s.type) {
+            case CY_PP_BKG_SUB: case CY_PP_CLIP_SHIFT: case CY_PP_SIGMA_CLIP: case CY_PP_MINMAX: case CY_PP_ABS_MINMAX:
+            case CY_PP_MAX_SCALE: case CY_PP_ABS_MAX_SCALE: case CY_PP_MIN_SHIFT: case CY_PP_NEG_FIX:
+                stats_seen = true;
+                break;
+            case CY_PP_CHAN_MAX_SCALE:
+                if (s.n < 0 || s.n > 2) return set_error(CY_ERR_INVALID, "stage %d: chref must be 0, 1 or 2", i);
+                stats_seen = true;
+                break;
+            case CY_PP_CHAN_RESIZE:
+                if (s.n != 1 && s.n != 3)
+                    return set_error(CY_ERR_INVALID, "ChanResizer: nchans must be 1 or 3 (the model takes 3-channel images)");
+                break;
+            case CY_PP_ZSCALE:
+                if (s.n < 3) ch->reject_all = 1;      // the reference returns None (preprocessing.py:955-957)
+                stats_seen = true;
+                break;
+            case CY_PP_CHAN3: case CY_PP_HISTEQ:
+                if (++nhe > 1)
+                    return set_error(CY_ERR_INVALID, "stage %d: one histogram equalisation per chain in this build", i);
+                stats_seen = true;
+                break;
+            case CY_PP_SHIFT: case CY_PP_STANDARDIZE:
+                if (s.n != 3) ch->reject_all = 1;     // length check of the reference fails -> None (:344-348, :381-389)
+                break;
+            case CY_PP_LOG_STRETCH:
+                if (!(s.flag & 1))
+                    return set_error(CY_ERR_INVALID, "LogStretcher without minmaxnorm turns masked pixels into non-zero "
+                                                     "values: not implemented in this build");
+                if (!(s.p[1] > s.p[0])) return set_error(CY_ERR_INVALID, "LogStretcher: data_norm_max must exceed data_norm_min");
+                stats_seen = true;
+                break;
+            case CY_PP_BORDER_MASK:
+                if (stats_seen)
+                    return set_error(CY_ERR_INVALID, "BorderMasker after a stage that computes image statistics is not "
+                                                     "implemented in this build (put it first)");
+                break;
+            default:
+                return set_error(CY_ERR_INVALID, "stage %d: unknown stage type %d", i, s.type);
+        }
+    }
     return CY_OK;
 }
 
@@ -1495,13 +2150,13 @@ static void src_coord_host(int d, double scale, int n, int* i0, int* i1) {
     *i0 = a;
     *i1 = a + 1 < n - 1 ? a + 1 : n - 1;
 }
-static constexpr int kFinBandH = 8;            // output rows per band of the fused final kernel
-static constexpr size_t kFinSmemMax = 100 * 1024;   // two CTAs per SM
+static constexpr int kFinBandH = 8;                 // output rows per band of the fused final kernel (<= 16)
+static constexpr size_t kFinSmemMax = 110 * 1024;   // two CTAs per SM
 
 static size_t fin_smem_bytes(int Sw, int rows, int Tx) {
-    return sizeof(cy::TileFinal) + (((size_t)Sw * 12 + 15) & ~(size_t)15) + (size_t)rows * Tx * 12;
+    return sizeof(cy::TileFinal) + (((size_t)Sw * 12 + 192 + 15) & ~(size_t)15) + (size_t)rows * Tx * 16;
 }
-// rows of shared memory the fused bands need (0: does not fit -> chain_out + pp_resize_kernel path)
+// rows of shared memory the fused bands need (0: does not fit -> chain image + pp_resize_kernel path)
 static int fin_rows_cap(const LbGeom& g, int Ty, int Tx) {
     int cap = 1;
     for (int oy0 = 0; oy0 < g.Sh; oy0 += kFinBandH) {
@@ -1516,85 +2171,172 @@ static int fin_rows_cap(const LbGeom& g, int Ty, int Tx) {
     return fin_smem_bytes(g.Sw, cap, Tx) <= kFinSmemMax ? cap : 0;
 }
 
+struct BkGeom {
+    int nsub, R, nchunks, nbs;
+};
+static int bk_geometry(const cy_pp_chain* ch, int Ty, int Tx, BkGeom* g) {
+    if (Tx > cy::kChunk) return cy::set_error(CY_ERR_INVALID, "cy_preprocess: tiles wider than %d pixels are not supported", cy::kChunk);
+    g->nsub = 1;
+    for (int i = 0; i < ch->nstages; ++i)
+        if (stage_uses_box_stats(ch->st[i])) g->nsub = 2;
+    g->R = cy::kChunk / Tx;
+    if (g->R > 256) g->R = 256;
+    if (g->R < 1) g->R = 1;
+    g->nchunks = (Ty + g->R - 1) / g->R;
+    g->nbs = cy::kNB * g->nsub;
+    return CY_OK;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 pp_get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+extern "C" size_t cy_preprocess_chain_scratch_bytes(const cy_pp_chain* ch, int B, int Ty, int Tx) {
+    if (!ch || B <= 0 || Ty <= 0 || Tx <= 0) return 0;
+    BkGeom g;
+    if (bk_geometry(ch, Ty, Tx, &g)) return 0;
+    const size_t N = (size_t)Ty * Tx, b = (size_t)B;
+    size_t t = align256(b * sizeof(cy::TileFinal)) + 256;
+    if (ch->nstages > 0)
+        t += align256(b * sizeof(cy::TileHdr)) + align256(b * N * 4) + align256(b * g.nchunks * (g.nbs + 1) * 2) +
+             align256(b * (g.nchunks + 1) * 4) + 3 * align256(b * g.nbs * 4) + 2 * align256(b * g.nbs * 8);
+    return t;
+}
+
 extern "C" size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg, int B, int Ty, int Tx) {
-    const size_t N = (size_t)Ty * Tx;
-    const int nbuf = 3 + ((cfg && cfg->enabled && cfg->subtract_bkg && cfg->use_box_mask_in_bkg) ? 1 : 0);
-    // + the per-tile final maps + (tiles too large for the fused final kernel) the fp32 HWC chain image
-    return (size_t)nbuf * align256((size_t)B * N * 4) + 2 * align256((size_t)B * 4) + align256((size_t)B * sizeof(cy::TileFinal)) +
-           align256((size_t)B * N * 12) + 256;
+    cy_pp_chain ch;
+    if (!cfg || cy_pp_chain_from_config(cfg, &ch)) return 0;
+    return cy_preprocess_chain_scratch_bytes(&ch, B, Ty, Tx);
 }
 
 extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long row_stride, int big_endian,
                              const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz,
                              float* chain_out, void* model_in, float* model_in_f32, int32_t* status, void* scratch,
                              uintptr_t stream) {
+    if (!cfg) return cy::set_error(CY_ERR_INVALID, "cy_preprocess: null argument");
+    cy_pp_chain ch;
+    int rc = cy_pp_chain_from_config(cfg, &ch);
+    if (rc) return rc;
+    return cy_preprocess_chain(&ch, img, row_stride, big_endian, tile_x0, tile_y0, B, Ty, Tx, imgsz, chain_out, model_in,
+                               model_in_f32, status, scratch, stream);
+}
+
+extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img, long long row_stride, int big_endian,
+                                   const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz,
+                                   float* chain_out, void* model_in, float* model_in_f32, int32_t* status, void* scratch,
+                                   uintptr_t stream) {
     using namespace cy;
-    if (!cfg || !img || !tile_x0 || !tile_y0 || !status || !scratch)
+    if (!chain_in || !img || !tile_x0 || !tile_y0 || !status || !scratch)
         return set_error(CY_ERR_INVALID, "cy_preprocess: null argument");
     if (!chain_out && !model_in) return set_error(CY_ERR_INVALID, "cy_preprocess: no output requested");
     if (B <= 0 || Ty <= 0 || Tx <= 0) return set_error(CY_ERR_INVALID, "cy_preprocess: invalid shape");
     if ((long long)Ty * Tx >= (1ll << 30)) return set_error(CY_ERR_INVALID, "cy_preprocess: tile too large");
     if (B > 65535) return set_error(CY_ERR_INVALID, "cy_preprocess: at most 65535 tiles per call");
-    if (cfg->enabled) {
-        if (cfg->nchannels != 1 && cfg->nchannels != 3)
-            return set_error(CY_ERR_INVALID, "nchannels must be 1 or 3 (the model takes 3-channel images)");
-        if (cfg->chan3_preproc && cfg->nchannels != 3)
-            return set_error(CY_ERR_INVALID, "chan3_preproc requires nchannels == 3 (scripts/run.py:253-256)");
-    }
+    cy_pp_chain chain = *chain_in;
+    int rc = cy_pp_chain_validate(&chain);
+    if (rc) return rc;
+    BkGeom g;
+    if ((rc = bk_geometry(&chain, Ty, Tx, &g))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     PPParams p;
-    p.cfg = *cfg;
+    memset(&p, 0, sizeof(p));
+    p.chain = chain;
     p.img = (const uint32_t*)img;
     p.row_stride = row_stride;
     p.big_endian = big_endian;
     p.x0 = tile_x0;
     p.y0 = tile_y0;
     p.B = B; p.Ty = Ty; p.Tx = Tx;
-    const size_t N = (size_t)Ty * Tx;
-    const size_t buf = align256((size_t)B * N * 4);
-    char* s = (char*)scratch;
-    p.tilebuf = (float*)s; s += buf;
-    p.keysA = (uint32_t*)s; s += buf;
-    p.keysB = (uint32_t*)s; s += buf;
-    const bool box = cfg->enabled && cfg->subtract_bkg && cfg->use_box_mask_in_bkg;
-    p.keysC = nullptr;
-    if (box) {
-        p.keysC = (uint32_t*)s;
-        s += buf;
+    p.nsub = g.nsub; p.rows_per_chunk = g.R; p.nchunks = g.nchunks; p.nbs = g.nbs;
+    // box geometry (preprocessing.py:610-621): xc = int(W/2), dx = int(W * fract / 2), rows / cols [c - d, c + d)
+    p.bx0 = p.by0 = 0; p.bx1 = Tx; p.by1 = Ty;
+    for (int i = 0; i < chain.nstages; ++i) {
+        const cy_pp_stage& s = chain.st[i];
+        if (stage_uses_box_stats(s) || s.type == CY_PP_BORDER_MASK) {
+            const double f = stage_box_fract(s);
+            const int xc = Tx / 2, yc = Ty / 2, dy = (int)(Ty * f / 2.0), dx = (int)(Tx * f / 2.0);
+            p.bx0 = xc - dx; p.bx1 = xc + dx; p.by0 = yc - dy; p.by1 = yc + dy;
+            if (s.type == CY_PP_BORDER_MASK) p.border_mask = 1;
+        }
     }
-    p.nlive = (int*)s; s += align256((size_t)B * 4);
-    p.nbox = (int*)s; s += align256((size_t)B * 4);
-    p.fin = (TileFinal*)s; s += align256((size_t)B * sizeof(TileFinal));
-    float* chain_scratch = (float*)s;
+    const size_t N = (size_t)Ty * Tx, b = (size_t)B;
+    char* s = (char*)scratch;
+    p.fin = (TileFinal*)s; s += align256(b * sizeof(TileFinal));
+    if (chain.nstages > 0) {
+        p.hdr = (TileHdr*)s; s += align256(b * sizeof(TileHdr));
+        p.vals = (float*)s; s += align256(b * N * 4);
+        p.off = (unsigned short*)s; s += align256(b * g.nchunks * (g.nbs + 1) * 2);
+        p.cbase = (int*)s; s += align256(b * (g.nchunks + 1) * 4);
+        p.cnt = (int*)s; s += align256(b * g.nbs * 4);
+        p.bmin = (float*)s; s += align256(b * g.nbs * 4);
+        p.bmax = (float*)s; s += align256(b * g.nbs * 4);
+        p.m1 = (double*)s; s += align256(b * g.nbs * 8);
+        p.m2 = (double*)s; s += align256(b * g.nbs * 8);
+    }
     p.chain_out = chain_out;
     p.status = status;
     static std::atomic<unsigned long long> attr_done{0};
     if (first_use_on_device(attr_done)) {
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
-        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BkSmem)));
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemMax));
     }
-    pp_sort_kernel<<<B, kSortThreads, sizeof(SortSmem), st>>>(p);
+    if (chain.nstages > 0) {
+        // TMA staging of the chunks: 2-D boxes of pw x R pixels of the mosaic (16-byte aligned base / pitch / box rows)
+        CUtensorMap tm;
+        memset(&tm, 0, sizeof(tm));
+        p.pw = Tx <= 256 ? Tx : 256;
+        p.npanels = Tx / p.pw;
+        const char* no_tma = getenv("CY_PP_NO_TMA");
+        p.use_tma = !(no_tma && atoi(no_tma)) && ((uintptr_t)img % 16 == 0) && ((row_stride * 4) % 16 == 0) && (Tx % 4 == 0) &&
+                    (Tx % p.pw == 0) && Ty >= g.R && row_stride >= Tx;
+        if (p.use_tma) {
+            auto enc = pp_get_encode();
+            if (!enc) {
+                p.use_tma = 0;
+            } else {
+                const cuuint64_t dims[2] = {(cuuint64_t)row_stride, (cuuint64_t)1 << 30};
+                const cuuint64_t str[1] = {(cuuint64_t)row_stride * 4};
+                const cuuint32_t box[2] = {(cuuint32_t)p.pw, (cuuint32_t)g.R};
+                const cuuint32_t estr[2] = {1, 1};
+                CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)img, dims, str, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) p.use_tma = 0;
+            }
+        }
+        if (!p.use_tma) { p.pw = Tx; p.npanels = 1; }
+        pp_bucket_kernel<<<B, kBkThreads, sizeof(BkSmem), st>>>(p, tm);
+    }
     pp_chain_kernel<<<B, kPPThreads, sizeof(Shared), st>>>(p);
     CY_CUDA_CHECK(cudaGetLastError());
 
-    LbGeom g;
-    int rc = lb_geometry(Ty, Tx, imgsz, &g);
-    if (rc) return rc;
+    LbGeom lg;
+    if ((rc = lb_geometry(Ty, Tx, imgsz, &lg))) return rc;
     FinalParams r;
+    memset(&r, 0, sizeof(r));
     r.p = p;
     r.out16 = model_in;
     r.out_f32 = model_in_f32;
-    r.Sh = g.Sh; r.Sw = g.Sw; r.new_h = g.new_h; r.new_w = g.new_w; r.top = g.top; r.left = g.left;
-    r.scale_y = g.scale_y; r.scale_x = g.scale_x;
-    r.f16 = cfg->out_f16 ? 1 : 0;
+    r.Sh = lg.Sh; r.Sw = lg.Sw; r.new_h = lg.new_h; r.new_w = lg.new_w; r.top = lg.top; r.left = lg.left;
+    r.scale_y = lg.scale_y; r.scale_x = lg.scale_x;
+    r.f16 = chain.out_f16 ? 1 : 0;
     const int sms = current_device_sms();
-    const int cap = model_in ? fin_rows_cap(g, Ty, Tx) : 0;
+    const int cap = model_in ? fin_rows_cap(lg, Ty, Tx) : 0;
     auto emit_chain = [&](float* dst) -> int {   // evaluated maps as an fp32 HWC image (parity output / resize input)
         FinalParams e = r;
         e.p.chain_out = dst;
         e.emit_only = 1;
-        const int rows_fit = (int)((kFinSmemMax - sizeof(TileFinal) - 64) / ((size_t)Tx * 12));
+        const int rows_fit = (int)((kFinSmemMax - sizeof(TileFinal) - 256) / ((size_t)Tx * 16));
         if (rows_fit < 1) return set_error(CY_ERR_INVALID, "cy_preprocess: tile rows of %d pixels do not fit shared memory", Tx);
         e.band_h = rows_fit < 8 ? rows_fit : 8;
         e.rows_cap = e.band_h;
@@ -1611,15 +2353,20 @@ extern "C" int cy_preprocess(const cy_pp_config* cfg, const void* img, long long
             r.emit_only = 0;
             r.band_h = kFinBandH;
             r.rows_cap = cap;
-            r.nbands = (g.Sh + kFinBandH - 1) / kFinBandH;
+            r.nbands = (lg.Sh + kFinBandH - 1) / kFinBandH;
             int chunks = (2 * sms + B - 1) / B;
             chunks = chunks < 1 ? 1 : (chunks > r.nbands ? r.nbands : chunks);
-            pp_final_kernel<<<dim3((unsigned)B, (unsigned)chunks), kFinThreads, fin_smem_bytes(g.Sw, cap, Tx), st>>>(r);
+            pp_final_kernel<<<dim3((unsigned)B, (unsigned)chunks), kFinThreads, fin_smem_bytes(lg.Sw, cap, Tx), st>>>(r);
         } else {
             // bands of this tile shape do not fit shared memory: materialise the fp32 HWC image once, then resize it
-            float* hwc = chain_out ? chain_out : chain_scratch;
-            if (!chain_out && (rc = emit_chain(hwc))) return rc;
+            float* hwc = chain_out;
+            if (!hwc) {
+                if (cudaMallocAsync(&hwc, b * N * 12, st) != cudaSuccess)
+                    return set_error(CY_ERR_NOMEM, "cy_preprocess: %zu bytes for the chain image", b * N * 12);
+                if ((rc = emit_chain(hwc))) return rc;
+            }
             rc = cy_letterbox_resize_fmt(hwc, B, Ty, Tx, imgsz, model_in, model_in_f32, r.f16, stream);
+            if (!chain_out) cudaFreeAsync(hwc, st);
             if (rc) return rc;
         }
     }

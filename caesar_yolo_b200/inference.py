@@ -186,7 +186,7 @@ class SFinder(object):
             plane[~np.isfinite(plane)] = 0
             eng.process_tiles(torch.from_numpy(plane).to(eng.device), W, False, 0, 0, [0])
         else:
-            if eng.pp_cfg.enabled:
+            if eng.pp_cfg.nstages > 0:
                 logger.error("Colour image with --preprocessing: the preprocessing chain of this build takes "
                              "single-plane images (FITS, grey PNG/JPG)")
                 return -1

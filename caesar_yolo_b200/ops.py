@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import (CaesarB200Error, PPConfig, Letterbox, c_int, c_float, c_double, c_i64, c_void_p, check, cur_stream,
+from ._capi import (CaesarB200Error, PPChain, PPConfig, Letterbox, c_int, c_float, c_double, c_i64, c_void_p, check, cur_stream,
                     lib, ptr)
 
 MAX_DET = 300          # ultralytics non_max_suppression max_det
@@ -69,6 +69,18 @@ def letterbox_shape(Ty, Tx, imgsz):
 DEFAULT_PRECISION = os.environ.get('CY_PRECISION', 'fp16')
 
 
+def chain_from_config(cfg):
+    """cy_pp_config (run.py's option set) -> cy_pp_chain (the stage list in run.py's order)."""
+    ch = PPChain()
+    check(lib.cy_pp_chain_from_config(ctypes.byref(cfg), ctypes.byref(ch)))
+    return ch
+
+
+def validate_chain(ch):
+    check(lib.cy_pp_chain_validate(ctypes.byref(ch)))
+    return ch
+
+
 def storage_dtype(precision):
     """torch dtype of the 16-bit storage format: 'fp16' or 'bf16' (None: DEFAULT_PRECISION)."""
     if precision is None:
@@ -87,6 +99,7 @@ def preprocess(cfg, img, row_stride, big_endian, tile_x0, tile_y0, Ty, Tx, imgsz
     status [B] i32).  want_chain=False skips the fp32 chain image (the production path: it only exists for parity)."""
     B = tile_x0.numel()
     dev = img.device
+    is_chain = isinstance(cfg, PPChain)     # a general stage list (cy_preprocess_chain) or run.py's option set
     Sh, Sw, _ = letterbox_shape(Ty, Tx, imgsz)
     if chain_out is None and want_chain:
         chain_out = torch.empty((B, Ty, Tx, 3), dtype=torch.float32, device=dev)
@@ -95,12 +108,16 @@ def preprocess(cfg, img, row_stride, big_endian, tile_x0, tile_y0, Ty, Tx, imgsz
     f32 = torch.empty((B, 3, Sh, Sw), dtype=torch.float32, device=dev) if want_f32 else None
     if status is None:
         status = torch.empty((B,), dtype=torch.int32, device=dev)
-    need = int(lib.cy_preprocess_scratch_bytes(ctypes.byref(cfg), c_int(B), c_int(Ty), c_int(Tx)))
+    size_fn = lib.cy_preprocess_chain_scratch_bytes if is_chain else lib.cy_preprocess_scratch_bytes
+    need = int(size_fn(ctypes.byref(cfg), c_int(B), c_int(Ty), c_int(Tx)))
+    if need == 0:
+        raise CaesarB200Error("invalid preprocessing chain / tile shape: %s" % lib.cy_last_error().decode())
     if scratch is None or scratch.numel() < need:
         scratch = torch.empty((need,), dtype=torch.uint8, device=dev)
-    check(lib.cy_preprocess(ctypes.byref(cfg), ptr(img), c_i64(row_stride), c_int(1 if big_endian else 0),
-                            ptr(tile_x0), ptr(tile_y0), c_int(B), c_int(Ty), c_int(Tx), c_int(imgsz), ptr(chain_out),
-                            ptr(model_in), ptr(f32), ptr(status), ptr(scratch), cur_stream()))
+    fn = lib.cy_preprocess_chain if is_chain else lib.cy_preprocess
+    check(fn(ctypes.byref(cfg), ptr(img), c_i64(row_stride), c_int(1 if big_endian else 0),
+             ptr(tile_x0), ptr(tile_y0), c_int(B), c_int(Ty), c_int(Tx), c_int(imgsz), ptr(chain_out),
+             ptr(model_in), ptr(f32), ptr(status), ptr(scratch), cur_stream()))
     return chain_out, model_in, f32, status
 
 

@@ -1,7 +1,7 @@
 """Host-side driver of the B200 hot path: FITS mosaic -> tiles -> preprocessing -> YOLOv8 forward -> decode/NMS ->
 per-tile merge -> records -> (all-gather) -> cross-tile merge -> catalog.  Python only orchestrates; every stage is a
 CUDA kernel behind the C ABI (ops.py)."""
-from ._capi import PPConfig
+from ._capi import PPChain, PPConfig
 
 
 def make_pp_config(enabled=True, subtract_bkg=False, sigma_bkg=3.0, use_box_mask_in_bkg=False, bkg_box_mask_fract=0.7,
@@ -68,7 +68,12 @@ class Engine(object):
         self.nc = self.model.nc
         self.names = self.model.names
         src_cfg = pp_cfg if pp_cfg is not None else make_pp_config(enabled=False)
-        self.pp_cfg = PPConfig.from_buffer_copy(src_cfg)         # private copy: the output format follows the model
+        # private copy of the stage list (a cy_pp_config is expanded to run.py's stage order): the output format
+        # follows the model
+        if isinstance(src_cfg, PPChain):
+            self.pp_cfg = ops.validate_chain(PPChain.from_buffer_copy(src_cfg))
+        else:
+            self.pp_cfg = ops.chain_from_config(src_cfg)
         self.pp_cfg.out_f16 = 1 if self.model.dtype == torch.float16 else 0
         self.imgsz = int(imgsz)
         self.score_thr, self.iou_thr = float(score_thr), float(iou_thr)
@@ -163,7 +168,7 @@ class Engine(object):
         chain = self._get('chain', (G, Ty, Tx, 3), torch.float32) if want_chain else None
         model_in = self._get('model_in', (G, Sh, Sw, 4), self.model.dtype)
         status = self._get('pp_status', (G,), torch.int32)
-        need = int(ops.lib.cy_preprocess_scratch_bytes(ops.ctypes.byref(self.pp_cfg), G, Ty, Tx))
+        need = int(ops.lib.cy_preprocess_chain_scratch_bytes(ops.ctypes.byref(self.pp_cfg), G, Ty, Tx))
         scratch = self._get('pp_scratch', (need,), torch.uint8)
         e = self._mark()
         ops.preprocess(self.pp_cfg, img_dev, row_stride, big_endian, x0, y0, Ty, Tx, self.imgsz, scratch=scratch,
@@ -218,7 +223,7 @@ class Engine(object):
 
     def pp_kernels(self):
         """Names of the preprocessing kernels cy_preprocess launches for this configuration (bench.py's roofline)."""
-        return "pp_sort_kernel + pp_chain_kernel + pp_final_kernel"
+        return "pp_bucket_kernel + pp_chain_kernel + pp_final_kernel"
 
     def finish(self):
         """Compacts the per-tile record slots -> (packed uint8 tensor of n cy_det_record, n) in tile-id order.

@@ -52,6 +52,44 @@ typedef struct {
     int32_t out_f16;             /* model_in format: 0 = bf16, 1 = fp16 (must match cy_model_set_precision) */
 } cy_pp_config;
 
+/* General preprocessing chain = caesar_yolo/preprocessing.py's DataPreprocessor(stages) for ANY stage order
+ * (preprocessing.py:47-67): a list of stage records interpreted by the chain kernel.  Stage parameters:
+ *   BKG_SUB          p0 sigma, flag use_mask_box, p1 mask_fract, chid                          (:591-658)
+ *   CLIP_SHIFT       p0 sigma, chid                                                            (:664-717)
+ *   SIGMA_CLIP       p0 sigma_low, p1 sigma_up, chid                                           (:723-771)
+ *   CHAN_RESIZE      n nchans (1 or 3: the cube Analyzer.predict builds already has 3 channels) (:1077-1133)
+ *   ZSCALE           p0..p2 contrasts, n = number of contrasts given (< 3 => every tile rejected, :955-957) (:934-971)
+ *   CHAN3            p0 sigma_clip_baseline, p1 sigma_clip_low, p2 sigma_clip_up, p3 zscale_contrast (:1020-1072)
+ *   MINMAX           p0 norm_min, p1 norm_max                                                  (:75-111)
+ *   ABS_MINMAX       p0 norm_min, p1 norm_max                                                  (:116-146)
+ *   MAX_SCALE        -                                                                         (:152-176)
+ *   ABS_MAX_SCALE    flag use_mask_box, p0 mask_fract                                          (:182-226)
+ *   CHAN_MAX_SCALE   n chref, flag use_mask_box, p0 mask_fract                                 (:232-288)
+ *   MIN_SHIFT        chid                                                                      (:294-327)
+ *   SHIFT            p0..p2 offsets, n = number given (!= 3 => every tile rejected)            (:333-363)
+ *   STANDARDIZE      p0..p2 means, p3..p5 sigmas, n = min(len(means), len(sigmas)) (!= 3 => rejected) (:369-402)
+ *   NEG_FIX          -                                                                         (:408-440)
+ *   LOG_STRETCH      chid = EXCLUDED channel (-1 none), flag bit0 minmaxnorm (required), bit1 clip_neg,
+ *                    p0 data_norm_min, p1 data_norm_max                                        (:480-538)
+ *   BORDER_MASK      p0 mask_fract; only before any stage that computes statistics             (:544-586)
+ *   HISTEQ           - (non-adaptive)                                                          (:977-1012)
+ * chid = -1: all channels. */
+enum {
+    CY_PP_BKG_SUB = 1, CY_PP_CLIP_SHIFT = 2, CY_PP_SIGMA_CLIP = 3, CY_PP_CHAN_RESIZE = 4, CY_PP_ZSCALE = 5,
+    CY_PP_CHAN3 = 6, CY_PP_MINMAX = 7, CY_PP_ABS_MINMAX = 8, CY_PP_MAX_SCALE = 9, CY_PP_ABS_MAX_SCALE = 10,
+    CY_PP_CHAN_MAX_SCALE = 11, CY_PP_MIN_SHIFT = 12, CY_PP_SHIFT = 13, CY_PP_STANDARDIZE = 14, CY_PP_NEG_FIX = 15,
+    CY_PP_LOG_STRETCH = 16, CY_PP_BORDER_MASK = 17, CY_PP_HISTEQ = 18
+};
+#define CY_PP_MAX_STAGES 16
+typedef struct { int32_t type, chid, flag, n; double p[8]; } cy_pp_stage;
+typedef struct {
+    int32_t nstages;
+    int32_t out_f16;       /* model_in format: 0 = bf16, 1 = fp16 */
+    int32_t reject_all;    /* set by cy_pp_chain_validate: the reference returns None for every image */
+    int32_t reserved;
+    cy_pp_stage st[CY_PP_MAX_STAGES];
+} cy_pp_chain;
+
 const char* cy_last_error(void);
 int cy_version(void);
 /* CY_OK iff the current device is sm_100. */
@@ -84,8 +122,20 @@ int cy_tile_neighbors(const cy_tile* tiles_host, int T, int* nb_off_host, int* n
  *                                input (fp16 when cfg->out_f16)
  * model_in_f32 (optional) [B,3,Sh,Sw] fp32 NCHW: the same before bf16 rounding (parity entry)
  * status [B]: 0 ok, -1 tile rejected like the reference (preprocess returned None / constant rows,
- *             evaluation.py:164-176), -3 degenerate statistics (empty clip set). */
+ *             evaluation.py:164-176), -3 degenerate statistics (empty clip set), -6 a stage met data this build does
+ *             not handle (order-reversing scale: non-positive maximum / sigma). */
 int cy_letterbox_shape(int Ty, int Tx, int imgsz, int* Sh_host, int* Sw_host, cy_letterbox* lb_host);
+/* run.py's option set -> stage list in run.py's order (scripts/run.py:272-293).  cfg->enabled == 0: empty chain. */
+int cy_pp_chain_from_config(const cy_pp_config* cfg_host, cy_pp_chain* chain_host);
+/* Checks a stage list (unknown types, stage combinations this build does not implement: CY_ERR_INVALID with the
+ * reason in cy_last_error) and fills chain->reject_all. */
+int cy_pp_chain_validate(cy_pp_chain* chain_host);
+size_t cy_preprocess_chain_scratch_bytes(const cy_pp_chain* chain_host, int B, int Ty, int Tx);
+/* cy_preprocess for a general stage list (same buffers and semantics). */
+int cy_preprocess_chain(const cy_pp_chain* chain_host, const void* img, long long row_stride, int big_endian,
+                        const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz,
+                        float* chain_out, void* model_in, float* model_in_f32, int32_t* status, void* scratch,
+                        uintptr_t stream);
 size_t cy_preprocess_scratch_bytes(const cy_pp_config* cfg_host, int B, int Ty, int Tx);
 int cy_preprocess(const cy_pp_config* cfg_host, const void* img, long long row_stride, int big_endian,
                   const int32_t* tile_x0, const int32_t* tile_y0, int B, int Ty, int Tx, int imgsz, float* chain_out,
@@ -108,8 +158,6 @@ int cy_conv_block_n(int cout);
 /* Diagnostics (tools/conv_probe.py): per-CTA clock64 timeline buffer for the conv kernel (NULL disables); the plan the
  * kernel would use for a shape: info8 = {mode, halves, units, block_n, a_stages, b_stages, acc_bufs, grid}. */
 int cy_conv_set_debug(void* dev_buf, int units_per_cta);
-/* Diagnostics: phase cycle sums (8 x int64) of block 0 of the tile sort kernel; NULL disables. */
-int cy_sort_set_debug(void* dev_buf);
 int cy_conv_plan_info(int B, int Hin, int Win, int cin, int cout, int ksize, int stride, int* info8);
 int cy_conv2d_nhwc(const void* in, int B, int Hin, int Win, int in_ctot, int in_coff, int cin, const void* w,
                    const float* bias, int cout, int cout_pad, int ksize, int stride, void* out, int out_ctot,

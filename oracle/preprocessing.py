@@ -262,3 +262,236 @@ def build_stages(subtract_bkg=False, sigma_bkg=3, use_box_mask_in_bkg=False, bkg
     if normalize_minmax:
         st.append(MinMaxNormalizer(norm_min=norm_min, norm_max=norm_max))
     return st
+
+
+# ------------------------------------------------------------------------------------------------ other operators
+# (the classes of caesar_yolo/preprocessing.py that run.py never instantiates)
+
+def _cond(data):
+    return np.logical_and(data != 0, np.isfinite(data))
+
+
+def _box(shape, fract):
+    """Central box of BkgSubtractor / AbsMaxScaler / ChanMaxScaler / BorderMasker (e.g. preprocessing.py:200-207)."""
+    xc, yc = int(shape[1] / 2), int(shape[0] / 2)
+    dy, dx = int(shape[0] * fract / 2.), int(shape[1] * fract / 2.)
+    return yc - dy, yc + dy, xc - dx, xc + dx
+
+
+class AbsMinMaxNormalizer(object):
+    """caesar_yolo/preprocessing.py:116-146."""
+
+    def __init__(self, norm_min=0, norm_max=1, **kw):
+        self.norm_min, self.norm_max = norm_min, norm_max
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        cond = _cond(data)
+        masked = np.ma.masked_where(~cond, data, copy=False)
+        mn, mx = masked.min(), masked.max()
+        with np.errstate(all="ignore"):
+            out = (data - mn) / (mx - mn) * (self.norm_max - self.norm_min) + self.norm_min
+        out = np.asarray(np.ma.filled(out, 0.0), dtype=np.float64)
+        out[~cond] = 0
+        return out
+
+
+class MaxScaler(object):
+    """caesar_yolo/preprocessing.py:152-176."""
+
+    def __init__(self, **kw):
+        pass
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        cond = _cond(data)
+        masked = np.ma.masked_where(~cond, data, copy=False)
+        mx = masked.max(axis=(0, 1)).data
+        with np.errstate(all="ignore"):
+            out = data / mx
+        out[~cond] = 0
+        return out
+
+
+class AbsMaxScaler(object):
+    """caesar_yolo/preprocessing.py:182-226."""
+
+    def __init__(self, use_mask_box=False, mask_fract=0.5, **kw):
+        self.use_mask_box, self.mask_fract = use_mask_box, mask_fract
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        cond = _cond(data)
+        cond_max = cond
+        if self.use_mask_box:
+            y0, y1, x0, x1 = _box(data.shape, self.mask_fract)
+            m = np.zeros(data.shape)
+            m[y0:y1, x0:x1, :] = 1
+            cond_max = np.logical_and(cond, m == 1)
+        mx = np.ma.masked_where(~cond_max, data, copy=False).max()
+        with np.errstate(all="ignore"):
+            out = np.asarray(np.ma.filled(data / mx, 0.0), dtype=np.float64)
+        out[~cond] = 0
+        return out
+
+
+class ChanMaxScaler(object):
+    """caesar_yolo/preprocessing.py:232-288."""
+
+    def __init__(self, chref=0, use_mask_box=False, mask_fract=0.5, **kw):
+        self.chref, self.use_mask_box, self.mask_fract = chref, use_mask_box, mask_fract
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        cond = _cond(data)
+        sl = (slice(None), slice(None))
+        if self.use_mask_box:
+            y0, y1, x0, x1 = _box(data.shape[:2], self.mask_fract)
+            sl = (slice(y0, y1), slice(x0, x1))
+        ref = data[sl + (self.chref,)]
+        mx = np.ma.masked_where(~_cond(ref), ref, copy=False).max()
+        for i in range(data.shape[-1]):
+            ch = data[sl + (i,)]
+            v = ch[_cond(ch)]
+            if v.size == 0:
+                raise ValueError("zero-size array to reduction operation maximum which has no identity")
+            m = v.max()
+            if m <= 0 or not np.isfinite(m):
+                return None
+        with np.errstate(all="ignore"):
+            out = data / mx
+        out[~cond] = 0
+        return out
+
+
+class MinShifter(object):
+    """caesar_yolo/preprocessing.py:294-327."""
+
+    def __init__(self, **kw):
+        self.chid = kw.get('chid', -1)
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        out = np.copy(data)
+        for i in range(data.shape[-1]):
+            if self.chid != -1 and i != self.chid:
+                continue
+            ch = data[:, :, i]
+            cond = _cond(ch)
+            sh = ch - ch[cond].min()
+            sh[~cond] = 0
+            out[:, :, i] = sh
+        return out
+
+
+class Shifter(object):
+    """caesar_yolo/preprocessing.py:333-363."""
+
+    def __init__(self, offsets, **kw):
+        self.offsets = offsets
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        if len(self.offsets) <= 0 or len(self.offsets) != data.shape[2]:
+            return None
+        cond = _cond(data)
+        out = data - self.offsets
+        out[~cond] = 0
+        return out
+
+
+class Standardizer(object):
+    """caesar_yolo/preprocessing.py:369-402."""
+
+    def __init__(self, means, sigmas, **kw):
+        self.means, self.sigmas = means, sigmas
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        n = data.shape[2]
+        if len(self.means) <= 0 or len(self.means) != n or len(self.sigmas) <= 0 or len(self.sigmas) != n:
+            return None
+        cond = _cond(data)
+        out = (data - self.means) / self.sigmas
+        out[~cond] = 0
+        return out
+
+
+class NegativeDataFixer(object):
+    """caesar_yolo/preprocessing.py:408-440."""
+
+    def __init__(self, **kw):
+        pass
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        out = np.copy(data)
+        for i in range(data.shape[-1]):
+            ch = data[:, :, i]
+            cond = _cond(ch)
+            v = ch[cond]
+            if v.max() > 0:
+                continue
+            sh = ch - v.min()
+            sh[~cond] = 0
+            out[:, :, i] = sh
+        return out
+
+
+class LogStretcher(object):
+    """caesar_yolo/preprocessing.py:480-538."""
+
+    def __init__(self, chid=-1, minmaxnorm=False, data_norm_min=-6, data_norm_max=6, clip_neg=False, **kw):
+        self.chid, self.minmaxnorm = chid, minmaxnorm
+        self.data_norm_min, self.data_norm_max, self.clip_neg = data_norm_min, data_norm_max, clip_neg
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        out = np.copy(data)
+        for i in range(data.shape[-1]):
+            if self.chid != -1 and i == self.chid:
+                continue
+            ch = data[:, :, i]
+            bad = np.logical_or(ch == 0, ~np.isfinite(ch))
+            pos = np.logical_and(ch > 0, np.isfinite(ch))
+            if ch[pos].size <= 0:
+                return None
+            lg = np.zeros_like(ch)
+            lg[pos] = np.log10(ch[pos])
+            lg[~pos] = lg[pos].min()
+            if self.minmaxnorm:
+                lg = (lg - self.data_norm_min) / (self.data_norm_max - self.data_norm_min)
+                if self.clip_neg:
+                    lg[lg < 0] = 0
+                lg[bad] = 0
+            out[:, :, i] = lg
+        return out
+
+
+class BorderMasker(object):
+    """caesar_yolo/preprocessing.py:544-586."""
+
+    def __init__(self, mask_fract=0.7, **kw):
+        self.mask_fract = mask_fract
+
+    def __call__(self, data):
+        if data is None:
+            return None
+        out = np.copy(data)
+        y0, y1, x0, x1 = _box(data.shape[:2], self.mask_fract)
+        for i in range(data.shape[-1]):
+            ch = np.copy(data[:, :, i])
+            m = np.zeros(ch.shape)
+            m[y0:y1, x0:x1] = 1
+            ch[m == 0] = 0
+            out[:, :, i] = ch
+        return out

@@ -43,11 +43,22 @@ def test_stage_order_and_parameters():
     assert [type(s).__name__ for s in st] == ['BkgSubtractor', 'SigmaClipShifter', 'SigmaClipper', 'ChanResizer',
                                               'ZScaleTransformer', 'Chan3Trasformer', 'MinMaxNormalizer']
     from caesar_yolo_b200.preprocessing import DataPreprocessor
-    cfg = DataPreprocessor(st).pp_config
-    assert cfg.subtract_bkg == 1 and cfg.clip_shift_data == 1 and cfg.clip_data == 1 and cfg.zscale_stretch == 1
-    assert cfg.chan3_preproc == 1 and cfg.normalize_minmax == 1 and cfg.nchannels == 3
-    assert cfg.sigma_clip_low == 4.0 and cfg.norm_max == 255.0
-    assert [cfg.zscale_contrasts[i] for i in range(3)] == [0.3, 0.2, 0.1]
+    from caesar_yolo_b200 import _capi
+    ch = DataPreprocessor(st).pp_config                     # cy_pp_chain: the stage list in the same order
+    assert ch.nstages == 7 and ch.reject_all == 0
+    assert [ch.st[i].type for i in range(7)] == [_capi.PP_BKG_SUB, _capi.PP_CLIP_SHIFT, _capi.PP_SIGMA_CLIP,
+                                                 _capi.PP_CHAN_RESIZE, _capi.PP_ZSCALE, _capi.PP_CHAN3, _capi.PP_MINMAX]
+    assert ch.st[2].p[0] == 4.0 and ch.st[3].n == 3 and ch.st[6].p[1] == 255.0
+    assert [ch.st[4].p[i] for i in range(3)] == [0.3, 0.2, 0.1] and ch.st[4].n == 3
+    assert ch.st[5].p[1] == 4.0 and ch.st[5].p[3] == 0.3    # Chan3Trasformer: sigma_clip_low, zscale_contrasts[0]
+    # the same flags through the C entry that expands run.py's option set
+    from caesar_yolo_b200 import ops, pipeline
+    ch2 = ops.chain_from_config(pipeline.make_pp_config(
+        subtract_bkg=True, clip_shift_data=True, clip_data=True, sigma_clip_low=4, nchannels=3, zscale_stretch=True,
+        zscale_contrasts=(0.3, 0.2, 0.1), chan3_preproc=True, normalize_minmax=True, norm_max=255.))
+    assert ch2.nstages == 7
+    for i in range(7):
+        assert ch2.st[i].type == ch.st[i].type and [ch2.st[i].p[k] for k in range(4)] == [ch.st[i].p[k] for k in range(4)]
 
 
 def test_validation_errors_return_1(tmp_path):

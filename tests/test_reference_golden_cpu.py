@@ -143,3 +143,47 @@ def test_capi_tiling_and_neighbours_match_reference(gold):
         tiles = ops.generate_tiles(*c['tile_args'])
         off, idx = ops.tile_neighbors(tiles)
         assert [sorted(int(v) for v in idx[off[i]:off[i + 1]]) for i in range(len(tiles))] == c['neighbors']
+
+
+def test_other_preprocessing_operators_match_reference():
+    """oracle/preprocessing.py's restatement of the operators run.py never instantiates, and of stage orders other than
+    run.py's, against outputs of the reference's own classes (tests/golden/make_ref_golden_f3.py): bit-identical."""
+    from oracle import preprocessing as opp
+    meta = json.load(open(os.path.join(GOLD, 'ref_preproc_f3.json')))['chains']
+    arr = np.load(os.path.join(GOLD, 'ref_preproc_f3.npz'))
+    assert len(meta) >= 25
+    for name, m in meta.items():
+        x = arr['img__' + m['image']]
+        cube = np.zeros(x.shape + (3,))
+        for c in range(3):
+            cube[:, :, c] = x
+        dp = opp.DataPreprocessor([getattr(opp, cn)(**kw) for cn, kw in m['chain']])
+        y = dp(np.copy(cube))
+        if m['none']:
+            assert y is None, name
+        else:
+            assert y is not None, name
+            assert np.array_equal(np.asarray(y, dtype=np.float64), arr[name]), name
+
+
+def test_chain_compiler_accepts_any_order_and_refuses_what_is_not_implemented():
+    """caesar_yolo_b200.preprocessing: every reference class name exists; unsupported combinations raise
+    NotImplementedError when the chain is compiled (never silently approximated); Scaler raises like the reference."""
+    from caesar_yolo_b200 import preprocessing as P
+    for cn in ('MinMaxNormalizer', 'AbsMinMaxNormalizer', 'MaxScaler', 'AbsMaxScaler', 'ChanMaxScaler', 'MinShifter',
+               'Shifter', 'Standardizer', 'NegativeDataFixer', 'Scaler', 'LogStretcher', 'BorderMasker', 'BkgSubtractor',
+               'SigmaClipShifter', 'SigmaClipper', 'Resizer', 'ChanDivider', 'ZScaleTransformer', 'HistEqualizer',
+               'Chan3Trasformer', 'ChanResizer', 'DataPreprocessor'):
+        assert hasattr(P, cn), cn
+    dp = P.DataPreprocessor([P.MinMaxNormalizer(), P.BkgSubtractor(sigma=3), P.ZScaleTransformer(), P.MaxScaler()])
+    assert dp.pp_chain.nstages == 4 and dp.pp_chain.reject_all == 0
+    assert P.DataPreprocessor([P.ZScaleTransformer(contrasts=[0.25])]).pp_chain.reject_all == 1
+    assert P.DataPreprocessor([P.Shifter(offsets=[1, 2])]).pp_chain.reject_all == 1
+    with pytest.raises(AttributeError):
+        P.Scaler([1, 1, 1])
+    for bad in ([P.Resizer(64)], [P.ChanDivider()], [P.LogStretcher()], [P.HistEqualizer(adaptive=True)],
+                [P.BkgSubtractor(), P.BorderMasker()], [P.HistEqualizer(), P.Chan3Trasformer()],
+                [P.BkgSubtractor(use_mask_box=True, mask_fract=0.7), P.AbsMaxScaler(use_mask_box=True, mask_fract=0.5)],
+                [lambda x: x]):
+        with pytest.raises(NotImplementedError):
+            P.DataPreprocessor(bad)
