@@ -287,7 +287,9 @@ pp_bucket_kernel(const __grid_constant__ PPParams p, const __grid_constant__ CUt
         for (int q = 0; q < p.npanels; ++q)
             tma_load_2d(&sm.raw[q * R * p.pw], &tm, mbar, tx0 + q * p.pw, ty0 + ch * R);
     };
-    const int full_chunks = p.use_tma ? Ty / R : 0;     // chunks loaded by TMA (a partial last chunk is read directly)
+    // chunks loaded by TMA (a partial last chunk is read directly): the box start must be 16-byte aligned, i.e. the
+    // tile's first column a multiple of 4 pixels (pitch and base are checked on the host)
+    const int full_chunks = (p.use_tma && (tx0 & 3) == 0) ? Ty / R : 0;
     if (tid == 0) {
         mbar_init(mbar, 1);
         fence_mbar_init();
