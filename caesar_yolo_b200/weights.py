@@ -211,15 +211,50 @@ def _load_calibration(variant, seed):
     return None
 
 
-def make_random_weights(variant='n', nc=5, seed=0, cls_bias=-3.0, calibration='auto'):
+# Random-init recipes.  Both draw the same backbone (conv weights ~ N(0, 1/fan_in), calibrated BN); they
+# differ in the Detect head only.
+#   'v1' (round 1): random DFL head (boxes of random aspect, 2-10 cells), all three pyramid levels fire, class gain 2.5
+#        (sigmoid saturates: scores 0.99-1.0).  Overlapping candidates with near-tied scores everywhere -- NMS and the
+#        IoU-graph merge pick the winner of a near-tie, which any change of arithmetic flips.
+#   'v2' ("separated peaks"): a well-conditioned decision structure for the end-to-end acceptance test --
+#        * the DFL head decodes every anchor to (almost) the same square box of 2 x 2.1 cells: neighbouring candidates
+#          overlap by FIXED IoUs, (1,0) 0.62, (1,1) 0.42, (2,0) 0.36, (2,1) 0.26, all >= 14 % away from the NMS (0.5)
+#          and soft-merge (0.3) thresholds, so a blob of candidates collapses to its single best member;
+#        * class gain 1.0: logits of the detections spread over 0..7, where the fp32 sigmoid still resolves them;
+#        * only the stride-8 level fires (class bias -100 on P4 / P5): no cross-level pairs sitting at IoU 0.25.
+#        What is left is the irreducible part: score-threshold crossings and true near-ties of the two best members of
+#        a blob, ~0.2 % of the sources with fp16 storage (tests/diag/recipe_probe.py).
+RECIPES = {
+    'v1': dict(bn_beta=0.0, bn_beta_jit=0.1, dfl_gain=1.5, dfl_center=None, dfl_beta=0.6, cls_gain=2.5, levels=None),
+    'v2': dict(bn_beta=0.0, bn_beta_jit=0.1, dfl_gain=0.05, dfl_center=2.14, dfl_beta=2.0, cls_gain=1.0, levels=(0,)),
+}
+# class-branch bias of the v2 recipe per variant: ~8 detections per 512^2 tile of the synthetic mosaics at scoreThr 0.5
+V2_CLS_BIAS = {'n': -4.6, 'l': -4.6}
+
+
+def _load_calibration_key(key):
+    if os.path.exists(_CALIB_PATH):
+        with open(_CALIB_PATH) as f:
+            return json.load(f).get(key)
+    return None
+
+
+def calibration_key(variant, seed, recipe='v1'):
+    """The BN calibration depends on the backbone draw only, which the recipes share."""
+    return '%s:%d' % (variant, seed)
+
+
+def make_random_weights(variant='n', nc=5, seed=0, cls_bias=-3.0, calibration='auto', recipe='v1', **knobs):
     """Seeded random-init YOLOv8 (our own init; the reference has none).  Conv weights ~ N(0, 1/fan_in); the BN
     running statistics come from init_calibration.json (per-layer scalar mean/var of the pre-BN activation on a
-    synthetic preprocessed tile, produced by tests/diag/calibrate_init.py for the (variant, seed) pairs it lists; other
-    seeds fall back to mean 0 / var 1) so that every layer works at unit scale and detections depend on the image.  The class-branch bias sets the candidate density; a linear DFL bias keeps
-    boxes a few cells wide."""
+    synthetic preprocessed tile, produced by tests/diag/calibrate_init.py for the (recipe, variant, seed) triples it
+    lists; others fall back to mean 0 / var 1) so that every layer works at unit scale and detections depend on the
+    image.  The class-branch bias sets the candidate density; the DFL bias sets the box size (RECIPES above)."""
     if is_yolo11(variant):
         return make_random_weights11(variant, nc, seed, cls_bias, calibration)
-    calib = _load_calibration(variant, seed) if calibration == 'auto' else calibration
+    r = dict(RECIPES[recipe])
+    r.update(knobs)
+    calib = _load_calibration_key(calibration_key(variant, seed, recipe)) if calibration == 'auto' else calibration
     g = torch.Generator().manual_seed(seed)
     layers, cb, cc = conv_bn_layers(variant, nc)
     sd = {}
@@ -228,14 +263,20 @@ def make_random_weights(variant='n', nc=5, seed=0, cls_bias=-3.0, calibration='a
         sd[p + '.conv.weight'] = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(fan_in)
         mu, var = (calib[p] if calib and p in calib else (0.0, 1.0))
         sd[p + '.bn.weight'] = 1.0 + 0.1 * torch.randn(cout, generator=g)
-        sd[p + '.bn.bias'] = 0.1 * torch.randn(cout, generator=g)
+        sd[p + '.bn.bias'] = r['bn_beta'] + r['bn_beta_jit'] * torch.randn(cout, generator=g)
         sd[p + '.bn.running_mean'] = torch.full((cout,), float(mu))
         sd[p + '.bn.running_var'] = float(var) * (0.8 + 0.4 * torch.rand(cout, generator=g))
+    k16 = torch.arange(16, dtype=torch.float32)
+    if r['dfl_center'] is None:
+        dfl_bias = (-r['dfl_beta'] * k16).repeat(4) + 1.0
+    else:
+        dfl_bias = (-r['dfl_beta'] * (k16 - float(r['dfl_center'])) ** 2).repeat(4)
     for l in range(3):
-        sd['model.22.cv2.%d.2.weight' % l] = torch.randn(64, cb, 1, 1, generator=g) * (1.5 / math.sqrt(cb))
-        sd['model.22.cv2.%d.2.bias' % l] = (-0.6 * torch.arange(16, dtype=torch.float32)).repeat(4) + 1.0
-        sd['model.22.cv3.%d.2.weight' % l] = torch.randn(nc, cc, 1, 1, generator=g) * (2.5 / math.sqrt(cc))
-        sd['model.22.cv3.%d.2.bias' % l] = torch.full((nc,), float(cls_bias))
+        sd['model.22.cv2.%d.2.weight' % l] = torch.randn(64, cb, 1, 1, generator=g) * (r['dfl_gain'] / math.sqrt(cb))
+        sd['model.22.cv2.%d.2.bias' % l] = dfl_bias.clone()
+        sd['model.22.cv3.%d.2.weight' % l] = torch.randn(nc, cc, 1, 1, generator=g) * (r['cls_gain'] / math.sqrt(cc))
+        on = r.get('levels') is None or l in r['levels']
+        sd['model.22.cv3.%d.2.bias' % l] = torch.full((nc,), float(cls_bias) if on else -100.0)
     sd['model.22.dfl.conv.weight'] = torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)
     return {'format': FORMAT, 'variant': variant, 'nc': nc, 'names': dict(CLASS_NAMES), 'state_dict': sd}
 

@@ -60,7 +60,8 @@ class OracleYolo(object):
         self.a = arch(self.variant) if not str(self.variant).startswith('11') else None
         self.mode = emulate_bf16 if isinstance(emulate_bf16, str) else ('bf16' if emulate_bf16 else 'fp32')
         self.emu = self.mode in ('bf16', 'fp16')
-        self._rnd = _fp16 if self.mode == 'fp16' else _bf16
+        self._rnd = _fp16 if self.mode in ('fp16', 'w16') else _bf16
+        wq = self.emu or self.mode == 'w16'      # 'w16': fp16-rounded weights, fp32 activations (diagnostic)
         sd = weights['state_dict']
         self.w = {}
         for k in sd:
@@ -72,10 +73,10 @@ class OracleYolo(object):
                 s = gamma / torch.sqrt(var + 1e-3)
                 wf = w * s.view(-1, 1, 1, 1)
                 bf = beta - mean * s
-                self.w[p] = (self._rnd(wf) if self.emu else wf, bf)
+                self.w[p] = (self._rnd(wf) if wq else wf, bf)
             elif k.endswith('.2.weight') and '.cv' in k:
                 p = k[:-len('.weight')]
-                self.w[p] = (self._rnd(sd[k].float()) if self.emu else sd[k].float(), sd[p + '.bias'].float())
+                self.w[p] = (self._rnd(sd[k].float()) if wq else sd[k].float(), sd[p + '.bias'].float())
 
     def _q(self, x):
         return self._rnd(x) if self.emu else x
