@@ -242,6 +242,60 @@ int cy_compact_records(const cy_det_record* slots, const int32_t* counts, int T,
 int cy_merge_global(cy_det_record* recs, int n, const cy_tile* tiles, int T, const int32_t* nb_off,
                     const int32_t* nb_idx, cy_source* out, int64_t* nout, uintptr_t stream);
 
+/* ------------------------------------------------------------------------------------------------ whole path
+ * FITS file -> merged catalog with no host-language orchestration: SFinder.run_parallel (caesar_yolo/inference.py:
+ * 578-658; the serial SFinder.run :485-552 is the tile_x <= 0 case: the whole region is one tile), TileTask.find_sources
+ * (:173-275) incl. the per-tile file read (utils.read_fits_crop, utils.py:340-418), gather_task_data_from_workers
+ * (:936-984), find_sources_at_edge + merge_edge_sources (:663-931).  One context per GPU / process; rank r of `world`
+ * owns a contiguous band of tile rows (replaces the tile -> worker map of :1008-1029, max_ntasks_per_worker).  The
+ * payload rows of the band are read with pread (read_threads threads) into two pinned staging buffers and uploaded
+ * in ~64 MB pieces on a copy stream that overlaps the compute of earlier tile groups. */
+typedef struct {
+    int32_t imgsz;                       /* --imgsize */
+    float score_thr, iou_thr;            /* --scoreThr, --iouThr */
+    float thr_soft, thr_hard;            /* --merge_overlap_iou_thr_soft / _hard */
+    int32_t tile_x, tile_y;              /* --tile_xsize / --tile_ysize; <= 0: no tiling (one tile = the region) */
+    double step_x, step_y;               /* --tile_xstep / --tile_ystep */
+    int32_t xmin, xmax, ymin, ymax;      /* --xmin ...: region of the image (inclusive), -1 = full axis */
+    int32_t batch_tiles;                 /* tiles per preprocessing group / conv batch (0: 296 = two per SM) */
+    int32_t read_threads;                /* file reader threads (0: 8) */
+    int32_t rank, world;
+} cy_run_config;
+/* All-gather of `bytes_per_rank` bytes per rank between device buffers, enqueued on `stream` (e.g. a wrapper of
+ * ncclAllGather(send, recv, bytes, ncclUint8, comm, stream)); returns 0 on success. */
+typedef int (*cy_allgather_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_rank, uintptr_t stream);
+
+/* chain_host == NULL: no preprocessing (empty stage list).  The model must be finalized; its storage format decides
+ * the model-input format. */
+int cy_ctx_create(void* model, const cy_pp_chain* chain_host, const cy_run_config* cfg_host, void** ctx_host);
+int cy_ctx_set_allgather(void* ctx, cy_allgather_fn fn, void* user);
+int cy_ctx_destroy(void* ctx);
+/* This rank's share: file -> records of its tiles (device, tile-id order).  Only unscaled BITPIX = -32 images with 2-4
+ * axes are read in place (the reference takes plane [0,0] of a cube); other payloads: convert on the host and use the
+ * _payload form (rows of 4-byte pixels in host memory, big_endian = raw FITS byte order, pinned != 0: page-locked). */
+int cy_run_local(void* ctx, const char* fits_path, int* nrecords_host);
+int cy_run_local_payload(void* ctx, const void* payload_host, int ny, int nx, int big_endian, int pinned,
+                         int* nrecords_host);
+int cy_ctx_records(void* ctx, const cy_det_record** recs_dev, int* n_host);
+/* Exchange helpers: the all-gather slot of this rank = 32-byte header (record count) + the first `cap` records;
+ * unpack: `world` gathered slots -> records of all ranks in rank (= tile-id) order; *max_count_host > cap means a
+ * slot overflowed (redo with a larger cap). */
+int cy_ctx_pack_slot(void* ctx, int cap, const void** slot_dev);
+int cy_ctx_unpack_slots(void* ctx, const void* slots_dev, int world, int cap, const cy_det_record** recs_dev,
+                        int* n_host, int* max_count_host);
+/* Edge flags + cross-tile merge of a gathered record list -> sources in the reference's catalog order, copied to the
+ * host (sources_host may be NULL: count only). */
+int cy_run_merge(void* ctx, const cy_det_record* recs_dev, int n, cy_source* sources_host, int capacity,
+                 int* nsources_host);
+/* cy_run_local + exchange (the registered all-gather when world > 1) + cy_run_merge. */
+int cy_run_mosaic(void* ctx, const char* fits_path, cy_source* sources_host, int capacity, int* nsources_host,
+                  int* nrecords_host);
+int cy_run_payload(void* ctx, const void* payload_host, int ny, int nx, int big_endian, int pinned,
+                   cy_source* sources_host, int capacity, int* nsources_host, int* nrecords_host);
+/* info_host[8]: tiles of the grid, tiles processed by this rank, payload bytes uploaded (cumulative), first / last
+ * (exclusive) tile id of this rank, records of this rank. */
+int cy_ctx_info(void* ctx, double* info_host);
+
 #ifdef __cplusplus
 }
 #endif
