@@ -68,6 +68,19 @@ class Letterbox(ctypes.Structure):
                 ("h0", ctypes.c_int32)]
 
 
+class RunConfig(ctypes.Structure):
+    """cy_run_config (whole-path entry)."""
+    _fields_ = [("imgsz", ctypes.c_int32), ("score_thr", c_float), ("iou_thr", c_float), ("thr_soft", c_float),
+                ("thr_hard", c_float), ("tile_x", ctypes.c_int32), ("tile_y", ctypes.c_int32), ("step_x", c_double),
+                ("step_y", c_double), ("xmin", ctypes.c_int32), ("xmax", ctypes.c_int32), ("ymin", ctypes.c_int32),
+                ("ymax", ctypes.c_int32), ("batch_tiles", ctypes.c_int32), ("read_threads", ctypes.c_int32),
+                ("rank", ctypes.c_int32), ("world", ctypes.c_int32)]
+
+
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                ctypes.c_size_t)
+
+
 # every exported symbol of include/caesar_b200.h (tests check that the library exports all of them)
 SYMBOLS = [
     "cy_last_error", "cy_version", "cy_device_check", "cy_memcpy_d2d", "cy_generate_tiles", "cy_tile_neighbors",
@@ -78,6 +91,8 @@ SYMBOLS = [
     "cy_stem_conv_nhwc4", "cy_model_profile", "cy_model_conv_bytes", "cy_model_destroy", "cy_num_anchors", "cy_decode_pred", "cy_postprocess_scratch_bytes",
     "cy_postprocess", "cy_nms_scratch_bytes", "cy_nms_batched", "cy_merge_tile", "cy_make_records",
     "cy_compact_scratch_bytes", "cy_compact_records", "cy_merge_global",
+    "cy_ctx_create", "cy_ctx_set_allgather", "cy_ctx_destroy", "cy_run_local", "cy_run_local_payload", "cy_ctx_records",
+    "cy_ctx_pack_slot", "cy_ctx_unpack_slots", "cy_run_merge", "cy_run_mosaic", "cy_run_payload", "cy_ctx_info",
 ]
 
 lib.cy_last_error.restype = ctypes.c_char_p

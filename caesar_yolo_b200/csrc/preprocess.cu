@@ -357,6 +357,7 @@ pp_bucket_kernel(const __grid_constant__ PPParams p, const __grid_constant__ CUt
         }
         // ---- registers <- shared memory (byte swap, NaN -> 0), sub-bin of every live pixel
         const int pw = via_tma ? p.pw : Tx, rpw = R * pw;
+        const bool need_xy = p.nsub == 2 || p.border_mask;   // pixel coordinates only when a stage uses the box
         float xv[kChunk / kBkThreads];
         int sb[kChunk / kBkThreads];
 #pragma unroll
@@ -365,17 +366,20 @@ pp_bucket_kernel(const __grid_constant__ PPParams p, const __grid_constant__ CUt
             sb[k] = -1;
             xv[k] = 0.f;
             if (i < len) {
-                int y, x;
-                if (via_tma) {
-                    const int q = i / rpw, rem = i - q * rpw;
-                    y = rem / pw;
-                    x = q * pw + (rem - y * pw);
-                } else {
-                    y = i / Tx;
-                    x = i - y * Tx;
-                }
                 float f = decode_pixel(sm.raw[i], p.big_endian);
-                const bool inb = in_box(p, r0 + y, x);
+                bool inb = true;
+                if (need_xy) {
+                    int y, x;
+                    if (via_tma) {
+                        const int q = i / rpw, rem = i - q * rpw;
+                        y = rem / pw;
+                        x = q * pw + (rem - y * pw);
+                    } else {
+                        y = i / Tx;
+                        x = i - y * Tx;
+                    }
+                    inb = in_box(p, r0 + y, x);
+                }
                 if (p.border_mask && !inb) f = 0.0f;
                 if (f != 0.0f) {
                     xv[k] = f;
@@ -740,8 +744,10 @@ struct Shared {
     int view, n;
     int prefix[kNB + 1];     // rank of the first element of every logical bin
     float bmin[kNB], bmax[kNB];
-    float gath[kGather];     // sorted elements of bin gath_bin
-    int gath_bin, gath_n;
+    float gath[kGather];     // elements of bin gath_bin as gathered (gath_mode 2: sorted)
+    float gath2[kGather];    // the same in sub-bucket order (gath_mode 1)
+    int gsub[256], gpre[257];
+    int gath_bin, gath_n, gath_mode;
     int plist[kNB], nplist;  // bins a query has to walk element by element
     int wtmp[32];
     float fres[4];
@@ -859,19 +865,84 @@ __device__ float value_at(Shared& sh, const TileView& tv, int r) {
     }
     const int j = lo, k = r - sh.prefix[j], m = sh.prefix[j + 1] - sh.prefix[j];
     __syncthreads();
-    if (sh.gath_bin == j) return sh.gath[k];
     if (m <= kGather) {
-        if (threadIdx.x == 0) sh.gath_n = 0;
-        int np2 = 32;
-        while (np2 < m) np2 <<= 1;
-        for (int i = threadIdx.x; i < np2; i += kPPThreads) sh.gath[i] = INFINITY;
+        // The bin's elements are gathered ONCE and counting-sorted into 256 linear sub-buckets of [bmin, bmax] (kept
+        // until another bin is asked for); a query then ranks the few elements of ONE sub-bucket.  gath_mode: 1 =
+        // sub-bucketed (sh.gath2 in sub-bucket order, sh.gpre = starts), 2 = fully sorted (a sub-bucket was too large:
+        // many equal values).
+        if (sh.gath_bin != j) {
+            const float bmn = sh.bmin[j], bmx = sh.bmax[j];
+            const float sc = bmx > bmn ? 256.0f / (bmx - bmn) : 0.0f;
+            __syncthreads();
+            if (threadIdx.x == 0) sh.gath_n = 0;
+            for (int i = threadIdx.x; i < 256; i += kPPThreads) sh.gsub[i] = 0;
+            __syncthreads();
+            for_bin_elements(tv, sh.view, j, [&](float x) {
+                sh.gath[atomicAdd(&sh.gath_n, 1)] = x;
+                atomicAdd(&sh.gsub[min(255, (int)((x - bmn) * sc))], 1);
+            });
+            __syncthreads();
+            if (threadIdx.x < 32) {        // exclusive scan of the 256 counts by one warp (8 per lane)
+                const int l = threadIdx.x;
+                int loc[8], sum = 0, mxc = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    loc[q] = sh.gsub[8 * l + q];
+                    sum += loc[q];
+                    mxc = max(mxc, loc[q]);
+                }
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (l >= o) inc += y;
+                }
+                int run = inc - sum;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    sh.gpre[8 * l + q] = run;
+                    sh.gsub[8 * l + q] = run;      // cursor of the scatter below
+                    run += loc[q];
+                }
+                if (l == 31) sh.gpre[256] = run;
+                mxc = __reduce_max_sync(0xffffffffu, mxc);
+                if (l == 0) sh.gath_mode = mxc <= 256 ? 1 : 2;
+            }
+            __syncthreads();
+            if (sh.gath_mode == 1) {
+                for (int i = threadIdx.x; i < m; i += kPPThreads) {
+                    const float x = sh.gath[i];
+                    sh.gath2[atomicAdd(&sh.gsub[min(255, (int)((x - bmn) * sc))], 1)] = x;
+                }
+            } else {
+                int np2 = 32;
+                while (np2 < m) np2 <<= 1;
+                for (int i = m + threadIdx.x; i < np2; i += kPPThreads) sh.gath[i] = INFINITY;
+                __syncthreads();
+                bitonic_sort_f<kPPThreads>(sh.gath, np2);
+            }
+            if (threadIdx.x == 0) sh.gath_bin = j;
+            __syncthreads();
+        }
+        if (sh.gath_mode == 2) return sh.gath[k];
+        // sub-bucket of rank k, then the (k - start)-th smallest of its elements (ties broken by position)
+        int sl = 0, sr = 256;
+        while (sr - sl > 1) {
+            const int mm = (sl + sr) >> 1;
+            if (sh.gpre[mm] <= k) sl = mm; else sr = mm;
+        }
+        const int s0 = sh.gpre[sl], cntb = sh.gpre[sl + 1] - s0, want = k - s0;
+        if (threadIdx.x < cntb) {
+            const float me = sh.gath2[s0 + threadIdx.x];
+            int rank = 0;
+            for (int q = 0; q < cntb; ++q) {
+                const float o = sh.gath2[s0 + q];
+                rank += (o < me) || (o == me && q < (int)threadIdx.x);
+            }
+            if (rank == want) sh.fres[0] = me;
+        }
         __syncthreads();
-        for_bin_elements(tv, sh.view, j, [&](float x) { sh.gath[atomicAdd(&sh.gath_n, 1)] = x; });
-        __syncthreads();
-        bitonic_sort_f<kPPThreads>(sh.gath, np2);
-        if (threadIdx.x == 0) sh.gath_bin = j;
-        __syncthreads();
-        return sh.gath[k];
+        return sh.fres[0];
     }
     // radix selection on the order-preserving key, most significant byte first
     uint32_t prefix_key = 0, mask = 0;
@@ -903,16 +974,32 @@ __device__ float value_at(Shared& sh, const TileView& tv, int r) {
 // First rank r in [a, b) of the active view with P(x) true, P(x) = f(x) >= t (STRICT: f(x) > t), f = the first nops ops
 // of c (plain composition, monotone); b if none.  *xbelow / *xabove: largest pixel value with !P / smallest with P over
 // the whole view (-inf / +inf if none) -- the value form of the rank boundary.
+// P(x) of lower_index.  `fast` (optional): the compiled form of exactly these ops; it decides when the value is further
+// from t than its rounding error can be (|v - t| > 1e-9 of the magnitudes involved; the compiled form differs from the
+// sequential evaluation by a few fp64 ulps), otherwise the reference operation order does.
+template <bool STRICT>
+__device__ __forceinline__ bool pred_ge(const Chan& c, int nops, const HistEq& he, const Comp* fast, double x, double t) {
+    if (fast) {
+        const double ax = fast->a0 * x;
+        const double v = fmin(fmax(ax + fast->b0, fast->l0), fast->h0);
+        const double margin = 1e-9 * (fabs(ax) + fabs(fast->b0) + fabs(t));
+        if (v > t + margin) return true;
+        if (v < t - margin) return false;
+    }
+    const double v = eval_ops<false>(c, nops, he, x);
+    return STRICT ? (v > t) : (v >= t);
+}
+
 template <bool STRICT>
 __device__ int lower_index(Shared& sh, const TileView& tv, const Chan& c, int nops, int a, int b, double t,
-                           float* xbelow, float* xabove) {
+                           float* xbelow, float* xabove, const Comp* fast = nullptr) {
+    if (fast && (!fast->ok || fast->has_he || nops != c.nops)) fast = nullptr;
     __syncthreads();
     if (threadIdx.x == 0) sh.sidx = kNB;
     __syncthreads();
     for (int j = threadIdx.x; j < kNB; j += kPPThreads) {
         if (sh.prefix[j + 1] > sh.prefix[j]) {
-            const double v = eval_ops<false>(c, nops, sh.he, (double)sh.bmax[j]);
-            if (STRICT ? (v > t) : (v >= t)) atomicMin(&sh.sidx, j);
+            if (pred_ge<STRICT>(c, nops, sh.he, fast, (double)sh.bmax[j], t)) atomicMin(&sh.sidx, j);
         }
     }
     __syncthreads();
@@ -925,8 +1012,7 @@ __device__ int lower_index(Shared& sh, const TileView& tv, const Chan& c, int no
         int cntb = 0;
         float mxb = -INFINITY, mna = INFINITY;
         for_bin_elements(tv, sh.view, jb, [&](float x) {
-            const double v = eval_ops<false>(c, nops, sh.he, (double)x);
-            if (STRICT ? (v > t) : (v >= t)) mna = fminf(mna, x);
+            if (pred_ge<STRICT>(c, nops, sh.he, fast, (double)x, t)) mna = fminf(mna, x);
             else { ++cntb; mxb = fmaxf(mxb, x); }
         });
         double d0 = (double)cntb, d1 = 0.0, d2 = 0.0, mn = (double)mna, mx = (double)mxb;
@@ -1050,9 +1136,9 @@ __device__ bool sigma_clip(Shared& sh, const TileView& tv, const Chan& c, const 
         float xbel, xabv;
         int na = a, nb = b;
         float nxa = xa, nxb = xb;
-        const int r1 = lower_index<false>(sh, tv, c, c.nops, a, b, lo, &xbel, &xabv);   // first f >= lo
+        const int r1 = lower_index<false>(sh, tv, c, c.nops, a, b, lo, &xbel, &xabv, &cc);   // first f >= lo
         if (r1 > a) { na = r1; nxa = xabv; }
-        const int r2 = lower_index<true>(sh, tv, c, c.nops, na, b, hi, &xbel, &xabv);   // first f > hi
+        const int r2 = lower_index<true>(sh, tv, c, c.nops, na, b, hi, &xbel, &xabv, &cc);   // first f > hi
         if (r2 < b) { nb = r2; nxb = xbel; }
         const int ncnt = live_count(c, na, nb);
         if (ncnt == cnt) break;
@@ -1081,12 +1167,13 @@ __device__ void push_op(Shared& sh, const TileView& tv, int ci, int kind, double
         } else {
             sh.fail = -4;
         }
+        compile_chan(c, sh.cc[ci]);     // the compiled form of the new op list: fast path of the two searches below
     }
     __syncthreads();
     // zero set of the plain composition is a contiguous rank range (monotone): [first f >= 0, first f > 0)
     float xb0, xa0, xb1, xa1;
-    const int h0 = lower_index<false>(sh, tv, c, c.nops, 0, sh.n, 0.0, &xb0, &xa0);
-    const int h1 = lower_index<true>(sh, tv, c, c.nops, h0, sh.n, 0.0, &xb1, &xa1);
+    const int h0 = lower_index<false>(sh, tv, c, c.nops, 0, sh.n, 0.0, &xb0, &xa0, &sh.cc[ci]);
+    const int h1 = lower_index<true>(sh, tv, c, c.nops, h0, sh.n, 0.0, &xb1, &xa1, &sh.cc[ci]);
     __syncthreads();
     if (threadIdx.x == 0) {
         add_zero_range(c, h0, h1, xa0, xb1);
@@ -1324,23 +1411,41 @@ __device__ bool histeq_stage(Shared& sh, const PPParams& p, const TileView& tv, 
             if (lo >= c.zx0[k] && hi <= c.zx1[k]) masked = true; else partial = true;
         }
         if (masked) continue;
-        if (!partial) {
-            const int b0 = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)lo));
-            const int b1 = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)hi));
-            if (b0 == b1) {
-                if (b0 >= 0) atomicAdd(&sh.hist[b0], cn);
-            } else {
-                partial = true;
-            }
+        // histogram bins of the value bin's ends through the plain (monotone) composition: every live element of the
+        // bin falls into [b0, b1] (live elements never pass through an exact zero, so plain == sticky for them)
+        const int b0 = he_bin(sh.he, eval_ops<false>(c, c.nops, sh.he, (double)lo));
+        const int b1 = he_bin(sh.he, eval_ops<false>(c, c.nops, sh.he, (double)hi));
+        if (!partial && b0 == b1) {
+            if (b0 >= 0) atomicAdd(&sh.hist[b0], cn);
+        } else {
+            sh.plist[atomicAdd(&sh.nplist, 1)] = j | ((b0 + 1) << 10) | ((b1 + 1) << 19);
         }
-        if (partial) sh.plist[atomicAdd(&sh.nplist, 1)] = j;
     }
     __syncthreads();
     const int np = sh.nplist;
+    const Comp& cc = sh.cc[ci];
+    const bool fast = cc.ok && !cc.has_he;
     for (int i = 0; i < np; ++i) {
-        for_bin_elements(tv, sh.view, sh.plist[i], [&](float x) {
+        const int e = sh.plist[i], j = e & 1023, b0 = ((e >> 10) & 511) - 1, b1 = ((e >> 19) & 511) - 1;
+        for_bin_elements(tv, sh.view, j, [&](float x) {
             if (in_zero_x(c, c.nz, x)) return;
-            const int hb = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)x));
+            int hb = -2;
+            if (fast && b0 >= 0) {
+                // compiled map + a search restricted to [b0, b1]; a value closer to an edge than the compiled form's
+                // rounding error can reach is decided by the reference operation order below
+                const double ax = cc.a0 * (double)x;
+                const double v = fmin(fmax(ax + cc.b0, cc.l0), cc.h0);
+                int lo = b0, hi = b1 + 1;          // edges[lo] <= v, (hi == 256 or v < edges[hi])
+                while (hi - lo > 1) {
+                    const int m = (lo + hi) >> 1;
+                    if (sh.he.edges[m] <= v) lo = m; else hi = m;
+                }
+                const double margin = 1e-9 * (fabs(ax) + fabs(cc.b0) + fabs(v));
+                const bool near_lo = lo > 0 && v - sh.he.edges[lo] < margin;
+                const bool near_hi = lo < 255 && sh.he.edges[lo + 1] - v < margin;
+                if (!near_lo && !near_hi) hb = min(lo, 255);
+            }
+            if (hb == -2) hb = he_bin(sh.he, eval_ops<true>(c, c.nops, sh.he, (double)x));
             if (hb >= 0) atomicAdd(&sh.hist[hb], 1);
         });
     }
@@ -1963,6 +2068,292 @@ __global__ void __launch_bounds__(kFinThreads, 2) pp_final_kernel(const __grid_c
     }
 }
 
+// ------------------------------------------------------------------------------------------ kernel 3b: fused final (production)
+//
+// pp_fused_kernel is the production form of the final pass (pp_final_kernel stays as the parity-output / fallback path).
+// The round-2 profile of pp_final_kernel showed an issue-bound kernel: 4.2 M warp instructions per 512^2 tile, 67 % of the
+// issue slots busy, 2.4 x the compulsory DRAM traffic.  What this kernel does differently:
+//   * the geometry (source columns / rows and weights of every output column / row, the source-row range of every band)
+//     is computed ONCE per call by pp_geom_kernel (fp64 source coordinates as cv2 does) and read from L1/L2;
+//   * the evaluated planes live in a RING of source rows in shared memory: consecutive bands overlap by two source rows,
+//     the ring keeps them, so every source pixel is evaluated exactly once per distinct plane (was 1.4 x);
+//   * raw rows of the NEXT band arrive by cp.async (16 bytes per copy when the tile is 16-byte aligned) while the current
+//     band is resampled: two barriers per band, no exposed global-load latency;
+//   * one thread owns one output column and walks the band's rows: the horizontal interpolation of a source row is
+//     reused by the next output row (1.6 instead of 4 shared-memory loads per output value at scale 0.8);
+//   * affine maps: fp64 FMA, then the clamp in fp32 (rounding is monotone, so float(clamp(v)) == clamp(float(v)));
+//     x / 255 by reciprocal + one FMA correction (correctly rounded).
+struct FusedParams {
+    PPParams p;
+    void* out16;         // [B,Sh,Sw,4] bf16 / fp16
+    float* out_f32;      // optional [B,3,Sh,Sw]
+    int Sh, Sw, new_h, new_w, top, left;
+    double scale_y, scale_x;
+    int band_h, ring, rawrows, nbands, chunks, f16;
+    unsigned magic_tx;   // ceil(2^32 / Tx): i / Tx == __umulhi(i, magic_tx) for i < 2^32 / Tx
+    unsigned magic_tx4;  // the same for Tx / 4 (16-byte copies)
+    // geometry tables (device, written by pp_geom_kernel)
+    int* gx0; int* gx1; float* gxw;       // [Sw]  source columns of tap 0 / 1 (-1: padding column), weight of tap 1
+    int* gy0; int* gy1; float* gwy;       // [Sh]  source rows (-1: padding row)
+    int* gs0; int* gs1;                    // [Sh]  ring offsets (row % ring) * Tx of the two source rows
+    int* gband;                            // [nbands][2] first / last source row a band needs (first > last: none)
+};
+
+__global__ void pp_geom_kernel(const FusedParams r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.Sw) {
+        const int rx = i - r.left;
+        int a = -1, c = -1;
+        float w = 0.f;
+        if (rx >= 0 && rx < r.new_w) src_coord(rx, r.scale_x, r.p.Tx, a, c, w);
+        r.gx0[i] = a; r.gx1[i] = c; r.gxw[i] = w;
+    }
+    if (i < r.Sh) {
+        const int ry = i - r.top;
+        int a = -1, c = -1;
+        float w = 0.f;
+        if (ry >= 0 && ry < r.new_h) src_coord(ry, r.scale_y, r.p.Ty, a, c, w);
+        r.gy0[i] = a; r.gy1[i] = c; r.gwy[i] = w;
+        r.gs0[i] = a >= 0 ? (a % r.ring) * r.p.Tx : 0;
+        r.gs1[i] = c >= 0 ? (c % r.ring) * r.p.Tx : 0;
+    }
+    if (i < r.nbands) {
+        const int oy0 = i * r.band_h, oy1 = min(r.Sh, oy0 + r.band_h);
+        const int ry0 = max(oy0 - r.top, 0), ry1 = min(oy1 - r.top, r.new_h);
+        int lo = 1, hi = 0;
+        if (ry0 < ry1) {
+            int a0, a1, c0, c1;
+            float w;
+            src_coord(ry0, r.scale_y, r.p.Ty, a0, a1, w);
+            src_coord(ry1 - 1, r.scale_y, r.p.Ty, c0, c1, w);
+            lo = a0; hi = c1;
+        }
+        r.gband[2 * i] = lo;
+        r.gband[2 * i + 1] = hi;
+    }
+}
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// x / 255 correctly rounded: q = x * r, then one FMA correction with the exact remainder
+__device__ __forceinline__ float div255(float x) {
+    const float rcp = 1.0f / 255.0f;
+    const float q = x * rcp;
+    const float e = fmaf(-q, 255.0f, x);
+    return fmaf(e, rcp, q);
+}
+
+static constexpr int kFuMaxThreads = 640;
+
+__global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid_constant__ FusedParams r) {
+    extern __shared__ __align__(16) unsigned char fu_smem[];
+    TileFinal& tf = *reinterpret_cast<TileFinal*>(fu_smem);
+    uint32_t* raw = reinterpret_cast<uint32_t*>(fu_smem + sizeof(TileFinal));
+    const PPParams& p = r.p;
+    const int Ty = p.Ty, Tx = p.Tx, NT = blockDim.x, tid = threadIdx.x, b = blockIdx.x;
+    float* planes = reinterpret_cast<float*>(raw + (size_t)r.rawrows * Tx);
+    const int plane_sz = r.ring * Tx;
+    {   // per-tile state (the histogram-equalisation tables are the bulk: skipped when no channel uses them)
+        const uint4* src = reinterpret_cast<const uint4*>(&p.fin[b]);
+        uint4* dst = reinterpret_cast<uint4*>(&tf);
+        const int n_head = (int)(offsetof(TileFinal, he) / 16), n_all = (int)(sizeof(TileFinal) / 16);
+        const int n_tail0 = (int)((offsetof(TileFinal, he) + sizeof(HistEq)) / 16);
+        for (int i = n_tail0 + tid; i < n_all; i += NT) dst[i] = src[i];
+        __syncthreads();
+        if (tf.valid) {
+            for (int i = tid; i < n_head; i += NT) dst[i] = src[i];
+            if (tf.use_he)
+                for (int i = n_head + tid; i < n_tail0; i += NT) dst[i] = src[i];
+        }
+        __syncthreads();
+    }
+    const bool valid = tf.valid != 0;
+    // distinct planes: channel c reads plane pidx[c]
+    const int pidx1 = (!valid || tf.same01) ? 0 : 1;
+    const int pidx2 = (!valid || tf.same02) ? 0 : (tf.same12 ? pidx1 : pidx1 + 1);
+    const int np = max(pidx1, pidx2) + 1;
+    int chan_of_plane[3] = {0, 0, 0};     // a channel whose map plane q holds
+    chan_of_plane[pidx1] = pidx1 ? 1 : 0;
+    if (pidx2 > pidx1) chan_of_plane[pidx2] = 2;
+    const long long g_row0 = (long long)p.y0[b] * p.row_stride + p.x0[b];
+    const uint32_t* gimg = p.img + g_row0;
+    const bool vec16 = ((reinterpret_cast<uintptr_t>(p.img) & 15) == 0) && ((p.row_stride & 3) == 0) && ((g_row0 & 3) == 0) &&
+                       ((Tx & 3) == 0);
+
+    const int bnd0 = (int)(((long long)blockIdx.y * r.nbands) / gridDim.y);
+    const int bnd1 = (int)(((long long)(blockIdx.y + 1) * r.nbands) / gridDim.y);
+    int have = -1;                         // source rows < have are in the ring (as far as the ring reaches back)
+    // rows the next Phase A has to evaluate: [nlo, nhi]; staged in `raw` by cp.async
+    int nlo = 1, nhi = 0;
+    auto stage_rows = [&](int band) {
+        nlo = 1; nhi = 0;
+        if (band < bnd1) {
+            const int lo = __ldg(&r.gband[2 * band]), hi = __ldg(&r.gband[2 * band + 1]);
+            if (lo <= hi) {
+                nlo = max(lo, have);
+                nhi = hi;
+                if (have < 0) nlo = lo;
+            }
+        }
+        if (nlo > nhi) return;
+        const int m = nhi - nlo + 1;
+        if (vec16) {
+            const int w4 = Tx >> 2, n4 = m * w4;
+            for (int i = tid; i < n4; i += NT) {
+                const int q = (int)__umulhi((unsigned)i, r.magic_tx4);
+                const int x4 = i - q * w4;
+                cp_async16(raw + (size_t)q * Tx + 4 * x4, gimg + (long long)(nlo + q) * p.row_stride + 4 * x4);
+            }
+        } else {
+            const int n = m * Tx;
+            for (int i = tid; i < n; i += NT) {
+                const int q = (int)__umulhi((unsigned)i, r.magic_tx);
+                const int x = i - q * Tx;
+                cp_async4(raw + i, gimg + (long long)(nlo + q) * p.row_stride + x);
+            }
+        }
+    };
+    stage_rows(bnd0);
+    cp_async_commit();
+
+    // my output column (NT >= Sw in the common case: the column geometry stays in registers)
+    for (int band = bnd0; band < bnd1; ++band) {
+        cp_async_wait_all();
+        __syncthreads();                   // raw rows of this band visible; Phase B of the previous band has finished
+        // ---- Phase A: new source rows -> planes (ring slots)
+        if (nlo <= nhi) {
+            const int m = nhi - nlo + 1, n = m * Tx;
+            const int slot0 = nlo % r.ring;
+            for (int q = 0; q < np; ++q) {
+                float* pl = planes + (size_t)q * plane_sz;
+                if (!valid) {
+                    for (int i = tid; i < n; i += NT) {
+                        const int rr = (int)__umulhi((unsigned)i, r.magic_tx);
+                        int slot = slot0 + rr;
+                        if (slot >= r.ring) slot -= r.ring;
+                        pl[slot * Tx + (i - rr * Tx)] = 0.0f;
+                    }
+                    continue;
+                }
+                const int ci = chan_of_plane[q];
+                const Comp& cc = tf.cc[ci];
+                const int nz = cc.nzx;
+                if (cc.ok && !cc.has_he && nz <= 2) {
+                    const double a = cc.a0, bb = cc.b0;
+                    const float l = (float)cc.l0, h = (float)cc.h0;
+                    const float z00 = nz > 0 ? cc.zx0[0] : INFINITY, z01 = nz > 0 ? cc.zx1[0] : -INFINITY;
+                    const float z10 = nz > 1 ? cc.zx0[1] : INFINITY, z11 = nz > 1 ? cc.zx1[1] : -INFINITY;
+#pragma unroll 4
+                    for (int i = tid; i < n; i += NT) {
+                        const int rr = (int)__umulhi((unsigned)i, r.magic_tx);
+                        const int x = i - rr * Tx;
+                        int slot = slot0 + rr;
+                        if (slot >= r.ring) slot -= r.ring;
+                        float f = decode_pixel(raw[i], p.big_endian);
+                        if (p.border_mask && !in_box(p, nlo + rr, x)) f = 0.0f;
+                        const bool masked = (f == 0.0f) || (f >= z00 && f <= z01) || (f >= z10 && f <= z11);
+                        const float v = fminf(fmaxf((float)fma(a, (double)f, bb), l), h);
+                        pl[slot * Tx + x] = masked ? 0.0f : v;
+                    }
+                } else {
+                    for (int i = tid; i < n; i += NT) {
+                        const int rr = (int)__umulhi((unsigned)i, r.magic_tx);
+                        const int x = i - rr * Tx;
+                        int slot = slot0 + rr;
+                        if (slot >= r.ring) slot -= r.ring;
+                        float f = decode_pixel(raw[i], p.big_endian);
+                        if (p.border_mask && !in_box(p, nlo + rr, x)) f = 0.0f;
+                        const bool masked = (f == 0.0f) || in_zero_x(cc, nz, f);
+                        pl[slot * Tx + x] = masked ? 0.0f : (float)eval_fast(cc, tf.ch[ci], tf.he, (double)f);
+                    }
+                }
+            }
+            have = nhi + 1;
+        }
+        __syncthreads();                   // planes ready; raw free
+        stage_rows(band + 1);
+        cp_async_commit();
+        // ---- Phase B: one thread = one output column, walking the band's output rows
+        const int oy0 = band * r.band_h, oy1 = min(r.Sh, oy0 + r.band_h);
+        const float* P0 = planes;
+        const float* P1 = planes + (size_t)(np > 1 ? 1 : 0) * plane_sz;
+        const float* P2 = planes + (size_t)(np > 2 ? 2 : 0) * plane_sz;
+        for (int ox = tid; ox < r.Sw; ox += NT) {
+            const int x0 = __ldg(&r.gx0[ox]), x1 = __ldg(&r.gx1[ox]);
+            const float wx = __ldg(&r.gxw[ox]), ux = 1.f - wx;
+            int cy0 = -9, cy1 = -9;                 // source rows whose horizontal interpolation is cached
+            float h0[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};
+            unsigned short* out = reinterpret_cast<unsigned short*>(r.out16) + (((long long)b * r.Sh + oy0) * r.Sw + ox) * 4;
+            for (int oy = oy0; oy < oy1; ++oy, out += (long long)r.Sw * 4) {
+                float v[3] = {114.f, 114.f, 114.f};   // cv2.copyMakeBorder value
+                const int y0 = __ldg(&r.gy0[oy]);
+                if (y0 >= 0 && x0 >= 0) {
+                    const int y1 = __ldg(&r.gy1[oy]);
+                    const float wy = __ldg(&r.gwy[oy]), uy = 1.f - wy;
+                    float n0[3], n1[3];
+                    if (y0 == cy0) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) n0[q] = h0[q];
+                    } else if (y0 == cy1) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) n0[q] = h1[q];
+                    } else {
+                        const int o = __ldg(&r.gs0[oy]);
+                        n0[0] = P0[o + x0] * ux + P0[o + x1] * wx;
+                        if (np > 1) n0[1] = P1[o + x0] * ux + P1[o + x1] * wx;
+                        if (np > 2) n0[2] = P2[o + x0] * ux + P2[o + x1] * wx;
+                    }
+                    if (y1 == y0) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) n1[q] = n0[q];
+                    } else if (y1 == cy1) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) n1[q] = h1[q];
+                    } else if (y1 == cy0) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) n1[q] = h0[q];
+                    } else {
+                        const int o = __ldg(&r.gs1[oy]);
+                        n1[0] = P0[o + x0] * ux + P0[o + x1] * wx;
+                        if (np > 1) n1[1] = P1[o + x0] * ux + P1[o + x1] * wx;
+                        if (np > 2) n1[2] = P2[o + x0] * ux + P2[o + x1] * wx;
+                    }
+                    cy0 = y0; cy1 = y1;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { h0[q] = n0[q]; h1[q] = n1[q]; }
+                    const float t0 = n0[0] * uy + n1[0] * wy;
+                    const float t1 = np > 1 ? n0[1] * uy + n1[1] * wy : t0;
+                    const float t2 = np > 2 ? n0[2] * uy + n1[2] * wy : t0;
+                    v[0] = t0;
+                    v[1] = pidx1 == 0 ? t0 : t1;
+                    v[2] = pidx2 == 0 ? t0 : (pidx2 == 1 ? t1 : t2);
+                }
+                // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
+                const float m0 = div255(v[2]), m1 = div255(v[1]), m2 = div255(v[0]);
+                uint2 pk;
+                pk.x = pack_h2(m0, m1, r.f16);
+                pk.y = pack_h2(m2, 0.f, r.f16);
+                *reinterpret_cast<uint2*>(out) = pk;
+                if (r.out_f32) {
+                    const long long plane = (long long)r.Sh * r.Sw;
+                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)oy * r.Sw + ox;
+                    of[0] = m0;
+                    of[plane] = m1;
+                    of[2 * plane] = m2;
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
 // ------------------------------------------------------------------------------------------ letterbox resize of an HWC image
 
 struct ResizeParams {
@@ -2173,6 +2564,9 @@ static int fin_rows_cap(const LbGeom& g, int Ty, int Tx) {
     return fin_smem_bytes(g.Sw, cap, Tx) <= kFinSmemMax ? cap : 0;
 }
 
+static constexpr size_t kFuTableBytes = 256 * 1024;   // geometry tables of the fused final kernel (part of the scratch)
+static constexpr size_t kFuSmemMax = 112 * 1024;      // two CTAs per SM
+
 struct BkGeom {
     int nsub, R, nchunks, nbs;
 };
@@ -2207,7 +2601,7 @@ extern "C" size_t cy_preprocess_chain_scratch_bytes(const cy_pp_chain* ch, int B
     BkGeom g;
     if (bk_geometry(ch, Ty, Tx, &g)) return 0;
     const size_t N = (size_t)Ty * Tx, b = (size_t)B;
-    size_t t = align256(b * sizeof(cy::TileFinal)) + 256;
+    size_t t = align256(b * sizeof(cy::TileFinal)) + 256 + kFuTableBytes;
     if (ch->nstages > 0)
         t += align256(b * sizeof(cy::TileHdr)) + align256(b * N * 4) + align256(b * g.nchunks * (g.nbs + 1) * 2) +
              align256(b * (g.nchunks + 1) * 4) + 3 * align256(b * g.nbs * 4) + 2 * align256(b * g.nbs * 8);
@@ -2284,6 +2678,8 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
         p.m1 = (double*)s; s += align256(b * g.nbs * 8);
         p.m2 = (double*)s; s += align256(b * g.nbs * 8);
     }
+    char* fu_tables = s;
+    s += kFuTableBytes;
     p.chain_out = chain_out;
     p.status = status;
     static std::atomic<unsigned long long> attr_done{0};
@@ -2291,6 +2687,7 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BkSmem)));
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemMax));
+        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFuSmemMax));
     }
     if (chain.nstages > 0) {
         // TMA staging of the chunks: 2-D boxes of pw x R pixels of the mosaic (16-byte aligned base / pitch / box rows)
@@ -2350,7 +2747,48 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
         return CY_OK;
     };
     if (chain_out && (rc = emit_chain(chain_out))) return rc;
-    if (model_in) {
+    bool fused_done = false;
+    if (model_in && cap > 0 && Tx >= 8 && !(getenv("CY_PP_OLD_FINAL") && atoi(getenv("CY_PP_OLD_FINAL")))) {
+        // production path: pp_geom_kernel (once per call) + pp_fused_kernel
+        FusedParams f;
+        memset(&f, 0, sizeof(f));
+        f.p = p;
+        f.out16 = model_in;
+        f.out_f32 = model_in_f32;
+        f.Sh = lg.Sh; f.Sw = lg.Sw; f.new_h = lg.new_h; f.new_w = lg.new_w; f.top = lg.top; f.left = lg.left;
+        f.scale_y = lg.scale_y; f.scale_x = lg.scale_x;
+        f.f16 = r.f16;
+        f.band_h = kFinBandH;
+        f.ring = cap;
+        f.rawrows = cap;
+        f.nbands = (lg.Sh + kFinBandH - 1) / kFinBandH;
+        f.magic_tx = (unsigned)(((1ull << 32) + (unsigned)Tx - 1) / (unsigned)Tx);
+        f.magic_tx4 = (Tx % 4 == 0) ? (unsigned)(((1ull << 32) + (unsigned)(Tx / 4) - 1) / (unsigned)(Tx / 4)) : 0u;
+        const size_t tab = ((size_t)lg.Sw * 12 + (size_t)lg.Sh * 20 + (size_t)f.nbands * 8 + 255) & ~(size_t)255;
+        const size_t smem = sizeof(TileFinal) + (size_t)cap * Tx * 4 * 4;
+        if (tab <= kFuTableBytes && smem <= kFuSmemMax && (long long)cap * Tx < (1ll << 32) / Tx) {
+            char* t = fu_tables;
+            f.gx0 = (int*)t; t += (size_t)lg.Sw * 4;
+            f.gx1 = (int*)t; t += (size_t)lg.Sw * 4;
+            f.gxw = (float*)t; t += (size_t)lg.Sw * 4;
+            f.gy0 = (int*)t; t += (size_t)lg.Sh * 4;
+            f.gy1 = (int*)t; t += (size_t)lg.Sh * 4;
+            f.gwy = (float*)t; t += (size_t)lg.Sh * 4;
+            f.gs0 = (int*)t; t += (size_t)lg.Sh * 4;
+            f.gs1 = (int*)t; t += (size_t)lg.Sh * 4;
+            f.gband = (int*)t;
+            int chunks = (2 * sms + B - 1) / B;
+            chunks = chunks < 1 ? 1 : (chunks > f.nbands ? f.nbands : chunks);
+            f.chunks = chunks;
+            const int gmax = lg.Sw > lg.Sh ? lg.Sw : lg.Sh;
+            pp_geom_kernel<<<(gmax + 255) / 256, 256, 0, st>>>(f);
+            int nt = (lg.Sw + 31) & ~31;
+            nt = nt > kFuMaxThreads ? kFuMaxThreads : (nt < 128 ? 128 : nt);
+            pp_fused_kernel<<<dim3((unsigned)B, (unsigned)chunks), nt, smem, st>>>(f);
+            fused_done = true;
+        }
+    }
+    if (model_in && !fused_done) {
         if (cap > 0) {
             r.emit_only = 0;
             r.band_h = kFinBandH;
