@@ -802,6 +802,35 @@ __device__ __forceinline__ void for_bin_elements(const TileView& tv, int view, i
     }
 }
 
+// Visits every element of the bins listed in sh.plist[0 .. np) (entry: low 10 bits = logical bin, the rest is passed
+// to f).  The work items are (bin, chunk) pairs; a warp fetches the segment bounds of 32 items at once (one per lane: the
+// three dependent global loads of an item overlap across lanes) and then walks the segments one after the other.
+template <class F>
+__device__ __forceinline__ void for_list_elements(const Shared& sh, const TileView& tv, int np, F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = np * tv.nchunks;
+    for (int base = warp * 32; base < total; base += kPPWarps * 32) {
+        const int t = base + lane;
+        int a = 0, e = 0, ent = 0;
+        if (t < total) {
+            const int i = t / tv.nchunks, c = t - i * tv.nchunks;
+            ent = sh.plist[i];
+            int s0, s1;
+            sub_range(tv, sh.view, ent & 1023, s0, s1);
+            const unsigned short* oc = tv.off + (long long)c * (tv.nbs + 1);
+            const int cb = tv.cbase[c];
+            a = cb + oc[s0];
+            e = cb + oc[s1];
+        }
+        const int nitems = min(32, total - base);
+        for (int q = 0; q < nitems; ++q) {
+            const int aa = __shfl_sync(0xffffffffu, a, q), ee = __shfl_sync(0xffffffffu, e, q);
+            const int en = __shfl_sync(0xffffffffu, ent, q);
+            for (int k = aa + lane; k < ee; k += 32) f(tv.vals[k], en);
+        }
+    }
+}
+
 // (all threads) make `view` the active view: logical-bin counts -> prefix ranks, minima / maxima
 __device__ void set_view(Shared& sh, const TileView& tv, int view) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -1050,10 +1079,10 @@ __device__ void range_sums(Shared& sh, const TileView& tv, const Chan& c, const 
         const float lo = sh.bmin[j], hi = sh.bmax[j];
         if (hi < xa || lo > xb) continue;
         bool partial = !(lo >= xa && hi <= xb) || !simple;
-        bool masked = false;
+        bool masked = false, touches = false;
         for (int k = 0; k < c.nz; ++k) {
             if (hi < c.zx0[k] || lo > c.zx1[k]) continue;
-            if (lo >= c.zx0[k] && hi <= c.zx1[k]) masked = true; else partial = true;
+            if (lo >= c.zx0[k] && hi <= c.zx1[k]) masked = true; else partial = touches = true;
         }
         if (masked) continue;
         if (!partial) {
@@ -1079,19 +1108,18 @@ __device__ void range_sums(Shared& sh, const TileView& tv, const Chan& c, const 
                 partial = true;
             }
         }
-        if (partial) sh.plist[atomicAdd(&sh.nplist, 1)] = j;
+        if (partial) sh.plist[atomicAdd(&sh.nplist, 1)] = j | (touches ? 1 << 10 : 0);
     }
     __syncthreads();
     const int np = sh.nplist;
-    for (int i = 0; i < np; ++i) {
-        for_bin_elements(tv, sh.view, sh.plist[i], [&](float x) {
-            if (x < xa || x > xb || in_zero_x(c, c.nz, x)) return;
-            const double d = eval_fast(cc, c, sh.he, (double)x) - pv;
-            n += 1.0;
-            u += d;
-            q = fma(d, d, q);
-        });
-    }
+    for_list_elements(sh, tv, np, [&](float x, int ent) {
+        if (x < xa || x > xb) return;
+        if ((ent >> 10) && in_zero_x(c, c.nz, x)) return;     // only bins that touch a masked interval test for it
+        const double d = eval_fast(cc, c, sh.he, (double)x) - pv;
+        n += 1.0;
+        u += d;
+        q = fma(d, d, q);
+    });
     block_sum3(n, u, q, sh.red);
     s0 = n;
     s1 = u;
@@ -1418,17 +1446,17 @@ __device__ bool histeq_stage(Shared& sh, const PPParams& p, const TileView& tv, 
         if (!partial && b0 == b1) {
             if (b0 >= 0) atomicAdd(&sh.hist[b0], cn);
         } else {
-            sh.plist[atomicAdd(&sh.nplist, 1)] = j | ((b0 + 1) << 10) | ((b1 + 1) << 19);
+            sh.plist[atomicAdd(&sh.nplist, 1)] = j | ((b0 + 1) << 10) | ((b1 + 1) << 19) | (partial ? 1 << 28 : 0);
         }
     }
     __syncthreads();
     const int np = sh.nplist;
     const Comp& cc = sh.cc[ci];
     const bool fast = cc.ok && !cc.has_he;
-    for (int i = 0; i < np; ++i) {
-        const int e = sh.plist[i], j = e & 1023, b0 = ((e >> 10) & 511) - 1, b1 = ((e >> 19) & 511) - 1;
-        for_bin_elements(tv, sh.view, j, [&](float x) {
-            if (in_zero_x(c, c.nz, x)) return;
+    {
+        for_list_elements(sh, tv, np, [&](float x, int e) {
+            const int b0 = ((e >> 10) & 511) - 1, b1 = ((e >> 19) & 511) - 1;
+            if ((e >> 28) && in_zero_x(c, c.nz, x)) return;   // only bins that touch a masked interval test for it
             int hb = -2;
             if (fast && b0 >= 0) {
                 // compiled map + a search restricted to [b0, b1]; a value closer to an edge than the compiled form's
@@ -2155,7 +2183,8 @@ static constexpr int kFuMaxThreads = 640;
 __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid_constant__ FusedParams r) {
     extern __shared__ __align__(16) unsigned char fu_smem[];
     TileFinal& tf = *reinterpret_cast<TileFinal*>(fu_smem);
-    uint32_t* raw = reinterpret_cast<uint32_t*>(fu_smem + sizeof(TileFinal));
+    int* rowtab = reinterpret_cast<int*>(fu_smem + sizeof(TileFinal));     // [16][3]: ring offsets of the two source rows, wy
+    uint32_t* raw = reinterpret_cast<uint32_t*>(fu_smem + sizeof(TileFinal) + 256);
     const PPParams& p = r.p;
     const int Ty = p.Ty, Tx = p.Tx, NT = blockDim.x, tid = threadIdx.x, b = blockIdx.x;
     float* planes = reinterpret_cast<float*>(raw + (size_t)r.rawrows * Tx);
@@ -2227,6 +2256,18 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
     for (int band = bnd0; band < bnd1; ++band) {
         cp_async_wait_all();
         __syncthreads();                   // raw rows of this band visible; Phase B of the previous band has finished
+        if (tid < r.band_h) {              // row geometry of this band's output rows (read in Phase B)
+            const int oy = band * r.band_h + tid;
+            int o0 = -1, o1 = -1, wyb = 0;
+            if (oy < r.Sh && __ldg(&r.gy0[oy]) >= 0) {
+                o0 = __ldg(&r.gs0[oy]);
+                o1 = __ldg(&r.gs1[oy]);
+                wyb = __float_as_int(__ldg(&r.gwy[oy]));
+            }
+            rowtab[3 * tid] = o0;
+            rowtab[3 * tid + 1] = o1;
+            rowtab[3 * tid + 2] = wyb;
+        }
         // ---- Phase A: new source rows -> planes (ring slots)
         if (nlo <= nhi) {
             const int m = nhi - nlo + 1, n = m * Tx;
@@ -2280,70 +2321,41 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
         __syncthreads();                   // planes ready; raw free
         stage_rows(band + 1);
         cp_async_commit();
-        // ---- Phase B: one thread = one output column, walking the band's output rows
+        // ---- Phase B: one thread = one output column, walking the band's output rows (row geometry from shared memory)
         const int oy0 = band * r.band_h, oy1 = min(r.Sh, oy0 + r.band_h);
         const float* P0 = planes;
         const float* P1 = planes + (size_t)(np > 1 ? 1 : 0) * plane_sz;
         const float* P2 = planes + (size_t)(np > 2 ? 2 : 0) * plane_sz;
+        const float pad = div255(114.f);              // cv2.copyMakeBorder value, /255
         for (int ox = tid; ox < r.Sw; ox += NT) {
             const int x0 = __ldg(&r.gx0[ox]), x1 = __ldg(&r.gx1[ox]);
             const float wx = __ldg(&r.gxw[ox]), ux = 1.f - wx;
-            int cy0 = -9, cy1 = -9;                 // source rows whose horizontal interpolation is cached
-            float h0[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};
             unsigned short* out = reinterpret_cast<unsigned short*>(r.out16) + (((long long)b * r.Sh + oy0) * r.Sw + ox) * 4;
-            for (int oy = oy0; oy < oy1; ++oy, out += (long long)r.Sw * 4) {
-                float v[3] = {114.f, 114.f, 114.f};   // cv2.copyMakeBorder value
-                const int y0 = __ldg(&r.gy0[oy]);
-                if (y0 >= 0 && x0 >= 0) {
-                    const int y1 = __ldg(&r.gy1[oy]);
-                    const float wy = __ldg(&r.gwy[oy]), uy = 1.f - wy;
-                    float n0[3], n1[3];
-                    if (y0 == cy0) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) n0[q] = h0[q];
-                    } else if (y0 == cy1) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) n0[q] = h1[q];
-                    } else {
-                        const int o = __ldg(&r.gs0[oy]);
-                        n0[0] = P0[o + x0] * ux + P0[o + x1] * wx;
-                        if (np > 1) n0[1] = P1[o + x0] * ux + P1[o + x1] * wx;
-                        if (np > 2) n0[2] = P2[o + x0] * ux + P2[o + x1] * wx;
-                    }
-                    if (y1 == y0) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) n1[q] = n0[q];
-                    } else if (y1 == cy1) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) n1[q] = h1[q];
-                    } else if (y1 == cy0) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) n1[q] = h0[q];
-                    } else {
-                        const int o = __ldg(&r.gs1[oy]);
-                        n1[0] = P0[o + x0] * ux + P0[o + x1] * wx;
-                        if (np > 1) n1[1] = P1[o + x0] * ux + P1[o + x1] * wx;
-                        if (np > 2) n1[2] = P2[o + x0] * ux + P2[o + x1] * wx;
-                    }
-                    cy0 = y0; cy1 = y1;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) { h0[q] = n0[q]; h1[q] = n1[q]; }
-                    const float t0 = n0[0] * uy + n1[0] * wy;
-                    const float t1 = np > 1 ? n0[1] * uy + n1[1] * wy : t0;
-                    const float t2 = np > 2 ? n0[2] * uy + n1[2] * wy : t0;
-                    v[0] = t0;
-                    v[1] = pidx1 == 0 ? t0 : t1;
-                    v[2] = pidx2 == 0 ? t0 : (pidx2 == 1 ? t1 : t2);
+            for (int k = 0; k < oy1 - oy0; ++k, out += (long long)r.Sw * 4) {
+                float m0 = pad, m1 = pad, m2 = pad;
+                const int o0 = rowtab[3 * k];
+                if (o0 >= 0 && x0 >= 0) {
+                    const int o1 = rowtab[3 * k + 1];
+                    const float wy = __int_as_float(rowtab[3 * k + 2]), uy = 1.f - wy;
+                    const int i00 = o0 + x0, i01 = o0 + x1, i10 = o1 + x0, i11 = o1 + x1;
+                    const float t0 = (P0[i00] * ux + P0[i01] * wx) * uy + (P0[i10] * ux + P0[i11] * wx) * wy;
+                    float t1 = t0, t2 = t0;
+                    if (np > 1) t1 = (P1[i00] * ux + P1[i01] * wx) * uy + (P1[i10] * ux + P1[i11] * wx) * wy;
+                    if (np > 2) t2 = (P2[i00] * ux + P2[i01] * wx) * uy + (P2[i10] * ux + P2[i11] * wx) * wy;
+                    const float v1 = pidx1 == 0 ? t0 : t1;
+                    const float v2 = pidx2 == 0 ? t0 : (pidx2 == 1 ? t1 : t2);
+                    // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
+                    m0 = div255(v2);
+                    m1 = div255(v1);
+                    m2 = div255(t0);
                 }
-                // predictor.preprocess: im[..., ::-1] (channel reversal), float32, /255
-                const float m0 = div255(v[2]), m1 = div255(v[1]), m2 = div255(v[0]);
                 uint2 pk;
                 pk.x = pack_h2(m0, m1, r.f16);
                 pk.y = pack_h2(m2, 0.f, r.f16);
                 *reinterpret_cast<uint2*>(out) = pk;
                 if (r.out_f32) {
                     const long long plane = (long long)r.Sh * r.Sw;
-                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)oy * r.Sw + ox;
+                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)(oy0 + k) * r.Sw + ox;
                     of[0] = m0;
                     of[plane] = m1;
                     of[2 * plane] = m2;
@@ -2765,7 +2777,7 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
         f.magic_tx = (unsigned)(((1ull << 32) + (unsigned)Tx - 1) / (unsigned)Tx);
         f.magic_tx4 = (Tx % 4 == 0) ? (unsigned)(((1ull << 32) + (unsigned)(Tx / 4) - 1) / (unsigned)(Tx / 4)) : 0u;
         const size_t tab = ((size_t)lg.Sw * 12 + (size_t)lg.Sh * 20 + (size_t)f.nbands * 8 + 255) & ~(size_t)255;
-        const size_t smem = sizeof(TileFinal) + (size_t)cap * Tx * 4 * 4;
+        const size_t smem = sizeof(TileFinal) + 256 + (size_t)cap * Tx * 4 * 4;
         if (tab <= kFuTableBytes && smem <= kFuSmemMax && (long long)cap * Tx < (1ll << 32) / Tx) {
             char* t = fu_tables;
             f.gx0 = (int*)t; t += (size_t)lg.Sw * 4;
