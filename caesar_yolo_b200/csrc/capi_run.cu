@@ -88,7 +88,7 @@ struct RunCtx {
 
 int parse_fits_header(int fd, FitsInfo* fi) {
     // Primary HDU of a FITS file: 80-byte cards in 2880-byte blocks up to END (utils.read_fits, utils.py:150-246: the
-    // reference takes plane [0, 0] of a 3-D / 4-D cube; a 3-channel cube is rejected).
+    // reference takes plane [0, 0] of a 4-D cube and rejects everything that is not 2-D or 4-D).
     char block[2880];
     long long off = 0;
     int bitpix = 0, naxis = -1;
@@ -121,8 +121,8 @@ int parse_fits_header(int fd, FitsInfo* fi) {
         off += 2880;
         if (off > (1ll << 24)) return set_error(CY_ERR_INVALID, "cy_run: FITS header without END");
     }
-    if (naxis < 2 || naxis > 4) return set_error(CY_ERR_INVALID, "cy_run: FITS image must have 2 to 4 axes (NAXIS=%d)", naxis);
-    if (naxis == 3 && ax[2] == 3) return set_error(CY_ERR_INVALID, "cy_run: 3-channel FITS cubes are not accepted (utils.py:211-214)");
+    if (naxis != 2 && naxis != 4)   // utils.read_fits / read_fits_crop (utils.py:207-216,378-386): 2-D images and 4-D cubes only
+        return set_error(CY_ERR_INVALID, "cy_run: invalid/unsupported number of channels (NAXIS=%d)", naxis);
     if (bitpix != -32 || bscale != 1.0 || bzero != 0.0)
         return set_error(CY_ERR_INVALID,
                          "cy_run: only unscaled BITPIX=-32 payloads are read in place (BITPIX=%d BSCALE=%g BZERO=%g): "

@@ -2184,7 +2184,8 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
     extern __shared__ __align__(16) unsigned char fu_smem[];
     TileFinal& tf = *reinterpret_cast<TileFinal*>(fu_smem);
     int* rowtab = reinterpret_cast<int*>(fu_smem + sizeof(TileFinal));     // [16][3]: ring offsets of the two source rows, wy
-    uint32_t* raw = reinterpret_cast<uint32_t*>(fu_smem + sizeof(TileFinal) + 256);
+    float* hef = reinterpret_cast<float*>(fu_smem + sizeof(TileFinal) + 256);   // [768] float tables of the equalisation
+    uint32_t* raw = reinterpret_cast<uint32_t*>(fu_smem + sizeof(TileFinal) + 256 + 3072);
     const PPParams& p = r.p;
     const int Ty = p.Ty, Tx = p.Tx, NT = blockDim.x, tid = threadIdx.x, b = blockIdx.x;
     float* planes = reinterpret_cast<float*>(raw + (size_t)r.rawrows * Tx);
@@ -2204,6 +2205,13 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
         __syncthreads();
     }
     const bool valid = tf.valid != 0;
+    if (valid && tf.use_he) {              // float copies of the interpolation tables: centres, slopes, cdf
+        for (int i = tid; i < 256; i += NT) {
+            hef[i] = (float)(tf.he.center[i] - tf.he.center[0]);
+            hef[256 + i] = (float)tf.he.slope[i];
+            hef[512 + i] = (float)tf.he.cdf[i];
+        }
+    }
     // distinct planes: channel c reads plane pidx[c]
     const int pidx1 = (!valid || tf.same01) ? 0 : 1;
     const int pidx2 = (!valid || tf.same02) ? 0 : (tf.same12 ? pidx1 : pidx1 + 1);
@@ -2286,11 +2294,20 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
                 const int ci = chan_of_plane[q];
                 const Comp& cc = tf.cc[ci];
                 const int nz = cc.nzx;
-                if (cc.ok && !cc.has_he && nz <= 2) {
-                    const double a = cc.a0, bb = cc.b0;
-                    const float l = (float)cc.l0, h = (float)cc.h0;
+                if (cc.ok && nz <= 2) {
+                    // affine + clamp (fp64 FMA, clamp in fp32) with at most two masked intervals in registers; a
+                    // histogram equalisation in the middle is interpolated in fp32 from float copies of the tables
+                    // (np.interp is continuous: a bracket that is off by one ulp of v changes nothing measurable)
+                    const bool he = cc.has_he != 0;
+                    // with an equalisation the first map is taken relative to the first histogram centre (folded into
+                    // the fp64 FMA), so the fp32 interpolation works on offsets of at most 256 bin widths
+                    const double c0d = he ? tf.he.center[0] : 0.0;
+                    const double a = cc.a0, bb = cc.b0 - c0d;
+                    const float l = (float)(cc.l0 - c0d), h = (float)(cc.h0 - c0d);
                     const float z00 = nz > 0 ? cc.zx0[0] : INFINITY, z01 = nz > 0 ? cc.zx1[0] : -INFINITY;
                     const float z10 = nz > 1 ? cc.zx0[1] : INFINITY, z11 = nz > 1 ? cc.zx1[1] : -INFINITY;
+                    const float a1 = (float)cc.a1, b1 = (float)cc.b1, l1 = (float)cc.l1, h1 = (float)cc.h1;
+                    const float hstep = (float)tf.he.inv_step;
 #pragma unroll 4
                     for (int i = tid; i < n; i += NT) {
                         const int rr = (int)__umulhi((unsigned)i, r.magic_tx);
@@ -2300,7 +2317,19 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
                         float f = decode_pixel(raw[i], p.big_endian);
                         if (p.border_mask && !in_box(p, nlo + rr, x)) f = 0.0f;
                         const bool masked = (f == 0.0f) || (f >= z00 && f <= z01) || (f >= z10 && f <= z11);
-                        const float v = fminf(fmaxf((float)fma(a, (double)f, bb), l), h);
+                        float v = fminf(fmaxf((float)fma(a, (double)f, bb), l), h);
+                        if (he) {
+                            // np.interp(v, centers, cdf): bracket guess from the uniform spacing, corrected by <= 2 steps
+                            int lo = min(254, max(0, (int)(v * hstep)));
+                            lo -= (lo > 0 && hef[lo] > v);
+                            lo -= (lo > 0 && hef[lo] > v);
+                            lo += (lo < 254 && hef[lo + 1] <= v);
+                            lo += (lo < 254 && hef[lo + 1] <= v);
+                            float u = fmaf(hef[256 + lo], v - hef[lo], hef[512 + lo]);
+                            if (!(v > 0.0f)) u = hef[512];
+                            if (v >= hef[255]) u = hef[512 + 255];
+                            v = fminf(fmaxf(fmaf(a1, u, b1), l1), h1);
+                        }
                         pl[slot * Tx + x] = masked ? 0.0f : v;
                     }
                 } else {
@@ -2777,7 +2806,7 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
         f.magic_tx = (unsigned)(((1ull << 32) + (unsigned)Tx - 1) / (unsigned)Tx);
         f.magic_tx4 = (Tx % 4 == 0) ? (unsigned)(((1ull << 32) + (unsigned)(Tx / 4) - 1) / (unsigned)(Tx / 4)) : 0u;
         const size_t tab = ((size_t)lg.Sw * 12 + (size_t)lg.Sh * 20 + (size_t)f.nbands * 8 + 255) & ~(size_t)255;
-        const size_t smem = sizeof(TileFinal) + 256 + (size_t)cap * Tx * 4 * 4;
+        const size_t smem = sizeof(TileFinal) + 256 + 3072 + (size_t)cap * Tx * 4 * 4;
         if (tab <= kFuTableBytes && smem <= kFuSmemMax && (long long)cap * Tx < (1ll << 32) / Tx) {
             char* t = fu_tables;
             f.gx0 = (int*)t; t += (size_t)lg.Sw * 4;

@@ -174,7 +174,7 @@ class Engine(object):
         ops.preprocess(self.pp_cfg, img_dev, row_stride, big_endian, x0, y0, Ty, Tx, self.imgsz, scratch=scratch,
                        chain_out=chain, model_in=model_in, status=status, want_chain=want_chain)
         self._stage('preprocess', e)
-        self.launches += 3
+        self.launches += 4        # bucket, chain, geometry, fused final
         if self.tile_img_sink is not None:   # Analyzer.write_fits: channel 0 of the preprocessed image, accepted tiles
             ok = status.cpu().numpy()
             ch0 = chain[:, :, :, 0].cpu().numpy()
@@ -223,7 +223,7 @@ class Engine(object):
 
     def pp_kernels(self):
         """Names of the preprocessing kernels cy_preprocess launches for this configuration (bench.py's roofline)."""
-        return "pp_bucket_kernel + pp_chain_kernel + pp_final_kernel"
+        return "pp_bucket_kernel + pp_chain_kernel + pp_geom_kernel + pp_fused_kernel"
 
     def finish(self):
         """Compacts the per-tile record slots -> (packed uint8 tensor of n cy_det_record, n) in tile-id order.

@@ -270,8 +270,8 @@ typedef int (*cy_allgather_fn)(void* user, const void* send_dev, void* recv_dev,
 int cy_ctx_create(void* model, const cy_pp_chain* chain_host, const cy_run_config* cfg_host, void** ctx_host);
 int cy_ctx_set_allgather(void* ctx, cy_allgather_fn fn, void* user);
 int cy_ctx_destroy(void* ctx);
-/* This rank's share: file -> records of its tiles (device, tile-id order).  Only unscaled BITPIX = -32 images with 2-4
- * axes are read in place (the reference takes plane [0,0] of a cube); other payloads: convert on the host and use the
+/* This rank's share: file -> records of its tiles (device, tile-id order).  Only unscaled BITPIX = -32 images with 2 or 4
+ * axes are read in place (the reference takes plane [0,0] of a 4-D cube); other payloads: convert on the host and use the
  * _payload form (rows of 4-byte pixels in host memory, big_endian = raw FITS byte order, pinned != 0: page-locked). */
 int cy_run_local(void* ctx, const char* fits_path, int* nrecords_host);
 int cy_run_local_payload(void* ctx, const void* payload_host, int ny, int nx, int big_endian, int pinned,
