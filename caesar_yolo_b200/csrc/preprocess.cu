@@ -826,7 +826,16 @@ __device__ __forceinline__ void for_list_elements(const Shared& sh, const TileVi
         for (int q = 0; q < nitems; ++q) {
             const int aa = __shfl_sync(0xffffffffu, a, q), ee = __shfl_sync(0xffffffffu, e, q);
             const int en = __shfl_sync(0xffffffffu, ent, q);
-            for (int k = aa + lane; k < ee; k += 32) f(tv.vals[k], en);
+            // four loads in flight per lane: the walk is bound by the latency of these global loads
+            int k = aa + lane;
+            for (; k + 96 < ee; k += 128) {
+                const float v0 = tv.vals[k], v1 = tv.vals[k + 32], v2 = tv.vals[k + 64], v3 = tv.vals[k + 96];
+                f(v0, en);
+                f(v1, en);
+                f(v2, en);
+                f(v3, en);
+            }
+            for (; k < ee; k += 32) f(tv.vals[k], en);
         }
     }
 }
