@@ -55,8 +55,43 @@ class SFinder(object):
             return make_pp_config(enabled=False)
         if isinstance(dp, DataPreprocessor):
             return dp.pp_config
-        raise NotImplementedError("config['preprocess_fcn'] must be a caesar_yolo_b200.preprocessing.DataPreprocessor "
-                                  "(arbitrary Python callables cannot run inside the CUDA tile pipeline)")
+        # any other callable (the reference's seam is "ndarray[H,W,3] -> ndarray[H,W,3] | None",
+        # evaluation.py:157-161) runs on the host, tile by tile (_process_tiles_host_callable); the CUDA chain is off
+        return make_pp_config(enabled=False)
+
+    def _host_callable(self):
+        dp = self.config.get('preprocess_fcn')
+        return dp if (dp is not None and not isinstance(dp, DataPreprocessor)) else None
+
+    def _process_tiles_host_callable(self, eng, tiles, ids, fcn):
+        """Tiles through a foreign preprocess_fcn: TileTask.find_sources -> Analyzer.predict (inference.py:190-215,
+        evaluation.py:128-193) with the callable on the HOST (it is the user's Python), everything after it on the GPU:
+        letterbox + forward + decode / NMS + per-tile merge + records, one tile per launch sequence."""
+        for tid in ids:
+            t = tiles[int(tid)]
+            x0, x1, y0, y1 = int(t['xmin']), int(t['xmax']), int(t['ymin']), int(t['ymax'])
+            rows = self.fits.rows(y0, y1)
+            data = np.array(rows[:, x0:x1], copy=True)
+            if self.fits.is_raw_f32:
+                data = data.view('>f4').astype(np.float32)
+            data = data.astype(np.float64)
+            data[~np.isfinite(data)] = 0                              # utils.py:219,394
+            H, W = data.shape
+            cube = np.zeros((H, W, 3))
+            cube[:, :, 0] = cube[:, :, 1] = cube[:, :, 2] = data      # evaluation.py:146-154
+            status = torch.zeros(1, dtype=torch.int32, device=eng.device)
+            out = fcn(cube)
+            if out is None or getattr(out, 'ndim', 0) != 3 or out.shape[2] != 3:
+                status[0] = -1                                        # evaluation.py:164-166
+                out = np.zeros((H, W, 3), np.float32)
+            else:   # evaluation.py:171-176 (bug-compatible: image[i] is ROW i)
+                if any(np.min(out[i]) == np.max(out[i]) for i in range(min(3, out.shape[0]))):
+                    status[0] = -1
+            H, W = out.shape[:2]
+            x, _ = ops.letterbox_resize(torch.from_numpy(np.ascontiguousarray(out, dtype=np.float32)).to(eng.device)
+                                        .unsqueeze(0), eng.imgsz, dtype=eng.model.dtype)
+            Sh, Sw, lb = ops.letterbox_shape(H, W, eng.imgsz)
+            eng._run_batch(x, status, torch.tensor([int(tid)], dtype=torch.int32, device=eng.device), H, W, Sh, Sw, lb)
 
     def _device(self):
         devs = self.config.get('devices') or ['cuda:0']
@@ -133,11 +168,14 @@ class SFinder(object):
         eng = self._engine()
         tiles = np.zeros(1, dtype=ops.TILE_DTYPE)
         tiles[0] = (x0, x1, y0, y1)
-        img = self.fits.rows(y0, y1)
         t0 = time.time()
         eng.begin(tiles)
-        dev_img = torch.from_numpy(np.array(img, copy=True).view(np.int32)).to(eng.device)   # memmap rows are read-only
-        eng.process_tiles(dev_img, self.fits.nx, self.fits.is_raw_f32, 0, y0, [0])
+        if self._host_callable() is not None:
+            self._process_tiles_host_callable(eng, tiles, [0], self._host_callable())
+        else:
+            img = self.fits.rows(y0, y1)
+            dev_img = torch.from_numpy(np.array(img, copy=True).view(np.int32)).to(eng.device)   # memmap rows are read-only
+            eng.process_tiles(dev_img, self.fits.nx, self.fits.is_raw_f32, 0, y0, [0])
         packed, n = eng.finish()
         recs = packed.cpu().numpy().view(ops.REC_DTYPE)
         status = 0
@@ -243,8 +281,16 @@ class SFinder(object):
                 st = eng.tile_status[a:b].cpu().numpy()
                 catalog.write_tile_outputs(recs, tiles, np.arange(a, b), st, self.class_names, self.image_id,
                                            self.outdir, self.save_tile_json, self.save_tile_regions)
-        src, n = run_image(eng, img, self.fits.is_raw_f32, tiles, rank=self.procId, world=self.nproc,
-                           on_local_records=hook)
+        if self._host_callable() is not None:
+            from .pipeline import split_tile_rows
+            eng.begin(tiles)
+            a, b = split_tile_rows(tiles, self.nproc)[self.procId]
+            eng._my_range = (a, b)
+            self._process_tiles_host_callable(eng, tiles, range(a, b), self._host_callable())
+            src, n = eng.exchange_and_merge(self.nproc, rank0_only=True, rank=self.procId, on_local_records=hook)
+        else:
+            src, n = run_image(eng, img, self.fits.is_raw_f32, tiles, rank=self.procId, world=self.nproc,
+                               on_local_records=hook)
         self.timing['run_s'] = time.time() - t0
         if self.procId == 0:
             self.sources = {"sources": catalog.sources_to_dicts(src, self.class_names)}

@@ -453,3 +453,41 @@ def test_tiled_mosaic_yolo11(tmp_path):
     slack = 0.05 + 2.0 / max(len(emu), 1)
     assert m_emu >= 0.90 - slack, m_emu
     assert m_f32 >= min(0.995, m_ref) - slack, (m_f32, m_ref)
+
+
+def test_foreign_preprocess_callable(tmp_path):
+    """config['preprocess_fcn'] may be ANY callable ndarray[H,W,3] -> ndarray[H,W,3] | None (evaluation.py:157-161): a
+    plain numpy function runs on the host tile by tile, the rest of the path on the GPU.  Compared with the oracle
+    SFinder given the same callable; a callable returning None rejects every tile (empty catalog, rc 0)."""
+    from caesar_yolo_b200 import synth, weights as W
+    from caesar_yolo_b200.inference import SFinder
+    from caesar_yolo_b200.model import YOLO
+
+    def fcn(cube):                       # sqrt stretch + min-max to 0..255: not expressible as a monotone op list of ours
+        lo, hi = np.percentile(cube, 1), np.percentile(cube, 99.5)
+        if not hi > lo:
+            return None
+        y = np.clip((cube - lo) / (hi - lo), 0, 1)
+        return np.sqrt(y) * 255.0
+
+    mosaic = synth.make_mosaic(1024, 1536, seed=8, nan_border_frac=0.0)
+    path = str(tmp_path / "m.fits")
+    synth.write_fits(path, mosaic)
+    w = W.make_random_weights('n', 5, seed=0, recipe='v2', cls_bias=W.V2_CLS_BIAS['n'])
+    sf = SFinder(YOLO(w, precision='fp16'), _config(path, str(tmp_path), fcn, True))
+    assert sf.run_parallel() == 0
+    got = json.load(open(str(tmp_path / "catalog_m.json")))['sources']
+    os.rename(str(tmp_path / "catalog_m.json"), str(tmp_path / "ours.json"))
+    osf = oinf.SFinder(oy.OracleModel(w), _config(path, str(tmp_path), fcn, True, devices=['cpu']))
+    assert osf.run_parallel() == 0
+    want = osf.sources['sources']
+    m = match_fraction(got, want)
+    print("foreign callable: ours %d, oracle %d sources, matched %.4f" % (len(got), len(want), m))
+    assert len(want) >= 10 and m >= 0.95 - 2.0 / len(want)
+    # serial path through the same seam
+    sf1 = SFinder(YOLO(w, precision='fp16'), _config(path, str(tmp_path), fcn, False))
+    assert sf1.run() == 0 and os.path.exists(str(tmp_path / "out_m.json"))
+    # a callable that rejects everything
+    sf2 = SFinder(YOLO(w, precision='fp16'), _config(path, str(tmp_path), lambda c: None, True))
+    assert sf2.run_parallel() == 0
+    assert json.load(open(str(tmp_path / "catalog_m.json")))['sources'] == []
