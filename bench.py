@@ -404,6 +404,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     from caesar_yolo_b200 import catalog, ops, pipeline, weights as W
     hbm_peak, tf_sust, tf_burst, peak_kind = peaks()
+    numa_node = pipeline.bind_host_to_device_numa(local) if world > 1 else None   # node-local pinned staging per rank
 
     img_native, host = make_mosaic_pinned(args)
     tiles = ops.generate_tiles(0, args.mosaic - 1, 0, args.mosaic - 1, args.tile, args.tile, args.step, args.step)
@@ -522,6 +523,7 @@ def main():
             "stage_ms_per_step": {k: round(v, 3) for k, v in stage_ms.items()}}
     if file_info is not None:
         line["e2e_file"] = file_info
+    line["host_numa_node"] = numa_node       # node the rank-0 process (and its pinned staging) was bound to; None: not bound
     known = sum(stage_ms.get(k, 0.0) for k in ('preprocess', 'forward', 'decode_nms', 'merge_tile_records'))
     line["exchange_ms"] = round(stage_ms.get('exchange', 0.0), 3)
     line["unattributed_ms"] = round(ms_step - known - stage_ms.get('exchange', 0.0) - stage_ms.get('merge_global', 0.0), 3)

@@ -2404,6 +2404,274 @@ __global__ void __launch_bounds__(kFuMaxThreads, 2) pp_fused_kernel(const __grid
     cp_async_wait_all();
 }
 
+// ------------------------------------------------------------------------------------------ kernel 3c: fused final, interleaved planes
+//
+// pp_fused4_kernel: the same pass as pp_fused_kernel with half the instructions.  The second profile (r02k) showed
+// pp_fused_kernel issue-bound at 81 % of the issue slots: 63 instructions per pixel and plane in Phase A (the pixel was
+// decoded and indexed once per plane) and 95 per output pixel in Phase B (twelve 4-byte shared-memory loads with their
+// own addresses).  Here the three maps of a pixel are evaluated in ONE pass (per-plane constants in registers) and stored
+// as one float4 (p0, p1, p2, -) in the ring, so a bilinear tap is ONE 16-byte load; a thread owns up to five output
+// columns (their geometry in registers) and every fourth row of the band.
+static constexpr int kFu4Threads = 512;
+
+struct PlaneK {              // constants of one distinct plane (registers)
+    double a, b;             // first affine map (relative to the first histogram centre when he)
+    float l, h;
+    float z00, z01, z10, z11;
+    float a1, b1, l1, h1;    // second affine map (after the equalisation)
+    int mode;                // 0: affine + clamp, 1: + equalisation, 2: generic (eval_fast)
+};
+
+__device__ __forceinline__ float plane_value(const PlaneK& k, const TileFinal& tf, int ci, const float* __restrict__ hef,
+                                             float hstep, float f) {
+    if (k.mode == 2) {
+        const Comp& cc = tf.cc[ci];
+        const bool masked = (f == 0.0f) || in_zero_x(cc, cc.nzx, f);
+        return masked ? 0.0f : (float)eval_fast(cc, tf.ch[ci], tf.he, (double)f);
+    }
+    const bool masked = (f == 0.0f) || (f >= k.z00 && f <= k.z01) || (f >= k.z10 && f <= k.z11);
+    float v = fminf(fmaxf((float)fma(k.a, (double)f, k.b), k.l), k.h);
+    if (k.mode == 1) {
+        int lo = min(254, max(0, (int)(v * hstep)));
+        lo -= (lo > 0 && hef[lo] > v);
+        lo -= (lo > 0 && hef[lo] > v);
+        lo += (lo < 254 && hef[lo + 1] <= v);
+        lo += (lo < 254 && hef[lo + 1] <= v);
+        float u = fmaf(hef[256 + lo], v - hef[lo], hef[512 + lo]);
+        if (!(v > 0.0f)) u = hef[512];
+        if (v >= hef[255]) u = hef[512 + 255];
+        v = fminf(fmaxf(fmaf(k.a1, u, k.b1), k.l1), k.h1);
+    }
+    return masked ? 0.0f : v;
+}
+
+__device__ __forceinline__ PlaneK make_plane(const TileFinal& tf, int ci, bool valid) {
+    PlaneK k;
+    const Comp& cc = tf.cc[ci];
+    const int nz = cc.nzx;
+    k.mode = (cc.ok && nz <= 2) ? (cc.has_he ? 1 : 0) : 2;
+    if (!valid) k.mode = 0;
+    const double c0d = (valid && k.mode == 1) ? tf.he.center[0] : 0.0;
+    k.a = valid ? cc.a0 : 0.0;
+    k.b = valid ? cc.b0 - c0d : 0.0;
+    k.l = valid ? (float)(cc.l0 - c0d) : 0.0f;
+    k.h = valid ? (float)(cc.h0 - c0d) : 0.0f;
+    k.z00 = (valid && nz > 0) ? cc.zx0[0] : INFINITY;
+    k.z01 = (valid && nz > 0) ? cc.zx1[0] : -INFINITY;
+    k.z10 = (valid && nz > 1) ? cc.zx0[1] : INFINITY;
+    k.z11 = (valid && nz > 1) ? cc.zx1[1] : -INFINITY;
+    k.a1 = (float)cc.a1; k.b1 = (float)cc.b1; k.l1 = (float)cc.l1; k.h1 = (float)cc.h1;
+    return k;
+}
+
+__global__ void __launch_bounds__(kFu4Threads, 2) pp_fused4_kernel(const __grid_constant__ FusedParams r) {
+    extern __shared__ __align__(16) unsigned char fu_smem[];
+    TileFinal& tf = *reinterpret_cast<TileFinal*>(fu_smem);
+    int* rowtab = reinterpret_cast<int*>(fu_smem + sizeof(TileFinal));          // [16][3]
+    float* hef = reinterpret_cast<float*>(fu_smem + sizeof(TileFinal) + 256);   // [768]
+    uint32_t* raw = reinterpret_cast<uint32_t*>(fu_smem + sizeof(TileFinal) + 256 + 3072);
+    const PPParams& p = r.p;
+    const int Tx = p.Tx, NT = kFu4Threads, tid = threadIdx.x, b = blockIdx.x;
+    float4* ring = reinterpret_cast<float4*>(raw + (size_t)r.rawrows * Tx);     // [ring rows][Tx] (p0, p1, p2, -)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(&p.fin[b]);
+        uint4* dst = reinterpret_cast<uint4*>(&tf);
+        const int n_head = (int)(offsetof(TileFinal, he) / 16), n_all = (int)(sizeof(TileFinal) / 16);
+        const int n_tail0 = (int)((offsetof(TileFinal, he) + sizeof(HistEq)) / 16);
+        for (int i = n_tail0 + tid; i < n_all; i += NT) dst[i] = src[i];
+        __syncthreads();
+        if (tf.valid) {
+            for (int i = tid; i < n_head; i += NT) dst[i] = src[i];
+            if (tf.use_he)
+                for (int i = n_head + tid; i < n_tail0; i += NT) dst[i] = src[i];
+        }
+        __syncthreads();
+    }
+    const bool valid = tf.valid != 0;
+    if (valid && tf.use_he) {
+        for (int i = tid; i < 256; i += NT) {
+            hef[i] = (float)(tf.he.center[i] - tf.he.center[0]);
+            hef[256 + i] = (float)tf.he.slope[i];
+            hef[512 + i] = (float)tf.he.cdf[i];
+        }
+    }
+    const float hstep = (valid && tf.use_he) ? (float)tf.he.inv_step : 0.0f;
+    const int pidx1 = (!valid || tf.same01) ? 0 : 1;
+    const int pidx2 = (!valid || tf.same02) ? 0 : (tf.same12 ? pidx1 : pidx1 + 1);
+    const int np = max(pidx1, pidx2) + 1;
+    const int c1 = pidx1 ? 1 : 0, c2 = pidx2 > pidx1 ? 2 : (pidx2 ? c1 : 0);   // a channel of plane 1 / plane 2
+    const PlaneK k0 = make_plane(tf, 0, valid);
+    const PlaneK k1 = make_plane(tf, np > 1 ? (pidx1 == 1 ? 1 : 2) : 0, valid);
+    const PlaneK k2 = make_plane(tf, np > 2 ? 2 : 0, valid);
+    const int ci1 = np > 1 ? (pidx1 == 1 ? 1 : 2) : 0, ci2 = np > 2 ? 2 : 0;
+    (void)c1; (void)c2;
+    const long long g_row0 = (long long)p.y0[b] * p.row_stride + p.x0[b];
+    const uint32_t* gimg = p.img + g_row0;
+    const bool vec16 = ((reinterpret_cast<uintptr_t>(p.img) & 15) == 0) && ((p.row_stride & 3) == 0) && ((g_row0 & 3) == 0) &&
+                       ((Tx & 3) == 0);
+    const int bnd0 = (int)(((long long)blockIdx.y * r.nbands) / gridDim.y);
+    const int bnd1 = (int)(((long long)(blockIdx.y + 1) * r.nbands) / gridDim.y);
+    int have = -1, nlo = 1, nhi = 0;
+    auto stage_rows = [&](int band) {
+        nlo = 1; nhi = 0;
+        if (band < bnd1) {
+            const int lo = __ldg(&r.gband[2 * band]), hi = __ldg(&r.gband[2 * band + 1]);
+            if (lo <= hi) {
+                nlo = have < 0 ? lo : max(lo, have);
+                nhi = hi;
+            }
+        }
+        if (nlo > nhi) return;
+        const int m = nhi - nlo + 1;
+        if (vec16) {
+            const int w4 = Tx >> 2, n4 = m * w4;
+            for (int i = tid; i < n4; i += NT) {
+                const int q = (int)__umulhi((unsigned)i, r.magic_tx4);
+                const int x4 = i - q * w4;
+                cp_async16(raw + (size_t)q * Tx + 4 * x4, gimg + (long long)(nlo + q) * p.row_stride + 4 * x4);
+            }
+        } else {
+            const int n = m * Tx;
+            for (int i = tid; i < n; i += NT) {
+                const int q = (int)__umulhi((unsigned)i, r.magic_tx);
+                cp_async4(raw + i, gimg + (long long)(nlo + q) * p.row_stride + (i - q * Tx));
+            }
+        }
+    };
+    stage_rows(bnd0);
+    cp_async_commit();
+
+    // Phase B ownership: thread = (column lane tid & 127, row group tid >> 7); columns lane, lane + 128, ... (<= 5 kept in
+    // registers), rows group, group + 4, ...
+    const int lane_c = tid & 127, grp = tid >> 7;
+    constexpr int kCols = 5;
+    int cx0[kCols], cx1[kCols];
+    float cwx[kCols];
+#pragma unroll
+    for (int c = 0; c < kCols; ++c) {
+        const int ox = lane_c + 128 * c;
+        cx0[c] = -2;                       // -2: no such column, -1: padding column
+        cx1[c] = 0;
+        cwx[c] = 0.f;
+        if (ox < r.Sw) {
+            cx0[c] = __ldg(&r.gx0[ox]);
+            cx1[c] = __ldg(&r.gx1[ox]);
+            cwx[c] = __ldg(&r.gxw[ox]);
+        }
+    }
+    const float pad = div255(114.f);
+    for (int band = bnd0; band < bnd1; ++band) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid < r.band_h) {
+            const int oy = band * r.band_h + tid;
+            int o0 = -1, o1 = -1, wyb = 0;
+            if (oy < r.Sh && __ldg(&r.gy0[oy]) >= 0) {
+                o0 = __ldg(&r.gs0[oy]);
+                o1 = __ldg(&r.gs1[oy]);
+                wyb = __float_as_int(__ldg(&r.gwy[oy]));
+            }
+            rowtab[3 * tid] = o0;
+            rowtab[3 * tid + 1] = o1;
+            rowtab[3 * tid + 2] = wyb;
+        }
+        // ---- Phase A: every new source pixel once, its three plane values as one float4
+        if (nlo <= nhi) {
+            const int n = (nhi - nlo + 1) * Tx;
+            const int slot0 = nlo % r.ring;
+#pragma unroll 2
+            for (int i = tid; i < n; i += NT) {
+                const int rr = (int)__umulhi((unsigned)i, r.magic_tx);
+                const int x = i - rr * Tx;
+                int slot = slot0 + rr;
+                if (slot >= r.ring) slot -= r.ring;
+                float f = decode_pixel(raw[i], p.big_endian);
+                if (p.border_mask && !in_box(p, nlo + rr, x)) f = 0.0f;
+                float4 v;
+                v.x = plane_value(k0, tf, 0, hef, hstep, f);
+                v.y = np > 1 ? plane_value(k1, tf, ci1, hef, hstep, f) : v.x;
+                v.z = np > 2 ? plane_value(k2, tf, ci2, hef, hstep, f) : v.x;
+                v.w = 0.f;
+                ring[slot * Tx + x] = v;
+            }
+            have = nhi + 1;
+        }
+        __syncthreads();
+        stage_rows(band + 1);
+        cp_async_commit();
+        // ---- Phase B
+        const int oy0 = band * r.band_h, nrows = min(r.Sh, oy0 + r.band_h) - oy0;
+        for (int k = grp; k < nrows; k += kFu4Threads / 128) {
+            const int o0 = rowtab[3 * k], o1 = rowtab[3 * k + 1];
+            const float wy = __int_as_float(rowtab[3 * k + 2]), uy = 1.f - wy;
+            unsigned short* orow = reinterpret_cast<unsigned short*>(r.out16) + (((long long)b * r.Sh + oy0 + k) * r.Sw) * 4;
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) {
+                if (cx0[c] == -2) continue;
+                const int ox = lane_c + 128 * c;
+                float m0 = pad, m1 = pad, m2 = pad;
+                if (o0 >= 0 && cx0[c] >= 0) {
+                    const float wx = cwx[c], ux = 1.f - wx;
+                    const float4 q00 = ring[o0 + cx0[c]], q01 = ring[o0 + cx1[c]];
+                    const float4 q10 = ring[o1 + cx0[c]], q11 = ring[o1 + cx1[c]];
+                    const float t0 = (q00.x * ux + q01.x * wx) * uy + (q10.x * ux + q11.x * wx) * wy;
+                    float t1 = t0, t2 = t0;
+                    if (np > 1) t1 = (q00.y * ux + q01.y * wx) * uy + (q10.y * ux + q11.y * wx) * wy;
+                    if (np > 2) t2 = (q00.z * ux + q01.z * wx) * uy + (q10.z * ux + q11.z * wx) * wy;
+                    const float v1 = pidx1 == 0 ? t0 : t1;
+                    const float v2 = pidx2 == 0 ? t0 : (pidx2 == 1 ? t1 : t2);
+                    m0 = div255(v2);      // predictor.preprocess: channel reversal, /255
+                    m1 = div255(v1);
+                    m2 = div255(t0);
+                }
+                uint2 pk;
+                pk.x = pack_h2(m0, m1, r.f16);
+                pk.y = pack_h2(m2, 0.f, r.f16);
+                *reinterpret_cast<uint2*>(orow + (long long)ox * 4) = pk;
+                if (r.out_f32) {
+                    const long long plane = (long long)r.Sh * r.Sw;
+                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)(oy0 + k) * r.Sw + ox;
+                    of[0] = m0;
+                    of[plane] = m1;
+                    of[2 * plane] = m2;
+                }
+            }
+        }
+        // columns beyond 5 x 128 (Sw > 640): plain loop
+        for (int ox = 128 * kCols + lane_c; ox < r.Sw; ox += 128) {
+            const int x0 = __ldg(&r.gx0[ox]), x1 = __ldg(&r.gx1[ox]);
+            const float wx = __ldg(&r.gxw[ox]), ux = 1.f - wx;
+            for (int k = grp; k < nrows; k += kFu4Threads / 128) {
+                const int o0 = rowtab[3 * k], o1 = rowtab[3 * k + 1];
+                const float wy = __int_as_float(rowtab[3 * k + 2]), uy = 1.f - wy;
+                float m0 = pad, m1 = pad, m2 = pad;
+                if (o0 >= 0 && x0 >= 0) {
+                    const float4 q00 = ring[o0 + x0], q01 = ring[o0 + x1], q10 = ring[o1 + x0], q11 = ring[o1 + x1];
+                    const float t0 = (q00.x * ux + q01.x * wx) * uy + (q10.x * ux + q11.x * wx) * wy;
+                    const float t1 = (q00.y * ux + q01.y * wx) * uy + (q10.y * ux + q11.y * wx) * wy;
+                    const float t2 = (q00.z * ux + q01.z * wx) * uy + (q10.z * ux + q11.z * wx) * wy;
+                    m0 = div255(pidx2 == 0 ? t0 : (pidx2 == 1 ? t1 : t2));
+                    m1 = div255(pidx1 == 0 ? t0 : t1);
+                    m2 = div255(t0);
+                }
+                uint2 pk;
+                pk.x = pack_h2(m0, m1, r.f16);
+                pk.y = pack_h2(m2, 0.f, r.f16);
+                *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(r.out16) +
+                                          (((long long)b * r.Sh + oy0 + k) * r.Sw + ox) * 4) = pk;
+                if (r.out_f32) {
+                    const long long plane = (long long)r.Sh * r.Sw;
+                    float* of = r.out_f32 + (long long)b * 3 * plane + (long long)(oy0 + k) * r.Sw + ox;
+                    of[0] = m0;
+                    of[plane] = m1;
+                    of[2 * plane] = m2;
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
 // ------------------------------------------------------------------------------------------ letterbox resize of an HWC image
 
 struct ResizeParams {
@@ -2616,6 +2884,7 @@ static int fin_rows_cap(const LbGeom& g, int Ty, int Tx) {
 
 static constexpr size_t kFuTableBytes = 256 * 1024;   // geometry tables of the fused final kernel (part of the scratch)
 static constexpr size_t kFuSmemMax = 112 * 1024;      // two CTAs per SM
+static constexpr size_t kFu4SmemMax = 200 * 1024;     // interleaved form: 110 KB for 512^2 tiles (two CTAs per SM)
 
 struct BkGeom {
     int nsub, R, nchunks, nbs;
@@ -2738,6 +3007,7 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BkSmem)));
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemMax));
         CY_CUDA_CHECK(cudaFuncSetAttribute(pp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFuSmemMax));
+        CY_CUDA_CHECK(cudaFuncSetAttribute(pp_fused4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFu4SmemMax));
     }
     if (chain.nstages > 0) {
         // TMA staging of the chunks: 2-D boxes of pw x R pixels of the mosaic (16-byte aligned base / pitch / box rows)
@@ -2832,9 +3102,31 @@ extern "C" int cy_preprocess_chain(const cy_pp_chain* chain_in, const void* img,
             f.chunks = chunks;
             const int gmax = lg.Sw > lg.Sh ? lg.Sw : lg.Sh;
             pp_geom_kernel<<<(gmax + 255) / 256, 256, 0, st>>>(f);
-            int nt = (lg.Sw + 31) & ~31;
-            nt = nt > kFuMaxThreads ? kFuMaxThreads : (nt < 128 ? 128 : nt);
-            pp_fused_kernel<<<dim3((unsigned)B, (unsigned)chunks), nt, smem, st>>>(f);
+            // interleaved-plane form (pp_fused4_kernel): staging rows = the most NEW source rows a band brings (all of
+            // a band's rows when a CTA starts in the middle of the tile, i.e. chunks > 1)
+            int max_new = 1, prev_hi = -1;
+            for (int bnd = 0; bnd < f.nbands; ++bnd) {
+                const int oy0 = bnd * kFinBandH, oy1 = oy0 + kFinBandH < lg.Sh ? oy0 + kFinBandH : lg.Sh;
+                const int ry0 = oy0 - lg.top > 0 ? oy0 - lg.top : 0, ry1 = oy1 - lg.top < lg.new_h ? oy1 - lg.top : lg.new_h;
+                if (ry0 >= ry1) continue;
+                int a0, a1, c0, c1;
+                src_coord_host(ry0, lg.scale_y, Ty, &a0, &a1);
+                src_coord_host(ry1 - 1, lg.scale_y, Ty, &c0, &c1);
+                const int lo = a0 > prev_hi + 1 ? a0 : prev_hi + 1;
+                if (c1 - lo + 1 > max_new) max_new = c1 - lo + 1;
+                prev_hi = c1;
+            }
+            const int raw4 = chunks > 1 ? cap : (max_new < cap ? max_new : cap);
+            const size_t smem4 = sizeof(TileFinal) + 256 + 3072 + (size_t)raw4 * Tx * 4 + (size_t)cap * Tx * 16;
+            const char* v1 = getenv("CY_PP_FUSED_V1");
+            if (smem4 <= kFu4SmemMax && !(v1 && atoi(v1))) {
+                f.rawrows = raw4;
+                pp_fused4_kernel<<<dim3((unsigned)B, (unsigned)chunks), kFu4Threads, smem4, st>>>(f);
+            } else {
+                int nt = (lg.Sw + 31) & ~31;
+                nt = nt > kFuMaxThreads ? kFuMaxThreads : (nt < 128 ? 128 : nt);
+                pp_fused_kernel<<<dim3((unsigned)B, (unsigned)chunks), nt, smem, st>>>(f);
+            }
             fused_done = true;
         }
     }

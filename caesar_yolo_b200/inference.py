@@ -107,6 +107,9 @@ class SFinder(object):
             weights = self.model.weights if hasattr(self.model, 'weights') else self.model
             dev = self._device()
             torch.cuda.set_device(dev)
+            if self.nproc > 1:       # one process per GPU: node-local pinned staging and reader threads
+                from .pipeline import bind_host_to_device_numa
+                bind_host_to_device_numa(dev.index if dev.index is not None else 0)
             dm = self.model.device_model() if hasattr(self.model, 'device_model') else weights
             self.engine = Engine(dm, self._pp_config(), imgsz=self.config['img_size'],
                                  score_thr=self.config['score_thr'], iou_thr=self.config['iou_thr'],

@@ -326,6 +326,36 @@ class Engine(object):
         return want
 
 
+def bind_host_to_device_numa(device_index):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned staging
+    buffers it allocates afterwards are node-local (first touch) and the reader threads run next to them: with one
+    process per GPU and every rank uploading its band at the same time, remote-node staging halves the H2D rate.
+    Returns the node (or None when the topology is not visible: nothing is changed then)."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def split_tile_rows(tiles, nparts):
     """Partition of the row-major tile grid into `nparts` contiguous bands of whole tile rows, balanced by tile count.
     Returns list of (first_tile_id, last_tile_id_exclusive).  (Replaces the reference's round-robin tile->rank map,

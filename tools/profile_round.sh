@@ -26,7 +26,7 @@ for IDX in 2 26 87; do
     ncu -i $O/${TAG}_conv_full_$IDX.ncu-rep --page details --csv > $O/${TAG}_conv_full_${IDX}_details.csv 2>/dev/null
 done
 # 4. --set full of the preprocessing kernels (first group of the bench command) and the stem
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pp_sort_kernel|pp_chain_kernel|pp_resize_kernel' -c 3 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pp_bucket_kernel|pp_chain_kernel|pp_fused_kernel' -c 3 \
     -f -o $O/${TAG}_pp_full $BENCH > $O/${TAG}_ncu_pp_full.log 2>&1
 ncu -i $O/${TAG}_pp_full.ncu-rep --page details --csv > $O/${TAG}_pp_full_details.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'stem_conv_kernel|sppf_pool3_kernel|upsample2_kernel|score_key_kernel|nms_tiles_kernel' -c 6 \
