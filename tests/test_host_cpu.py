@@ -200,3 +200,13 @@ def test_fits_reader_cubes_scaling_and_integer_payloads(tmp_path):
                             "NAXIS1  =                   11", "NAXIS2  =                    7"], a.tobytes())
         f = FitsImage(p)
         assert f.bitpix == bitpix and np.array_equal(f.rows(1, 6), a[1:6].astype(np.float32))
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    """bind_host_to_device_numa must never raise: without a visible GPU / sysfs topology it returns None and leaves the
+    affinity mask alone."""
+    import os
+    from caesar_yolo_b200 import pipeline
+    before = os.sched_getaffinity(0)
+    assert pipeline.bind_host_to_device_numa(0) is None
+    assert os.sched_getaffinity(0) == before
