@@ -80,6 +80,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-file', action='store_true', help='skip the FITS-file-inclusive measurement')
+    ap.add_argument('--no-alt', action='store_true', help='skip the informational run in the other 16-bit format')
     a = ap.parse_args()
     if a.mosaic is None:
         a.mosaic = 32768 if a.config == 4 else 16384
@@ -501,6 +502,31 @@ def main():
         except OSError:
             pass
 
+    # The other 16-bit storage format on the same box, same workload (resident timing only): bf16 is the format
+    # north_star names and draws less power per MMA than fp16 (the step sits at the board power cap), fp16 keeps three
+    # more significand bits (parity).  Informational; the headline fields belong to the default format.
+    alt = None
+    if not args.no_alt:
+        altp = 'bf16' if eng.model.precision == 'fp16' else 'fp16'
+        eng2 = pipeline.Engine(w, pipeline.make_pp_config(**PP_FLAGS), imgsz=args.imgsz, score_thr=SCORE_THR,
+                               iou_thr=IOU_THR, thr_soft=SOFT, thr_hard=HARD, device=dev, batch_tiles=args.batch,
+                               precision=altp)
+
+        def step_alt():
+            eng2.begin(tiles)
+            eng2.process_tiles(band_dev, args.mosaic, True, 0, y0b, my_ids)
+            return eng2.exchange_and_merge(world)
+        for _ in range(2):
+            step_alt()
+        k2 = max(2, args.steps // 2)
+        eng2.stage_events = []
+        ms2, _, (src_alt, _) = timed(step_alt, k2)
+        st2 = {k: v / k2 for k, v in eng2.stage_times_ms().items()}
+        alt = {"dtype": altp, "value": T / (ms2 / k2 * 1e-3), "unit": "tiles/s", "ms_per_step": ms2 / k2,
+               "forward_ms_per_step": round(st2.get('forward', 0.0), 3), "sources": int(len(src_alt)),
+               "note": "same box, same workload, mosaic resident; %d timed steps" % k2}
+        del eng2
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -523,6 +549,8 @@ def main():
             "stage_ms_per_step": {k: round(v, 3) for k, v in stage_ms.items()}}
     if file_info is not None:
         line["e2e_file"] = file_info
+    if alt is not None:
+        line["alt_precision"] = alt
     line["host_numa_node"] = numa_node       # node the rank-0 process (and its pinned staging) was bound to; None: not bound
     known = sum(stage_ms.get(k, 0.0) for k in ('preprocess', 'forward', 'decode_nms', 'merge_tile_records'))
     line["exchange_ms"] = round(stage_ms.get('exchange', 0.0), 3)

@@ -40,6 +40,35 @@ class MosaicRunner(object):
         self._cb = ALLGATHER_FN(lambda user, s, r, n, st: int(fn(s, r, n, st)))
         check(lib.cy_ctx_set_allgather(self._h, self._cb, None))
 
+    def set_allgather_torch(self):
+        """Registers torch.distributed's all-gather (NCCL) as the exchange of cy_run_mosaic: the callback stages the
+        slot through two torch tensors on the context's own stream (wrapped as an ExternalStream, so the copies and the
+        collective are ordered with the C side's work without a host synchronisation)."""
+        import torch
+        import torch.distributed as dist
+        from ._capi import c_uptr
+        state = {}
+
+        def gather(send_ptr, recv_ptr, nbytes, stream):
+            try:
+                world = dist.get_world_size()
+                if state.get('n') != nbytes:
+                    dev = torch.device('cuda', torch.cuda.current_device())
+                    state['send'] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    state['recv'] = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
+                    state['n'] = nbytes
+                ext = torch.cuda.ExternalStream(stream)
+                with torch.cuda.stream(ext):
+                    check(lib.cy_memcpy_d2d(c_void_p(state['send'].data_ptr()), c_void_p(send_ptr),
+                                            ctypes.c_size_t(nbytes), c_uptr(stream)))
+                    dist.all_gather_into_tensor(state['recv'], state['send'])
+                    check(lib.cy_memcpy_d2d(c_void_p(recv_ptr), c_void_p(state['recv'].data_ptr()),
+                                            ctypes.c_size_t(nbytes * world), c_uptr(stream)))
+                return 0
+            except Exception:
+                return 1
+        self.set_allgather(gather)
+
     def run(self, fits_path, capacity=1 << 20):
         """-> (sources structured array (ops.SRC_DTYPE), number of records)."""
         out = np.zeros(capacity, dtype=ops.SRC_DTYPE)

@@ -88,3 +88,25 @@ def test_run_mosaic_allgather_callback_single_process(tmp_path):
     with pytest.raises(CaesarB200Error):
         r.run(p16)                       # scaled payloads are converted on the host (cy_run_payload)
     r.close()
+
+
+def test_run_payload_pageable_and_pinned(tmp_path):
+    """cy_run_payload: rows of 4-byte pixels in host memory (native byte order here), pageable and page-locked."""
+    import ctypes
+    from caesar_yolo_b200 import ops, pipeline, runner
+    from caesar_yolo_b200._capi import c_int, c_void_p, check, lib
+    path, dm, ref, nrec = _setup(tmp_path, 1024, 1536, 1.0)
+    from caesar_yolo_b200.fits import FitsImage
+    fimg = FitsImage(path)
+    native = np.ascontiguousarray(np.array(fimg.rows(0, fimg.ny)).view('>f4').astype(np.float32))
+    r = runner.MosaicRunner(dm, pipeline.make_pp_config(**PP), imgsz=640, score_thr=0.5, tile=(512, 512))
+    for pinned in (0, 1):
+        buf = torch.from_numpy(native)
+        if pinned:
+            buf = buf.pin_memory()
+        out = np.zeros(1 << 16, dtype=ops.SRC_DTYPE)
+        ns, nr = c_int(0), c_int(0)
+        check(lib.cy_run_payload(r._h, c_void_p(buf.data_ptr()), c_int(fimg.ny), c_int(fimg.nx), c_int(0), c_int(pinned),
+                                 out.ctypes.data_as(c_void_p), c_int(len(out)), ctypes.byref(ns), ctypes.byref(nr)))
+        assert nr.value == nrec and out[:ns.value].tobytes() == ref.tobytes()
+    r.close()
