@@ -381,10 +381,27 @@ int run_local(RunCtx* c, const RowSource& src, int ny, int nx, int big_endian) {
         for (auto& kv : shapes) {
             const std::vector<int>& ids = kv.second;
             const int n = (int)ids.size();
-            int gsz = bt;
-            if (n >= bt / 2 && n <= bt) gsz = (n + 1) / 2;   // host-staged input: two groups, the second upload overlaps
-            for (int s = 0; s < n; s += gsz) {
-                std::vector<int> g(ids.begin() + s, ids.begin() + std::min(n, s + gsz));
+            // a small LEADING group (the first whole tile rows with >= 32 tiles) starts computing as soon as its rows
+            // are in HBM; the upload of everything else overlaps it (pipeline.lead_group_size)
+            int lead = 0;
+            for (int k = 0; k < n;) {
+                const int y = c->tiles[ids[k]].ymin;
+                while (k < n && c->tiles[ids[k]].ymin == y) ++k;
+                if (k >= 32) {
+                    lead = k;
+                    break;
+                }
+            }
+            std::vector<int> starts;
+            if (lead > 0 && 2 * lead <= n) {
+                starts.push_back(0);
+                for (int s = lead; s < n; s += bt) starts.push_back(s);
+            } else {
+                for (int s = 0; s < n; s += bt) starts.push_back(s);
+            }
+            for (size_t gi = 0; gi < starts.size(); ++gi) {
+                const int s = starts[gi], e = gi + 1 < starts.size() ? starts[gi + 1] : n;
+                std::vector<int> g(ids.begin() + s, ids.begin() + e);
                 int ylast = 0;
                 for (int id : g) ylast = std::max(ylast, c->tiles[id].ymax);
                 if ((rc = ready(ylast))) return rc;

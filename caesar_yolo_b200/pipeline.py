@@ -146,11 +146,15 @@ class Engine(object):
         shapes = sorted(set(zip(h.tolist(), w.tolist())), reverse=True)
         for (Ty, Tx) in shapes:
             ids = tile_ids[(h == Ty) & (w == Tx)]
-            gsz = self.pp_tiles
-            if min_groups > 1 and 2 * 74 <= len(ids) <= self.pp_tiles:
-                gsz = -(-len(ids) // min_groups)      # host-staged input: two groups, so the second upload overlaps
-            for s in range(0, len(ids), gsz):
-                g = ids[s:s + gsz]
+            starts = list(range(0, len(ids), self.pp_tiles))
+            if min_groups > 1:
+                # host-staged input: a small LEADING group (whole tile rows, >= 32 tiles) starts computing as soon as
+                # its rows are in HBM; the upload of everything else overlaps it
+                lead = lead_group_size(self.tiles['ymin'][ids])
+                if 0 < lead and 2 * lead <= len(ids):
+                    starts = [0] + list(range(lead, len(ids), self.pp_tiles))
+            for k, s in enumerate(starts):
+                g = ids[s:(starts[k + 1] if k + 1 < len(starts) else len(ids))]
                 if ready is not None:
                     ready(int(self.tiles['ymax'][g].max()))
                 self._run_group(img_dev, row_stride, big_endian, origin_x, origin_y, g, Ty, Tx)
@@ -324,6 +328,20 @@ class Engine(object):
         want = min(want, self.T * ops.MAX_DET)
         self._buf['xcap'] = want
         return want
+
+
+def lead_group_size(ymins, min_tiles=32):
+    """Tiles of the leading group of a host-staged run: the first whole tile rows that hold at least `min_tiles` tiles
+    (ymins: ymin of the tiles in id order = row-major)."""
+    n = len(ymins)
+    k = 0
+    while k < n:
+        y = ymins[k]
+        while k < n and ymins[k] == y:
+            k += 1
+        if k >= min_tiles:
+            return k
+    return 0
 
 
 def bind_host_to_device_numa(device_index):
@@ -510,8 +528,8 @@ def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, piece_bytes=
     staging), a numpy array / memmap, or a fits.FitsImage (rows are read from the file with preadv into pinned staging
     buffers); big_endian: raw FITS byte order.  The rows of this rank's tiles (contiguous band of tile rows) are
     uploaded in pieces of ~piece_bytes on a copy stream; every tile group waits only for the rows it needs, so all but
-    the first group's read + upload overlap the compute of earlier groups (a rank with less than one full group of
-    tiles is split into two groups for the same reason).
+    the first group's read + upload overlap the compute of earlier groups; the first group is kept small (the first
+    whole tile rows with >= 32 tiles) so that little of the upload is exposed.
     on_local_records(packed, n, first_tile_id, last_tile_id_excl): called with this rank's records before the exchange
     (per-tile output files).  Returns (sources structured array or None on ranks != 0, n_records_total)."""
     engine.begin(tiles)
