@@ -234,3 +234,29 @@ def test_letterbox_resize_matches_cv2_path(Ty, Tx, imgsz):
     nhwc = model_in[0, :, :, :3].permute(2, 0, 1)
     assert (nhwc - want[0]).abs().max().item() <= 2 ** -8 * want.abs().max().item()
     assert (model_in[..., 3] == 0).all()
+
+
+def test_fused_final_ring_path_equals_banded_path():
+    """The production launch shape (>= 296 tiles per call: one CTA walks ALL bands of its tile and keeps the evaluated
+    source rows in the shared-memory ring) must give bit-identical model inputs to small calls (one band per CTA, no
+    row carried over), for 16-byte aligned and unaligned tile columns."""
+    from caesar_yolo_b200 import ops, synth
+    kw = FLAGSETS['config2_255']
+    mosaic = synth.make_mosaic(2048 + 8, 2048 + 8, seed=5, nan_border_frac=0.0)
+    mosaic[700:760, 300:420] = np.nan
+    img = torch.from_numpy(mosaic).to(DEV)
+    cfg = make_cfg(**kw)
+    for off in (0, 3):                              # off = 3: tile columns not 16-byte aligned (no vector copies / TMA)
+        xs, ys = [], []
+        for k in range(300):
+            xs.append(off + 4 * ((k * 37) % 380))
+            ys.append((k * 53) % 1500)
+        x0 = torch.tensor(xs, dtype=torch.int32, device=DEV)
+        y0 = torch.tensor(ys, dtype=torch.int32, device=DEV)
+        _, big, _, st_big = ops.preprocess(cfg, img, mosaic.shape[1], False, x0, y0, 512, 512, 640, want_chain=False)
+        pick = [0, 1, 150, 299]
+        _, small, _, st_small = ops.preprocess(cfg, img, mosaic.shape[1], False, x0[pick].contiguous(),
+                                               y0[pick].contiguous(), 512, 512, 640, want_chain=False)
+        torch.cuda.synchronize()
+        assert (st_big[pick].cpu() == st_small.cpu()).all()
+        assert torch.equal(big[pick].view(torch.int16), small.view(torch.int16)), off
