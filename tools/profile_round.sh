@@ -27,7 +27,7 @@ for IDX in 2 26 87; do
     rm -f $O/${TAG}_conv_full_$IDX.ncu-rep      # gpurun brings back at most 64 MiB: keep the CSV exports only
 done
 # 4. --set full of the preprocessing kernels (first group of the bench command) and the stem
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pp_bucket_kernel|pp_chain_kernel|pp_fused_kernel' -c 3 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pp_bucket_kernel|pp_chain_kernel|pp_fused4_kernel' -c 3 \
     -f -o $O/${TAG}_pp_full $BENCH > $O/${TAG}_ncu_pp_full.log 2>&1
 ncu -i $O/${TAG}_pp_full.ncu-rep --page details --csv > $O/${TAG}_pp_full_details.csv 2>/dev/null
 ncu -i $O/${TAG}_pp_full.ncu-rep --page raw --csv > $O/${TAG}_pp_full_raw.csv 2>/dev/null
