@@ -555,9 +555,11 @@ def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, piece_bytes=
         src = _RowSource(engine, img_host, nx, rows_per_piece)
         state = {'row': Y0, 'events': []}                         # events[i] = (last_row_excl, event)
 
-        def upload_piece():
+        def upload_piece(y_stop):
             r0 = state['row']
             r1 = min(Y1, r0 + rows_per_piece)
+            if r0 < y_stop < r1:
+                r1 = y_stop                  # a piece ends where the waiting group's rows end: it waits for no other byte
             k = len(state['events'])
             rows, slot = src.get(k, r0, r1)
             with torch.cuda.stream(copy_stream):
@@ -572,7 +574,7 @@ def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, piece_bytes=
         def ready(y_needed):
             """Called before a tile group is launched: rows [Y0, y_needed) must be in HBM."""
             while state['row'] < min(y_needed, Y1):
-                upload_piece()
+                upload_piece(min(y_needed, Y1))
             for r1, ev in state['events']:
                 if r1 >= min(y_needed, Y1):
                     compute.wait_event(ev)
