@@ -324,8 +324,10 @@ int run_local(RunCtx* c, const RowSource& src, int ny, int nx, int big_endian) {
         cudaEventDestroy(ev0);
         int row = Y0, npieces = 0;
         std::vector<int> piece_end;
-        auto upload_piece = [&]() -> int {
-            const int r0 = row, r1 = std::min(Y1, r0 + rpp);
+        auto upload_piece = [&](int y_stop) -> int {
+            const int r0 = row;
+            int r1 = std::min(Y1, r0 + rpp);
+            if (r0 < y_stop && y_stop < r1) r1 = y_stop;   // a piece ends where the waiting group's rows end
             const size_t nb = (size_t)(r1 - r0) * row_bytes;
             const char* hsrc;
             if (src.host_pinned) {
@@ -363,7 +365,7 @@ int run_local(RunCtx* c, const RowSource& src, int ny, int nx, int big_endian) {
         auto ready = [&](int y_needed) -> int {     // rows [Y0, y_needed) must be in HBM before the group runs
             const int want = std::min(y_needed, Y1);
             while (row < want) {
-                int r = upload_piece();
+                int r = upload_piece(want);
                 if (r) return r;
             }
             for (int i = 0; i < npieces; ++i)

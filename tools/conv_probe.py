@@ -80,11 +80,13 @@ def main():
             check(lib.cy_conv_set_debug(ctypes.c_void_p(0), 0))
             t = buf.cpu().numpy().reshape(grid, U, 8)
             if a.epi:
-                nu0 = min((info[2] + grid - 1) // grid, U)
+                nu0 = min((info[2] + (grid // 2 if (info[0] % 100) >= 10 else grid) - 1) // (grid // 2 if (info[0] % 100) >= 10 else grid), U)
                 d = t[0, 1:nu0 - 1].astype(float)
                 print("   CTA0 epilogue warp 0, clk per unit: wait staging buffer %.0f | TMEM load %.0f | math + st.shared %.0f | fence + TMA store %.0f | acc wait %.0f | total %.0f"
                       % (d[:, 0].mean(), d[:, 1].mean(), d[:, 2].mean(), d[:, 3].mean(), (d[:, 6] - d[:, 5]).mean(), (d[:, 7] - d[:, 6]).mean()))
                 continue
+            if (info[0] % 100) >= 10:            # CTA pairs: one timeline per cluster (worker = blockIdx.x >> 1)
+                grid //= 2
             nu = [(info[2] - c + grid - 1) // grid for c in range(grid)]
             c = 0
             t0 = t[c, 0, 0]
