@@ -28,7 +28,7 @@ extern "C" int cy_conv_plan_info(int B, int Hin, int Win, int cin, int cout, int
     cy::ConvPlan plan;
     char err[256];
     if (cy::conv_make_plan(d, &plan, err, sizeof(err)) != 0) return cy::set_error(CY_ERR_INVALID, "%s", err);
-    info8[0] = plan.kp.mode + 10 * plan.kp.pair + 100 * plan.kp.b_resident; info8[1] = plan.kp.halves; info8[2] = plan.kp.n_units; info8[3] = plan.kp.block_n;
+    info8[0] = plan.kp.mode + 10 * plan.kp.pair; info8[1] = plan.kp.halves; info8[2] = plan.kp.n_units; info8[3] = plan.kp.block_n;
     info8[4] = plan.kp.a_stages; info8[5] = plan.kp.b_stages; info8[6] = plan.kp.acc_bufs; info8[7] = (int)plan.grid.x;
     return CY_OK;
 }

@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         uint32_t ph = 0;
         const int b_rows = p.block_n / kCtasPerUnit;   // weight rows this CTA stages per tile
         for (int u = worker; u < p.n_units; u += n_workers) {
-            if (p.b_resident && u != worker) break;    // resident weights: the slots were filled for the first unit
             const int n_tile = u % p.n_tiles_n;
             for (int ck = 0; ck < p.cchunks; ++ck) {
                 for (int al = 0; al < p.n_aloads; ++al) {
@@ -287,7 +286,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                     for (int t = 0; t < L.ntaps; ++t) {
                         const uint32_t a_off = p.tap[L.tap0 + t].a_off;
                         if (dbg) wait_b -= clock64();
-                        mbar_wait(&b_full[sb], p.b_resident ? 0u : phb);   // resident: phase 0 completed once, for good
+                        mbar_wait(&b_full[sb], phb);
                         if (dbg) wait_b += clock64();
                         tc_fence_after();
                         if (elect_one()) {
@@ -305,10 +304,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                                     else umma_bf16(td, da + 2u * k, db + 2u * k, idesc, accum | (uint32_t)k);
                                 }
                             }
-                            if (!p.b_resident) {
-                                if (PAIR) umma_commit_pair(&b_empty[sb]);
-                                else umma_commit(&b_empty[sb]);
-                            }
+                            if (PAIR) umma_commit_pair(&b_empty[sb]);
+                            else umma_commit(&b_empty[sb]);
                         }
                         __syncwarp();
                         accum = 1;
@@ -877,15 +874,7 @@ int conv_make_plan(const ConvDesc& d, ConvPlan* plan, char* err, size_t errlen) 
     } else {
         a_stages = mode == 3 ? 3 : 2;
         b_stages = (int)((budget - (size_t)a_stages * kp.a_stage_bytes) / kp.b_stage_bytes);
-        // Resident weights: a single N tile whose taps x channel chunks all fit next to the A ring is loaded once per
-        // CTA instead of once per unit (N = 64 layers at 160^2 / 80^2: 9 x 8 KB, or 9 x 4 KB per CTA of a pair) -- no
-        // weight traffic, no per-tap barrier round trips in the unit loop.  CY_CONV_BRES=0 disables it.
-        const int loads = kp.cchunks * ntaps;
-        if (kp.n_tiles_n == 1 && loads <= b_stages && loads <= 18 && env_int("CY_CONV_BRES", 1)) {
-            kp.b_resident = 1;
-            b_stages = loads;
-        }
-        if (b_stages > 12 && !kp.b_resident) b_stages = 12;
+        if (b_stages > 12) b_stages = 12;
     }
     if (a_stages < 1 || b_stages < 1) FAIL("shared-memory budget too small for one stage");
     (void)a_loads_per_unit;

@@ -85,8 +85,6 @@ struct ConvKParams {
     int mode;
     int f16;                       // storage format of in / w / res / bf16-sized out: 0 bf16, 1 fp16
     int pair;                      // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2), a unit = 2 x halves half tiles
-    int b_resident;                // 1: the whole weight tile (all taps x channel chunks) is loaded ONCE per CTA and stays
-                                   //    in its b_stages = taps * cchunks ring slots (single N tile, small K)
     unsigned long long* dbg;       // optional per-CTA timeline (clock64 stamps), 8 words per unit, see conv_probe
     int dbg_units;
     int dbg_epi;                   // timeline slots 0..3 = epilogue phase sums instead of the MMA stamps

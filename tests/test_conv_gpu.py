@@ -195,25 +195,3 @@ def test_stem_conv_matches_torch(B, H, W, cout, act):
     assert got.shape == y.shape
     err = (got - y).abs().max().item()
     assert err < 2e-2 * max(1.0, y.abs().max().item()), (err, y.abs().max().item())
-
-
-@pytest.mark.parametrize("res", [False, True])
-@pytest.mark.parametrize("pair", ["0", "2"])
-def test_conv_resident_weights(monkeypatch, res, pair):
-    """Single-N-tile 3x3 layers whose nine weight tiles fit next to the A ring keep them in shared memory for the whole
-    launch (b_resident): many units per CTA / CTA pair so the slots are re-read across units, with and without the
-    residual operand; CY_CONV_BRES=0 (streamed weights) must give the same result."""
-    from caesar_yolo_b200 import ops
-    import ctypes
-    monkeypatch.setenv("CY_CONV_PAIR", pair)
-    c = dict(B=12, H=160, W=160, cin=64, cout=64, k=3, s=1)
-    info = (ctypes.c_int * 8)()
-    ops.check(ops.lib.cy_conv_plan_info(c['B'], c['H'], c['W'], c['cin'], c['cout'], c['k'], c['s'], info))
-    assert info[0] % 10 == 2 and info[2] > 3 * info[7]      # 3x3 halo reuse, several units per CTA
-    if pair == "2":
-        assert info[0] >= 100 and info[5] == 9               # resident: one slot per tap
-    _run_case(act=True, res=res, out_f32=False, seed=71, **c)
-    monkeypatch.setenv("CY_CONV_BRES", "0")
-    ops.check(ops.lib.cy_conv_plan_info(c['B'], c['H'], c['W'], c['cin'], c['cout'], c['k'], c['s'], info))
-    assert info[0] < 100
-    _run_case(act=True, res=res, out_f32=False, seed=71, **c)
