@@ -452,6 +452,10 @@ static constexpr int kMergeWords = kMergeMaxN / 32;  // 10
 // One CTA (128 threads) per tile.  dets [B, det_stride, 6]; keeps detections with !(score < thr_score), links
 // pairs with iou >= hard or (same class and iou >= soft), connected components by recursive-DFS order, winner =
 // first member in DFS preorder with strictly greatest score (score_best starts at 0).
+// The three sequential parts of the reference (ordered score filter, DFS, ordered output) run on ONE WARP with the
+// 32 lanes working on a step together: ballot-scan compaction, and a DFS whose visited set lives in registers (lane w
+// owns word w of the bitmask) so that "next unvisited neighbour in ascending order" is one shared-memory load per lane +
+// one ballot instead of a 10-word scan through local memory by a single thread.
 __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict__ dets, const int* __restrict__ ndets,
                                                          int det_stride, float thr_score, float thr_soft,
                                                          float thr_hard, const int* __restrict__ pre_status,
@@ -462,8 +466,12 @@ __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict
     __shared__ int s_cls[kMergeMaxN];
     __shared__ int s_src[kMergeMaxN];
     __shared__ uint32_t s_adj[kMergeMaxN][kMergeWords];
-    __shared__ int s_N, s_bad;
+    __shared__ short s_stack[kMergeMaxN];
+    __shared__ int s_keep[kMergeMaxN];
+    __shared__ int s_N, s_bad, s_nk;
+    __shared__ float s_raw[kMergeMaxN * 6];
     const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (pre_status && pre_status[b] != 0) {  // tile rejected upstream (predict returned -1): no detections
         if (threadIdx.x == 0) {
             nkeep[b] = 0;
@@ -472,33 +480,44 @@ __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict
         return;
     }
     const int n_in = min(ndets[b], kMergeMaxN);
-    // the tile's detections are staged in shared memory first: the ordered compaction below is done by one thread, and
-    // reading its 6 x 300 values straight from global memory was ~300 dependent L2 round trips
-    __shared__ float s_raw[kMergeMaxN * 6];
     {
         const float* G = dets + (long long)b * det_stride * 6;
         for (int i = threadIdx.x; i < n_in * 6; i += blockDim.x) s_raw[i] = G[i];
     }
+    for (int i = threadIdx.x; i < kMergeMaxN * kMergeWords; i += blockDim.x) (&s_adj[0][0])[i] = 0u;
     __syncthreads();
     const float* D = s_raw;
-    if (threadIdx.x == 0) {
-        // score filter keeps order (evaluation.py:276-287); sequential compaction of <=300 entries
-        int n = 0, bad = 0;
-        for (int i = 0; i < n_in; ++i) {
-            const float sc = D[i * 6 + 4];
-            if (sc < thr_score) continue;
-            const float4 bx = make_float4(D[i * 6 + 0], D[i * 6 + 1], D[i * 6 + 2], D[i * 6 + 3]);
-            if (!(bx.x < bx.z) || !(bx.y < bx.w)) bad = 1;  // get_iou would assert (utils.py:78-81)
-            s_box[n] = bx;
-            s_score[n] = sc;
-            s_cls[n] = (int)D[i * 6 + 5];
-            s_src[n] = i;
-            ++n;
+    if (warp == 0) {
+        // score filter keeps order (evaluation.py:276-287): ballot scan, 32 entries per round
+        int n = 0;
+        bool bad = false;
+        for (int base = 0; base < n_in; base += 32) {
+            const int i = base + lane;
+            float sc = 0.f;
+            bool keep = false;
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_in) {
+                sc = D[i * 6 + 4];
+                keep = !(sc < thr_score);
+                bx = make_float4(D[i * 6 + 0], D[i * 6 + 1], D[i * 6 + 2], D[i * 6 + 3]);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = n + __popc(m & ((1u << lane) - 1u));
+                if (!(bx.x < bx.z) || !(bx.y < bx.w)) bad = true;  // get_iou would assert (utils.py:78-81)
+                s_box[pos] = bx;
+                s_score[pos] = sc;
+                s_cls[pos] = (int)D[i * 6 + 5];
+                s_src[pos] = i;
+            }
+            n += __popc(m);
         }
-        s_N = n;
-        s_bad = (bad && n >= 2) ? 1 : 0;
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            s_N = n;
+            s_bad = (bad && n >= 2) ? 1 : 0;
+        }
     }
-    for (int i = threadIdx.x; i < kMergeMaxN * kMergeWords; i += blockDim.x) (&s_adj[0][0])[i] = 0u;
     __syncthreads();
     const int N = s_N;
     int* ko = keep_idx + (long long)b * det_stride;
@@ -509,64 +528,78 @@ __global__ void __launch_bounds__(128) merge_tile_kernel(const float* __restrict
         }
         return;
     }
-    // adjacency: thread handles rows i = tid, tid+128, ...
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const float4 bi = s_box[i];
-        const int ci = s_cls[i];
-        for (int j = i + 1; j < N; ++j) {
-            const float iou = ref_get_iou(bi, s_box[j]);
-            if (iou >= thr_hard || (ci == s_cls[j] && iou >= thr_soft)) {
-                atomicOr(&s_adj[i][j >> 5], 1u << (j & 31));
-                atomicOr(&s_adj[j][i >> 5], 1u << (i & 31));
+    // adjacency: rows are handed out in pairs (r, N-1-r) so that every thread tests about the same number of pairs
+    for (int r = threadIdx.x; 2 * r < N; r += blockDim.x) {
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const int i = side == 0 ? r : N - 1 - r;
+            if (side == 1 && i == r) break;
+            const float4 bi = s_box[i];
+            const int ci = s_cls[i];
+            for (int j = i + 1; j < N; ++j) {
+                const float iou = ref_get_iou(bi, s_box[j]);
+                if (iou >= thr_hard || (ci == s_cls[j] && iou >= thr_soft)) {
+                    atomicOr(&s_adj[i][j >> 5], 1u << (j & 31));
+                    atomicOr(&s_adj[j][i >> 5], 1u << (i & 31));
+                }
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // iterative emulation of the recursive DFS (graph.py:9-23): adjacency ascending
-        uint32_t visited[kMergeWords];
-        for (int w = 0; w < kMergeWords; ++w) visited[w] = 0u;
-        short stack[kMergeMaxN];
+    if (warp == 0) {
+        // iterative emulation of the recursive DFS (graph.py:9-23), adjacency ascending; all lanes run the same control
+        // flow, lane w holds word w of the visited set
+        uint32_t vis = 0u;
         int nk = 0;
         for (int v = 0; v < N; ++v) {
-            if (visited[v >> 5] >> (v & 31) & 1u) continue;
+            const uint32_t vw = __shfl_sync(0xffffffffu, vis, v >> 5);
+            if ((vw >> (v & 31)) & 1u) continue;
             float sbest = 0.f;
             int best = -1;
             int sp = 0;
-            stack[sp++] = (short)v;
-            visited[v >> 5] |= 1u << (v & 31);
+            if (lane == 0) s_stack[0] = (short)v;
+            sp = 1;
+            if (lane == (v >> 5)) vis |= 1u << (v & 31);
             if (s_score[v] > sbest) {
                 sbest = s_score[v];
                 best = v;
             }
+            int u = v;                                  // top of the stack
             while (sp > 0) {
-                const int u = stack[sp - 1];
                 // next unvisited neighbour of u in ascending order
-                int nxt = -1;
-                for (int w = 0; w < kMergeWords; ++w) {
-                    const uint32_t m = s_adj[u][w] & ~visited[w];
-                    if (m) {
-                        nxt = w * 32 + __ffs(m) - 1;
-                        break;
-                    }
-                }
-                if (nxt < 0) {
+                const uint32_t m = lane < kMergeWords ? (s_adj[u][lane] & ~vis) : 0u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
+                if (bal == 0u) {
                     --sp;
+                    __syncwarp();
+                    if (sp > 0) u = s_stack[sp - 1];
                     continue;
                 }
-                visited[nxt >> 5] |= 1u << (nxt & 31);
-                if (s_score[nxt] > sbest) {  // preorder visit
-                    sbest = s_score[nxt];
+                const int wl = __ffs(bal) - 1;
+                const uint32_t mm = __shfl_sync(0xffffffffu, m, wl);
+                const int nxt = wl * 32 + __ffs(mm) - 1;
+                if (lane == wl) vis |= 1u << (nxt & 31);
+                const float sn = s_score[nxt];
+                if (sn > sbest) {  // preorder visit
+                    sbest = sn;
                     best = nxt;
                 }
-                stack[sp++] = (short)nxt;
+                if (lane == 0) s_stack[sp] = (short)nxt;
+                ++sp;
+                u = nxt;
             }
             // best == -1 only when every score in the component is <= 0; the reference then indexes [-1]
-            ko[nk++] = best >= 0 ? s_src[best] : s_src[N - 1];
+            if (lane == 0) s_keep[nk] = best >= 0 ? s_src[best] : s_src[N - 1];
+            ++nk;
         }
-        nkeep[b] = nk;
-        status[b] = 0;
+        if (lane == 0) {
+            s_nk = nk;
+            nkeep[b] = nk;
+            status[b] = 0;
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s_nk; i += blockDim.x) ko[i] = s_keep[i];
 }
 
 // ------------------------------------------------------------------------------------------ host launchers
