@@ -125,6 +125,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // Programmatic dependent launch: all CTAs of a conv grid are resident at once (one per SM), so the next conv of the
+    // stream may be scheduled onto an SM as soon as this grid's CTA there has exited; it runs its prologue (barrier
+    // init, TMEM allocation, descriptor prefetch, first weight tiles) during this grid's tail and blocks in
+    // grid_dep_wait() below until this grid has completed.
+    grid_dep_launch_dependents();
     const uint32_t row_bytes = p.kc * 2;
     const int a_stages = p.a_stages, b_stages = p.b_stages;
     // PAIR: two CTAs of a cluster (one TPC) work on one unit with tcgen05 cta_group::2: every MMA covers 128 rows
@@ -181,6 +186,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr int halves = HALVES;
+    // everything that reads activations / residuals or writes the output waits for the preceding grid; the weight
+    // producer (warp 2) only reads the static weights and starts filling its ring right away
+    if (warp != 2) grid_dep_wait();
 
     // The three single-issuer roles below run their loops with the WHOLE warp (all control flow warp-uniform) and
     // gate only the issuing instructions with elect.sync: the compiler then keeps descriptors / coordinates in uniform
@@ -553,13 +561,16 @@ static int launch_t(const ConvPlan& pl, cudaStream_t st) {
     cfg.blockDim = dim3(kConvThreads, 1, 1);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const int pdl = env_int("CY_CONV_PDL", 1);      // 0: plain stream order between conv launches
+    cfg.numAttrs = pdl ? 2 : 1;
     return (int)cudaLaunchKernelEx(&cfg, kern, kp);
 }
 
