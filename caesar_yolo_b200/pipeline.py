@@ -227,7 +227,8 @@ class Engine(object):
 
     def pp_kernels(self):
         """Names of the preprocessing kernels cy_preprocess launches for this configuration (bench.py's roofline)."""
-        return "pp_bucket_kernel + pp_chain_kernel + pp_geom_kernel + pp_fused_kernel"
+        return ("pp_bucket_kernel + pp_chain_kernel + pp_geom_kernel + pp_fused4_kernel (pp_fused_kernel for tiles whose "
+                "interleaved planes do not fit shared memory)")
 
     def finish(self):
         """Compacts the per-tile record slots -> (packed uint8 tensor of n cy_det_record, n) in tile-id order.
