@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int lane = threadIdx.x & 31;
     // Programmatic dependent launch: all CTAs of a conv grid are resident at once (one per SM), so the next conv of the
     // stream may be scheduled onto an SM as soon as this grid's CTA there has exited; it runs its prologue (barrier
-    // init, TMEM allocation, descriptor prefetch, first weight tiles) during this grid's tail and blocks in
+    // init, TMEM allocation, descriptor prefetch) during this grid's tail and blocks in
     // grid_dep_wait() below until this grid has completed.
     grid_dep_launch_dependents();
     const uint32_t row_bytes = p.kc * 2;
@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr int halves = HALVES;
-    // everything that reads activations / residuals or writes the output waits for the preceding grid; the weight
-    // producer (warp 2) only reads the static weights and starts filling its ring right away
-    if (warp != 2) grid_dep_wait();
+    // everything past the prologue waits for the preceding grid (weights included: the parity entry cy_conv2d_nhwc may
+    // be handed weights that a kernel just before it on the stream produced)
+    grid_dep_wait();
 
     // The three single-issuer roles below run their loops with the WHOLE warp (all control flow warp-uniform) and
     // gate only the issuing instructions with elect.sync: the compiler then keeps descriptors / coordinates in uniform
