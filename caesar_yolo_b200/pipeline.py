@@ -150,7 +150,7 @@ class Engine(object):
             if min_groups > 1:
                 # host-staged input: a small LEADING group (whole tile rows, >= 32 tiles) starts computing as soon as
                 # its rows are in HBM; the upload of everything else overlaps it
-                lead = lead_group_size(self.tiles['ymin'][ids])
+                lead = lead_group_size(self.tiles['ymin'][ids], LEAD_TILES)
                 if 0 < lead and 2 * lead <= len(ids):
                     starts = [0] + list(range(lead, len(ids), self.pp_tiles))
             for k, s in enumerate(starts):
@@ -329,6 +329,9 @@ class Engine(object):
         want = min(want, self.T * ops.MAX_DET)
         self._buf['xcap'] = want
         return want
+
+
+LEAD_TILES = int(os.environ.get('CY_LEAD_TILES', '32'))   # smallest leading group of a host-staged run (tuning knob)
 
 
 def lead_group_size(ymins, min_tiles=32):
