@@ -331,6 +331,16 @@ class Engine(object):
         return want
 
 
+def piece_end(r0, y_end, rows_per_piece, y_stop):
+    """Last row (exclusive) of the upload piece that starts at row r0: at most rows_per_piece rows, never past the band
+    end y_end, and cut at y_stop — the last row the tile group waiting for this upload reads — when that falls inside
+    the piece, so that the group waits for no byte it does not need."""
+    r1 = min(y_end, r0 + rows_per_piece)
+    if r0 < y_stop < r1:
+        r1 = y_stop
+    return r1
+
+
 LEAD_TILES = int(os.environ.get('CY_LEAD_TILES', '32'))   # smallest leading group of a host-staged run (tuning knob)
 
 
@@ -561,9 +571,7 @@ def run_image(engine, img_host, big_endian, tiles, rank=0, world=1, piece_bytes=
 
         def upload_piece(y_stop):
             r0 = state['row']
-            r1 = min(Y1, r0 + rows_per_piece)
-            if r0 < y_stop < r1:
-                r1 = y_stop                  # a piece ends where the waiting group's rows end: it waits for no other byte
+            r1 = piece_end(r0, Y1, rows_per_piece, y_stop)
             k = len(state['events'])
             rows, slot = src.get(k, r0, r1)
             with torch.cuda.stream(copy_stream):

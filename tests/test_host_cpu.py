@@ -210,3 +210,32 @@ def test_numa_binding_is_a_no_op_without_topology():
     before = os.sched_getaffinity(0)
     assert pipeline.bind_host_to_device_numa(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_upload_pieces_partition_the_band_and_stop_at_group_rows():
+    """Host-staged runs (pipeline.run_image / cy_run_mosaic) upload a rank's band in pieces; a piece is cut at the last
+    row the waiting tile group reads.  Replays the `ready(y)` protocol on the piece arithmetic alone: the pieces partition
+    the band in order, none is longer than rows_per_piece, and after ready(y) the uploaded prefix ends exactly at y when y
+    lies inside the band (so the leading group of a run waits for its own rows only)."""
+    from caesar_yolo_b200.pipeline import piece_end, lead_group_size
+    for Y0, Y1, rpp, stops in [(0, 16384, 1024, [512, 5632, 10752, 15872, 16384]),     # 16k mosaic, lead row + 296-tile groups
+                               (2048, 4096, 1024, [2560, 4096]),                       # a rank's band at N = 8
+                               (0, 700, 1024, [512, 700]),                             # band shorter than a piece
+                               (0, 3000, 1000, [1000, 2000, 3000]),                    # stops on piece boundaries
+                               (5, 2053, 300, [517, 2053])]:
+        row, pieces = Y0, []
+        for y in stops:
+            want = min(y, Y1)
+            while row < want:
+                r1 = piece_end(row, Y1, rpp, want)
+                assert row < r1 <= min(Y1, row + rpp)
+                pieces.append((row, r1))
+                row = r1
+            assert row == want                                           # the prefix ends at the group's last row
+        assert pieces[0][0] == Y0 and pieces[-1][1] == Y1
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    # leading group: the first whole tile rows holding >= 32 tiles
+    ym = np.repeat(np.arange(0, 16384, 512), 32)
+    assert lead_group_size(ym) == 32 and lead_group_size(ym, 64) == 64 and lead_group_size(ym[:16]) == 0
+    ym2 = np.repeat(np.arange(0, 2048, 512), 5)
+    assert lead_group_size(ym2, 8) == 10
